@@ -1,0 +1,9 @@
+"""gfnerf_b200 -- B200-native (sm_100a) implementation of GF-NeRF's per-ray hot path.
+
+The directory is named `gf-nerf_b200`; import it as `gfnerf_b200` (the repo-root shim
+package of that name points its __path__ here).
+"""
+from . import _lib  # noqa: F401
+from .hash_3d_anchored import Hash3DAnchored, Hash3DAnchoredCore  # noqa: F401
+
+__version__ = "0.1.0"

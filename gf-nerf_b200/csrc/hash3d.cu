@@ -1,0 +1,420 @@
+// Hash3DAnchored encode: forward gather and backward scatter for sm_100a.
+//
+// Replaces Hash3DAnchoredForwardKernel / Hash3DAnchoredBackwardKernel and the
+// host glue of Hash3DAnchoredFunction (reference gfnerf/bindings/field/
+// Hash3DAnchored_cuda.cu:11-79, 81-155, 160-239).
+//
+// Design (DESIGN.md "hash encode"):
+//  * one thread per sample walks all 16 levels, so the point, its anchor and the
+//    per-(level,volume) primes are read once instead of 16x, and the 32 outputs
+//    leave as four 16-byte stores of the fp16 values the reference computes anyway;
+//  * lanes of a warp hold CONSECUTIVE samples of one ray (the sampler's compact
+//    layout), so on coarse levels the 32 lanes of a gather hit the same few
+//    32-byte sectors and the LSU coalesces them;
+//  * the table is an fp16 shadow that is only re-cast when feat_pool changes,
+//    not on every forward as the reference does (:185);
+//  * backward: lanes that fall into the same grid cell (contiguous runs along the
+//    ray) are summed with a segmented shuffle reduction and ONE lane issues the
+//    8 vectorised fp32 reductions (red.global.add.v2.f32) for the run.
+//
+// Arithmetic follows the oracle's FMA convention exactly (oracle/gf_oracle.c).
+#include "common.cuh"
+
+namespace gf {
+
+template <bool POW2>
+__device__ __forceinline__ uint32_t wrap(uint32_t h, uint32_t local_size) {
+  if (POW2) return h & (local_size - 1u);
+  return h % local_size;
+}
+
+struct Cell {
+  uint32_t px, py, pz;
+  float a, b, c;
+};
+
+// :26-46  pt*mul + bias, floor, fractional part.
+__device__ __forceinline__ Cell cell_of(float x, float y, float z, float mul, const float* __restrict__ bias) {
+  float p0 = __fmaf_rn(x, mul, __ldg(bias + 0));
+  float p1 = __fmaf_rn(y, mul, __ldg(bias + 1));
+  float p2 = __fmaf_rn(z, mul, __ldg(bias + 2));
+  float f0 = floorf(p0), f1 = floorf(p1), f2 = floorf(p2);
+  Cell c;
+  c.px = __float2uint_rz(f0);  // saturating, negative/NaN -> 0
+  c.py = __float2uint_rz(f1);
+  c.pz = __float2uint_rz(f2);
+  c.a = __fsub_rn(p0, f0);
+  c.b = __fsub_rn(p1, f1);
+  c.c = __fsub_rn(p2, f2);
+  return c;
+}
+
+// :48-55 corner rows, order 000,001,010,011,100,101,110,111 (bits x,y,z)
+template <bool POW2>
+__device__ __forceinline__ void corners(const Cell& c, uint32_t pa, uint32_t pb, uint32_t pc, uint32_t local_size,
+                                        uint32_t (&pos)[8]) {
+  uint32_t x0 = c.px * pa, x1 = (c.px + 1u) * pa;
+  uint32_t y0 = c.py * pb, y1 = (c.py + 1u) * pb;
+  uint32_t z0 = c.pz * pc, z1 = (c.pz + 1u) * pc;
+  pos[0] = wrap<POW2>(x0 ^ y0 ^ z0, local_size);
+  pos[1] = wrap<POW2>(x0 ^ y0 ^ z1, local_size);
+  pos[2] = wrap<POW2>(x0 ^ y1 ^ z0, local_size);
+  pos[3] = wrap<POW2>(x0 ^ y1 ^ z1, local_size);
+  pos[4] = wrap<POW2>(x1 ^ y0 ^ z0, local_size);
+  pos[5] = wrap<POW2>(x1 ^ y0 ^ z1, local_size);
+  pos[6] = wrap<POW2>(x1 ^ y1 ^ z0, local_size);
+  pos[7] = wrap<POW2>(x1 ^ y1 ^ z1, local_size);
+}
+
+// :58-69 trilinear weights, products left to right
+__device__ __forceinline__ void weights(const Cell& c, float (&w)[8]) {
+  float ia = __fsub_rn(1.f, c.a), ib = __fsub_rn(1.f, c.b), ic = __fsub_rn(1.f, c.c);
+  float iaib = __fmul_rn(ia, ib), iab = __fmul_rn(ia, c.b), aib = __fmul_rn(c.a, ib), ab = __fmul_rn(c.a, c.b);
+  w[0] = __fmul_rn(iaib, ic);
+  w[1] = __fmul_rn(iaib, c.c);
+  w[2] = __fmul_rn(iab, ic);
+  w[3] = __fmul_rn(iab, c.c);
+  w[4] = __fmul_rn(aib, ic);
+  w[5] = __fmul_rn(aib, c.c);
+  w[6] = __fmul_rn(ab, ic);
+  w[7] = __fmul_rn(ab, c.c);
+}
+
+__global__ void level_scales_kernel(float* out) {
+  int l = threadIdx.x;
+  if (l < GF_N_LEVELS)  // the reference's expression, evaluated by the device's exp2f (:28)
+    out[l] = exp2f((10.f - 3.f) * float(l) / float(GF_N_LEVELS - 1) + 3.f);
+}
+
+__global__ void cast_table_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int64_t n4) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = __ldg(in + i);
+    __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    out[i] = o;
+  }
+}
+
+__global__ void cast_table_tail_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t from, int64_t n) {
+  int64_t i = from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+
+constexpr int kHashBlock = 256;
+
+template <bool POW2, typename AnchorT, bool OUT16, bool OUT32>
+__global__ void __launch_bounds__(kHashBlock)
+hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volumes, uint32_t local_size,
+                const __half2* __restrict__ feat, const int32_t* __restrict__ prim_pool,
+                const float* __restrict__ bias_pool, const float* __restrict__ scales,
+                const float* __restrict__ pts, const AnchorT* __restrict__ anchors,
+                uint4* __restrict__ out16, float4* __restrict__ out32) {
+  if (d_n_ptr) {
+    int64_t dn = *d_n_ptr;
+    n = dn < n ? dn : n;
+  }
+  __shared__ float s_scale[GF_N_LEVELS];
+  if (threadIdx.x < GF_N_LEVELS) s_scale[threadIdx.x] = __ldg(scales + threadIdx.x);
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+    const int64_t vol = (int64_t)anchors[i];
+#pragma unroll 1
+    for (int q = 0; q < GF_N_LEVELS / 4; q++) {
+      uint32_t packed[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int l = 4 * q + j;
+        const int64_t tr = ((int64_t)l * n_volumes + vol) * 3;
+        const Cell c = cell_of(x, y, z, s_scale[l], bias_pool + tr);
+        const uint32_t pa = (uint32_t)__ldg(prim_pool + tr), pb = (uint32_t)__ldg(prim_pool + tr + 1),
+                       pc = (uint32_t)__ldg(prim_pool + tr + 2);
+        uint32_t pos[8];
+        corners<POW2>(c, pa, pb, pc, local_size, pos);
+        const __half2* tab = feat + (int64_t)l * local_size;
+        __half2 f[8];
+#pragma unroll
+        for (int d = 0; d < 8; d++) f[d] = __ldg(tab + pos[d]);
+        float w[8];
+        weights(c, w);
+        // nvcc's contraction of w000*f000 + w001*f001 + ... (:73-77)
+        float t0 = __fmul_rn(w[1], __low2float(f[1]));
+        float t1 = __fmul_rn(w[1], __high2float(f[1]));
+        t0 = __fmaf_rn(w[0], __low2float(f[0]), t0);
+        t1 = __fmaf_rn(w[0], __high2float(f[0]), t1);
+#pragma unroll
+        for (int d = 2; d < 8; d++) {
+          t0 = __fmaf_rn(w[d], __low2float(f[d]), t0);
+          t1 = __fmaf_rn(w[d], __high2float(f[d]), t1);
+        }
+        __half2 o = __floats2half2_rn(t0, t1);
+        packed[j] = *reinterpret_cast<uint32_t*>(&o);
+      }
+      if (OUT16) out16[i * 4 + q] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      if (OUT32) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          __half2 h0 = *reinterpret_cast<__half2*>(&packed[2 * h]);
+          __half2 h1 = *reinterpret_cast<__half2*>(&packed[2 * h + 1]);
+          out32[i * 8 + 2 * q + h] = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+        }
+      }
+    }
+  }
+}
+
+// fp16 round trip of a product, :148-151  (__half)(w0 * ws[d])
+__device__ __forceinline__ float q16(float v) { return __half2float(__float2half_rn(v)); }
+
+template <bool POW2, typename AnchorT, bool GRAD_F16>
+__global__ void __launch_bounds__(kHashBlock)
+hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volumes, uint32_t local_size,
+                const int32_t* __restrict__ prim_pool, const float* __restrict__ bias_pool,
+                const float* __restrict__ scales, const float* __restrict__ pts,
+                const AnchorT* __restrict__ anchors, const void* __restrict__ grad_in_v,
+                float* __restrict__ grad_table, int aggregate) {
+  if (d_n_ptr) {
+    int64_t dn = *d_n_ptr;
+    n = dn < n ? dn : n;
+  }
+  __shared__ float s_scale[GF_N_LEVELS];
+  if (threadIdx.x < GF_N_LEVELS) s_scale[threadIdx.x] = __ldg(scales + threadIdx.x);
+  __syncthreads();
+  const int lane = lane_id();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // warp-uniform trip count: every lane of a warp runs the same iterations
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
+    const int64_t i = base + lane;
+    const bool valid = i < n;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int64_t vol = 0;
+    if (valid) {
+      x = __ldg(pts + 3 * i);
+      y = __ldg(pts + 3 * i + 1);
+      z = __ldg(pts + 3 * i + 2);
+      vol = (int64_t)anchors[i];
+    }
+#pragma unroll 2
+    for (int l = 0; l < GF_N_LEVELS; l++) {
+      const int64_t tr = ((int64_t)l * n_volumes + vol) * 3;
+      const Cell c = cell_of(x, y, z, s_scale[l], bias_pool + tr);
+      const uint32_t pa = (uint32_t)__ldg(prim_pool + tr), pb = (uint32_t)__ldg(prim_pool + tr + 1),
+                     pc = (uint32_t)__ldg(prim_pool + tr + 2);
+      uint32_t pos[8];
+      corners<POW2>(c, pa, pb, pc, local_size, pos);
+      float w[8];
+      weights(c, w);
+      // this level's two gradients, quantised like the reference: fp16(g*128)  (:209)
+      float g0 = 0.f, g1 = 0.f;
+      if (valid) {
+        __half2 gh;
+        if (GRAD_F16) {
+          gh = __ldg(reinterpret_cast<const __half2*>(grad_in_v) + i * GF_N_LEVELS + l);
+        } else {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(grad_in_v) + i * GF_N_LEVELS + l);
+          gh = __floats2half2_rn(__fmul_rn(v.x, GF_GRAD_SCALE), __fmul_rn(v.y, GF_GRAD_SCALE));
+        }
+        g0 = __low2float(gh);
+        g1 = __high2float(gh);
+      }
+      float c0[8], c1[8];
+#pragma unroll
+      for (int d = 0; d < 8; d++) {
+        c0[d] = q16(__fmul_rn(g0, w[d]));
+        c1[d] = q16(__fmul_rn(g1, w[d]));
+      }
+      bool writer = valid && (g0 != 0.f || g1 != 0.f);  // :147 skip when both are zero
+      if (aggregate) {
+        // runs of lanes in the same cell of the same volume -> one reduction per run
+        const uint32_t ppx = __shfl_up_sync(0xffffffffu, c.px, 1), ppy = __shfl_up_sync(0xffffffffu, c.py, 1),
+                       ppz = __shfl_up_sync(0xffffffffu, c.pz, 1);
+        const int64_t pvol = __shfl_up_sync(0xffffffffu, vol, 1);
+        const bool head = lane == 0 || ppx != c.px || ppy != c.py || ppz != c.pz || pvol != vol;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        if (__popc(heads) <= 24) {  // warp-uniform: worth reducing
+          const uint32_t above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
+          const int end = above ? (__ffs(above) - 1) : 32;
+          if (!valid) {
+#pragma unroll
+            for (int d = 0; d < 8; d++) c0[d] = c1[d] = 0.f;
+          }
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const bool take = lane + off < end;
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+              float o0 = __shfl_down_sync(0xffffffffu, c0[d], off);
+              float o1 = __shfl_down_sync(0xffffffffu, c1[d], off);
+              if (take) {
+                c0[d] += o0;
+                c1[d] += o1;
+              }
+            }
+          }
+          writer = head && valid;
+        }
+      }
+      if (writer) {
+        float2* tab = reinterpret_cast<float2*>(grad_table) + (int64_t)l * local_size;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+          const float s0 = c0[d] * (1.f / GF_GRAD_SCALE), s1 = c1[d] * (1.f / GF_GRAD_SCALE);
+          if (s0 != 0.f || s1 != 0.f) atomicAdd(tab + pos[d], make_float2(s0, s1));
+        }
+      }
+    }
+  }
+}
+
+// table row of every corner, int32 [n,16,8] -- the parity probe for "bit-exact hash indices"
+template <bool POW2, typename AnchorT>
+__global__ void __launch_bounds__(kHashBlock)
+hash_rows_kernel(int64_t n, int32_t n_volumes, uint32_t local_size, const int32_t* __restrict__ prim_pool,
+                 const float* __restrict__ bias_pool, const float* __restrict__ scales,
+                 const float* __restrict__ pts, const AnchorT* __restrict__ anchors, int32_t* __restrict__ rows) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+    const int64_t vol = (int64_t)anchors[i];
+    for (int l = 0; l < GF_N_LEVELS; l++) {
+      const int64_t tr = ((int64_t)l * n_volumes + vol) * 3;
+      const Cell c = cell_of(x, y, z, __ldg(scales + l), bias_pool + tr);
+      uint32_t pos[8];
+      corners<POW2>(c, (uint32_t)__ldg(prim_pool + tr), (uint32_t)__ldg(prim_pool + tr + 1),
+                    (uint32_t)__ldg(prim_pool + tr + 2), local_size, pos);
+#pragma unroll
+      for (int d = 0; d < 8; d++) rows[(i * GF_N_LEVELS + l) * 8 + d] = (int32_t)((int64_t)l * local_size + pos[d]);
+    }
+  }
+}
+
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace gf
+
+using namespace gf;
+
+extern "C" {
+
+int gf_hash_level_scales(float* d_scales16, float* h_copy16, void* stream) {
+  GF_REQUIRE(d_scales16 != nullptr, "gf_hash_level_scales: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  level_scales_kernel<<<1, 32, 0, st>>>(d_scales16);
+  int rc = check_launch("level_scales_kernel");
+  if (rc) return rc;
+  if (h_copy16) {
+    GF_CUDA(cudaMemcpyAsync(h_copy16, d_scales16, sizeof(float) * GF_N_LEVELS, cudaMemcpyDeviceToHost, st));
+    GF_CUDA(cudaStreamSynchronize(st));
+  }
+  return GF_OK;
+}
+
+int gf_hash_cast_table(const float* feat_f32, void* feat_f16, int64_t n_elems, void* stream) {
+  GF_REQUIRE(feat_f32 && feat_f16 && n_elems >= 0, "gf_hash_cast_table: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t n4 = n_elems / 4;
+  if (n4 > 0) {
+    cast_table_kernel<<<stride_grid(n4, 256, 8, 4), 256, 0, st>>>((const float4*)feat_f32, (uint2*)feat_f16, n4);
+    int rc = check_launch("cast_table_kernel");
+    if (rc) return rc;
+  }
+  if (n4 * 4 < n_elems) {
+    cast_table_tail_kernel<<<1, 32, 0, st>>>(feat_f32, (__half*)feat_f16, n4 * 4, n_elems);
+    return check_launch("cast_table_tail_kernel");
+  }
+  return GF_OK;
+}
+
+int gf_hash_forward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                    const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
+                    const float* level_scales, const float* pts, const void* anchors, int anchor_i64,
+                    void* out_f16, float* out_f32, void* stream) {
+  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL,
+             "gf_hash_forward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
+             (long long)local_size);
+  GF_REQUIRE(out_f16 || out_f32, "gf_hash_forward: no output buffer");
+  if (n == 0) return GF_OK;
+  GF_REQUIRE(feat_f16 && prim_pool && bias_pool && level_scales && pts && anchors, "gf_hash_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stride_grid(n, kHashBlock, 8, 4);
+  const bool p2 = is_pow2(local_size);
+#define GF_FWD(P2, AT, O16, O32)                                                                              \
+  hash_fwd_kernel<P2, AT, O16, O32><<<grid, kHashBlock, 0, st>>>(                                             \
+      n, d_n_ptr, n_volumes, (uint32_t)local_size, (const __half2*)feat_f16, prim_pool, bias_pool,            \
+      level_scales, pts, (const AT*)anchors, (uint4*)out_f16, (float4*)out_f32)
+#define GF_FWD_O(P2, AT)                                     \
+  do {                                                       \
+    if (out_f16 && out_f32) GF_FWD(P2, AT, true, true);      \
+    else if (out_f16) GF_FWD(P2, AT, true, false);           \
+    else GF_FWD(P2, AT, false, true);                        \
+  } while (0)
+  if (p2) {
+    if (anchor_i64) GF_FWD_O(true, int64_t); else GF_FWD_O(true, int32_t);
+  } else {
+    if (anchor_i64) GF_FWD_O(false, int64_t); else GF_FWD_O(false, int32_t);
+  }
+#undef GF_FWD_O
+#undef GF_FWD
+  return check_launch("hash_fwd_kernel");
+}
+
+int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                     const int32_t* prim_pool, const float* bias_pool, const float* level_scales,
+                     const float* pts, const void* anchors, int anchor_i64, const void* grad_in,
+                     int grad_in_is_scaled_f16, float* grad_table, void* stream) {
+  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL,
+             "gf_hash_backward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
+             (long long)local_size);
+  if (n == 0) return GF_OK;
+  GF_REQUIRE(prim_pool && bias_pool && level_scales && pts && anchors && grad_in && grad_table,
+             "gf_hash_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stride_grid(n, kHashBlock, 4, 4);
+  const bool p2 = is_pow2(local_size);
+  const int aggregate = 1;
+#define GF_BWD(P2, AT, G16)                                                                               \
+  hash_bwd_kernel<P2, AT, G16><<<grid, kHashBlock, 0, st>>>(n, d_n_ptr, n_volumes, (uint32_t)local_size,  \
+                                                            prim_pool, bias_pool, level_scales, pts,      \
+                                                            (const AT*)anchors, grad_in, grad_table, aggregate)
+#define GF_BWD_G(P2, AT)                                    \
+  do {                                                      \
+    if (grad_in_is_scaled_f16) GF_BWD(P2, AT, true);        \
+    else GF_BWD(P2, AT, false);                             \
+  } while (0)
+  if (p2) {
+    if (anchor_i64) GF_BWD_G(true, int64_t); else GF_BWD_G(true, int32_t);
+  } else {
+    if (anchor_i64) GF_BWD_G(false, int64_t); else GF_BWD_G(false, int32_t);
+  }
+#undef GF_BWD_G
+#undef GF_BWD
+  return check_launch("hash_bwd_kernel");
+}
+
+int gf_hash_corner_rows(int64_t n, int32_t n_volumes, int64_t local_size, const int32_t* prim_pool,
+                        const float* bias_pool, const float* level_scales, const float* pts,
+                        const void* anchors, int anchor_i64, int32_t* rows, void* stream) {
+  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size * GF_N_LEVELS <= 0x7fffffffLL,
+             "gf_hash_corner_rows: bad sizes");
+  if (n == 0) return GF_OK;
+  GF_REQUIRE(prim_pool && bias_pool && level_scales && pts && anchors && rows, "gf_hash_corner_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stride_grid(n, kHashBlock, 8, 4);
+  const bool p2 = is_pow2(local_size);
+#define GF_ROWS(P2, AT)                                                                                    \
+  hash_rows_kernel<P2, AT><<<grid, kHashBlock, 0, st>>>(n, n_volumes, (uint32_t)local_size, prim_pool,     \
+                                                        bias_pool, level_scales, pts, (const AT*)anchors, rows)
+  if (p2) {
+    if (anchor_i64) GF_ROWS(true, int64_t); else GF_ROWS(true, int32_t);
+  } else {
+    if (anchor_i64) GF_ROWS(false, int64_t); else GF_ROWS(false, int32_t);
+  }
+#undef GF_ROWS
+  return check_launch("hash_rows_kernel");
+}
+
+}  // extern "C"

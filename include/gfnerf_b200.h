@@ -1,0 +1,236 @@
+/*
+ * gfnerf_b200.h -- C-ABI of the B200-native GF-NeRF per-ray hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (device
+ * pointers unless the parameter name starts with `h_`), takes the CUDA stream
+ * as an opaque `void*` (a `cudaStream_t`; NULL = legacy default stream) and
+ * returns 0 on success or a negative gf_status.  After a failure
+ * `gf_last_error()` returns a thread-local, NUL-terminated description.
+ * Nothing here includes torch or CUDA headers, so the reference's binding
+ * layer (TORCH_LIBRARY custom classes) or any other FFI
+ * (ctypes, cgo, JNI) can bind it directly.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the
+ * reference checkout, gfnerf/bindings/...).
+ */
+#ifndef GFNERF_B200_H
+#define GFNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_N_LEVELS 16          /* field/Hash3DAnchored.h:18 N_LEVELS   */
+#define GF_N_CHANNELS 2         /* field/Hash3DAnchored.h:17 N_CHANNELS */
+#define GF_HASH_DIM 32          /* N_LEVELS * N_CHANNELS                */
+#define GF_MAX_SAMPLE_PER_RAY 1024   /* PtsSampler/PersSampler_cuda.cu:9  */
+#define GF_MAX_OCT_PER_RAY 1024      /* PtsSampler/PersSampler_cuda.cu:8  */
+#define GF_TREE_NODE_BYTES 128  /* sizeof(TreeNode),  PtsSampler/PersSampler.h:40-49 */
+#define GF_TRANS_INFO_BYTES 576 /* sizeof(TransInfo), PtsSampler/PersSampler.h:31-38 */
+#define GF_N_PROS 12            /* PtsSampler/PersSampler.h:15 */
+#define GF_GRAD_SCALE 128.0f    /* field/Hash3DAnchored_cuda.cu:209 grad_scale */
+
+typedef enum {
+  GF_OK = 0,
+  GF_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, unsupported width) */
+  GF_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed; see gf_last_error()      */
+  GF_ERR_UNSUPPORTED = -3
+} gf_status;
+
+/* ---- library ---------------------------------------------------------- */
+const char* gf_last_error(void);
+/* "gfnerf_b200 <semver> sm_100a" */
+const char* gf_version(void);
+/* number of kernel launches issued by this library in this process (all threads) */
+int64_t gf_launch_count(void);
+
+/* ---- Hash3DAnchored ---------------------------------------------------
+ * Replaces Hash3DAnchoredForwardKernel / Hash3DAnchoredBackwardKernel and the
+ * host glue Hash3DAnchoredFunction::{forward,backward}
+ * (field/Hash3DAnchored_cuda.cu:11-79, 81-155, 160-239).
+ *
+ * Layouts (all row-major, contiguous):
+ *   feat_f16   __half [n_levels*local_size, 2]   fp16 shadow of feat_pool
+ *   prim_pool  int32  [16, n_volumes, 3]
+ *   bias_pool  float  [16*n_volumes, 3]
+ *   pts        float  [n, 3]   (already (warp+1.5)/3, nerfacto_field.py:431)
+ *   anchors    int64 [n] (anchor_i64=1, the reference dtype) or int32 [n]
+ *   level_scales float[16] device table, see gf_hash_level_scales
+ *   n may also come from device memory: if d_n_ptr != NULL the kernels use
+ *   min(n, *d_n_ptr) points, so a producer on the same stream can hand over a
+ *   data-dependent count without a host sync.
+ */
+
+/* Fills a device table with s_l = exp2f(7*l/15 + 3) evaluated ON THE DEVICE with
+ * the reference's expression (Hash3DAnchored_cuda.cu:28).  h_copy (16 floats,
+ * host, optional) receives the same values after a stream sync. */
+int gf_hash_level_scales(float* d_scales16, float* h_copy16, void* stream);
+
+/* feat_pool fp32 -> fp16 shadow (Hash3DAnchored_cuda.cu:185 `.to(kFloat16)`) */
+int gf_hash_cast_table(const float* feat_f32, void* feat_f16, int64_t n_elems, void* stream);
+
+/* out_f16: __half [n,32] (may be NULL), out_f32: float [n,32] (may be NULL);
+ * both hold the fp16-rounded value the reference returns (:73-77,195). */
+int gf_hash_forward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                    const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
+                    const float* level_scales,
+                    const float* pts, const void* anchors, int anchor_i64,
+                    void* out_f16, float* out_f32, void* stream);
+
+/* grad_in: fp32 [n,32] dL/dout (unscaled; grad_in_is_scaled_f16=0) -- the kernel
+ * applies the reference's x128 -> fp16 quantisation (:209) -- or __half [n,32]
+ * already scaled by 128 (grad_in_is_scaled_f16=1, produced by gf_mlp_backward).
+ * grad_table: float [n_levels*local_size, 2]; ACCUMULATED into (caller zeroes it),
+ * in units of dL/dfeat (the /128 of :238 is applied per contribution). */
+int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                     const int32_t* prim_pool, const float* bias_pool, const float* level_scales,
+                     const float* pts, const void* anchors, int anchor_i64,
+                     const void* grad_in, int grad_in_is_scaled_f16,
+                     float* grad_table, void* stream);
+
+/* Parity probe: rows int32 [n,16,8] = table row (level offset included) of the 8 corners of
+ * every (point, level), order 000,001,...,111 (:48-55).  Not on the hot path. */
+int gf_hash_corner_rows(int64_t n, int32_t n_volumes, int64_t local_size, const int32_t* prim_pool,
+                        const float* bias_pool, const float* level_scales, const float* pts,
+                        const void* anchors, int anchor_i64, int32_t* rows, void* stream);
+
+/* ---- PersSampler -------------------------------------------------------
+ * Replaces FindRayOctreeIntersectionKernel<false/true>, RayMarchKernel<false/true>
+ * and PersSampler::GetSamples (PtsSampler/PersSampler_cuda.cu:53-152, 190-318,
+ * 321-477).  tree_nodes / pers_trans are the reference's state blobs
+ * (128 B TreeNode, 576 B TransInfo; PersSampler.h:31-49), search_order is the
+ * uint8[64] table of PersSampler.cpp:137-151.
+ *
+ * One fused pass per ray (traverse + march), no host sync.  Outputs are written
+ * for sample k of ray r at slot r*1024+k ("dense", the reference layout
+ * [R,1024,...]); untouched slots are NOT written, so the caller zero-fills the
+ * dense tensors when it needs the reference's padding (:437-444).
+ */
+typedef struct {
+  float* world_pts;      /* [R,1024,3] or NULL */
+  float* warp_pts;       /* [R,1024,3] */
+  float* dirs;           /* [R,1024,3] or NULL */
+  float* dists;          /* [R,1024]   */
+  float* ts;             /* [R,1024]   */
+  int64_t* anchors_i64;  /* [R,1024,3] (trans_idx, node_idx, block_idx) or NULL */
+  int32_t* anchors_i32;  /* [R,1024,2] (trans_idx, node_idx)            or NULL */
+  int64_t* pts_idx_start_end; /* [R,2] start = exclusive prefix of counts, or NULL */
+  int32_t* counts;       /* [R] samples per ray (always written) */
+  float* first_oct_dis;  /* [R] */
+  int32_t* n_oct;        /* [R] leaves intersected per ray, or NULL */
+} gf_sampler_out;
+
+int gf_sampler_get_samples(int64_t n_rays, const float* rays_o, const float* rays_d_unit,
+                           const float* noise /* [1024 + n_rays + 10] already x fineness */,
+                           const void* tree_nodes, int64_t n_nodes,
+                           const void* pers_trans, int64_t n_trans,
+                           const uint8_t* search_order,
+                           float global_near, float sample_l, int scale_by_dis,
+                           int64_t max_oct_intersect_per_ray,
+                           const gf_sampler_out* out, void* stream);
+
+/* exclusive prefix sum of counts[R] -> offsets[R+1] (offsets[R] = total), int32;
+ * also writes *d_total. Single launch, no host sync. */
+int gf_sampler_scan_counts(int64_t n_rays, const int32_t* counts, int32_t* offsets,
+                           int32_t* d_total, void* stream);
+
+/* dense [R,1024,..] -> compact [V,..] gather using offsets; compact outputs:
+ * pts01 = (warp+1.5)/3 float[V,3], anchor int32[V], node int32[V], t float[V],
+ * delta float[V], ray_id int32[V]. */
+int gf_sampler_compact(int64_t n_rays, const int32_t* counts, const int32_t* offsets,
+                       const float* warp_pts, const float* dists, const float* ts,
+                       const int32_t* anchors_i32,
+                       float* c_pts01, int32_t* c_anchor, int32_t* c_node, float* c_t,
+                       float* c_delta, int32_t* c_ray, void* stream);
+
+/* MarkVistNodeKernel + the stat update + MarkInvalidNodes of
+ * PersSampler::UpdateOctNodes (PersSampler_cuda.cu:518-655), compact layout.
+ * weight_stats/alpha_stats/visit_cnt: int64 [n_nodes] state, updated in place;
+ * tree_nodes blob updated in place (trans_idx := -1 for pruned leaves).
+ * scratch: int64 [3*n_nodes] (adders + mark), overwritten. */
+int gf_sampler_update_oct_nodes(int64_t n_rays, const int32_t* counts, const int32_t* offsets,
+                                const int32_t* c_node, const float* weights, const float* alphas,
+                                void* tree_nodes, int64_t n_nodes,
+                                int64_t* weight_stats, int64_t* alpha_stats, int64_t* visit_cnt,
+                                int64_t* scratch, void* stream);
+
+/* QueryFrameTransform for arbitrary points (TransQueryFrameKernel, :854-922) */
+int gf_sampler_trans_query_frame(int64_t n_pts, const void* tree_nodes, int64_t n_nodes,
+                                 const void* pers_trans, const int64_t* anchors,
+                                 const float* world_pts, float* warp_pts, void* stream);
+
+/* ---- compositing --------------------------------------------------------
+ * Replaces RaySamples.get_weights_f2nerf (nerfstudio/cameras/rays.py:178-200)
+ * and RGBRenderer.combine_rgb / DepthRenderer('expected') / AccumulationRenderer
+ * (nerfstudio/model_components/renderers.py:97-110, 269-283, 220), one warp per
+ * ray, shuffle scan.  Samples of ray r are [offsets[r], offsets[r+1]).
+ * Per-sample outputs (weights, alphas, trans) may be NULL.
+ * depth is the UNCLIPPED expected depth sum(w t)/(sum(w)+1e-10); the caller
+ * applies the global clip of renderers.py:281 with t_max = gf_composite's
+ * d_tmax output (max t over valid samples; min is 0 because of padding).
+ */
+int gf_composite_forward(int64_t n_rays, const int32_t* offsets,
+                         const float* sigma, const float* delta, const float* rgb /*[V,3]*/,
+                         const float* t,
+                         float* weights, float* alphas, float* trans,
+                         float* out_rgb /*[R,3]*/, float* out_depth /*[R]*/, float* out_acc /*[R]*/,
+                         float* d_tmax /* [1], atomicMax'ed; caller zeroes */, void* stream);
+
+/* Gradients of out_rgb (g_rgb [R,3]) and optionally out_acc (g_acc [R], may be
+ * NULL) w.r.t. sigma and rgb.  d_sigma[V], d_rgb[V,3]. */
+int gf_composite_backward(int64_t n_rays, const int32_t* offsets,
+                          const float* sigma, const float* delta, const float* rgb,
+                          const float* g_rgb, const float* g_acc,
+                          float* d_sigma, float* d_rgb, void* stream);
+
+/* ---- fused field MLP ----------------------------------------------------
+ * Replaces MLPNetwork x2 (gfnerf/mlp.py:25-57 as built at
+ * gfnerf/nerfacto_field.py:174-179,217-227), trunc_exp(x+1) (:499),
+ * the tcnn SH degree-4 direction encoding (:152-158,521), the appearance
+ * embedding lookup (:530-537) and the concat (:540-547).
+ * fp16 tensor-core math, fp32 accumulate.  Hidden width H = 64.
+ *
+ * params: one fp32 blob, torch nn.Linear layout (weight [out,in] row-major, then bias):
+ *   base.0: W[H,32] b[H] ; base.1: W[16,H] b[16]
+ *   head.0: W[H,63] b[H] ; head.1: W[H,H] b[H] ; head.2: W[3,H] b[3]
+ * (gf_mlp_param_count(H) floats).  Head input order: SH(16) | geo(15) | emb(32).
+ */
+int64_t gf_mlp_param_count(int hidden);
+
+int gf_mlp_forward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params,
+                   const void* feat_f16 /*[n,32] __half*/, const int32_t* ray_id /*[n]*/,
+                   const float* ray_dirs /*[R,3] unit*/, const float* ray_emb /*[R,32] or NULL (zeros)*/,
+                   float* sigma /*[n]*/, float* rgb /*[n,3]*/, void* stream);
+
+/* d_sigma [n], d_rgb [n,3] -> d_feat_scaled_f16 __half [n,32] (= dL/dfeat * 128, the
+ * reference's grad_in), d_params fp32 [param_count] ACCUMULATED, d_ray_emb [R,32]
+ * ACCUMULATED (may be NULL).  Hidden activations are recomputed. */
+int gf_mlp_backward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params,
+                    const void* feat_f16, const int32_t* ray_id,
+                    const float* ray_dirs, const float* ray_emb,
+                    const float* d_sigma, const float* d_rgb,
+                    void* d_feat_scaled_f16, float* d_params, float* d_ray_emb, void* stream);
+
+/* ---- loss + optimiser tail ------------------------------------------------
+ * CharbonnierLoss (nerfstudio/model_components/losses.py:73-84, eps 1e-6,
+ * out_norm 'b'): loss = sum(sqrt((x-y)^2+eps^2))/R.  Writes g_rgb = dL/drgb and
+ * accumulates the loss into d_loss[0] (caller zeroes).
+ */
+int gf_charbonnier(int64_t n_rays, const float* rgb, const float* target, float eps,
+                   float* g_rgb, float* d_loss, void* stream);
+
+/* torch.optim.Adam (no amsgrad, no weight decay) as configured at
+ * gfnerf/config.py:132-135 / Hash3DAnchored.cpp:146-150.  step >= 1.
+ * If shadow_f16 != NULL it is refreshed with the updated parameters.
+ * grad is divided by grad_div first (world size for the DDP mean) and zeroed if
+ * zero_grad != 0. */
+int gf_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                 void* shadow_f16, float lr, float beta1, float beta2, float eps,
+                 int64_t step, float grad_div, int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFNERF_B200_H */

@@ -1,0 +1,61 @@
+"""Shared synthetic-input builders for the parity tests (seeded, small)."""
+import numpy as np
+
+
+def first_primes_from(start, count):
+    """`count` consecutive primes >= start (deterministic prime pool for fixtures)."""
+    out = []
+    x = start | 1
+    while len(out) < count:
+        i, ok = 3, x % 2 == 1
+        while ok and i * i <= x:
+            ok = x % i != 0
+            i += 2
+        if ok:
+            out.append(x)
+        x += 2
+    return np.array(out, np.int64)
+
+
+def lcg_primes(count, seed=1234):
+    """primes in [2^28, 2^30) picked by a seeded LCG walk (SURVEY 8d fixture recipe)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    while len(out) < count:
+        x = int(rng.randint(1 << 28, 1 << 30)) | 1
+        while True:
+            i, ok = 3, True
+            while ok and i * i <= x:
+                ok = x % i != 0
+                i += 2
+            if ok:
+                break
+            x += 2
+        if x < (1 << 30):
+            out.append(x)
+    return np.array(out, np.int32)
+
+
+def hash_inputs(n, n_volumes, log2T, seed=0, along_rays=True):
+    rng = np.random.RandomState(seed)
+    local = 1 << log2T
+    feat = rng.uniform(-1e-2, 1e-2, size=(16 * local, 2)).astype(np.float32)
+    prim = lcg_primes(16 * n_volumes * 3, seed + 1).reshape(16, n_volumes, 3)
+    bias = np.zeros((16 * n_volumes, 3), np.float32)
+    if along_rays:
+        # samples in runs along rays, like the sampler emits them: (warp+1.5)/3 with warp in ~[-1,1]
+        n_runs = max(1, n // 64)
+        start = rng.uniform(0.2, 0.8, size=(n_runs, 1, 3))
+        d = rng.normal(size=(n_runs, 1, 3))
+        d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        k = np.arange(64).reshape(1, 64, 1)
+        pts = (start + d * k / 768.0).reshape(-1, 3)[:n]
+        if pts.shape[0] < n:
+            pts = np.concatenate([pts, rng.uniform(0.17, 0.83, size=(n - pts.shape[0], 3))])
+        anchors = np.repeat(rng.randint(0, n_volumes, size=n_runs), 64)[:n]
+        if anchors.shape[0] < n:
+            anchors = np.concatenate([anchors, rng.randint(0, n_volumes, size=n - anchors.shape[0])])
+    else:
+        pts = rng.uniform(0.17, 0.83, size=(n, 3))
+        anchors = rng.randint(0, n_volumes, size=n)
+    return feat, prim, bias, np.clip(pts, 0, 1).astype(np.float32), anchors.astype(np.int64)

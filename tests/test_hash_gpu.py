@@ -1,0 +1,146 @@
+"""GPU parity: gf_hash_* (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact corner rows and bit-exact forward values (both follow the same FMA convention);
+gradients within 1e-5 relative of the exactly-summed oracle (fp32 atomics, order-dependent).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests.helpers import hash_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def make_core(feat, prim, bias, log2T):
+    from gfnerf_b200.hash_3d_anchored import Hash3DAnchoredCore
+    core = Hash3DAnchoredCore(log2T, prim.shape[1])
+    core.feat_pool_.data.copy_(torch.from_numpy(feat))
+    core.prim_pool_ = torch.from_numpy(prim.astype(np.int32)).cuda().contiguous()
+    core.bias_pool_ = torch.from_numpy(bias).cuda().contiguous()
+    return core
+
+
+def test_device_level_scales_reported():
+    from gfnerf_b200.hash_3d_anchored import Hash3DAnchoredCore
+    core = Hash3DAnchoredCore(8, 1)
+    host = orc.hash_level_scales()
+    dev = core.level_scales_host
+    # the device's exp2f is an approximation (ex2.approx + range handling): allow 2 ulp, report equality
+    np.testing.assert_allclose(dev, host, rtol=3e-7)
+    print("device exp2f level scales bit-equal to host:", bool(np.array_equal(dev, host)))
+
+
+@pytest.mark.parametrize("n,n_vol,log2T,along", [(4096, 5, 12, True), (10000, 37, 15, False), (33, 1, 4, True)])
+def test_corner_rows_and_forward_bit_exact(n, n_vol, log2T, along):
+    from gfnerf_b200 import _lib
+    feat, prim, bias, pts, anchors = hash_inputs(n, n_vol, log2T, seed=n, along_rays=along)
+    core = make_core(feat, prim, bias, log2T)
+    scales = core.level_scales_host
+    ref_out, ref_idx = orc.hash_forward(feat, prim, bias, pts, anchors, scales, want_idx=True)
+    tp, ta = torch.from_numpy(pts).cuda(), torch.from_numpy(anchors).cuda()
+    rows = torch.empty((n, 16, 8), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().gf_hash_corner_rows(n, n_vol, core.local_size_, _lib.ptr(core.prim_pool_),
+                                              _lib.ptr(core.bias_pool_), _lib.ptr(core.level_scales_), _lib.ptr(tp),
+                                              _lib.ptr(ta), 1, _lib.ptr(rows), _lib.cur_stream()))
+    assert np.array_equal(rows.cpu().numpy(), ref_idx)
+    out = core.AnchoredQuery(tp, ta)
+    assert np.array_equal(out.detach().cpu().numpy(), ref_out)
+    # int32 anchors + fp16 output + device-side count
+    out16 = torch.zeros((n, 32), dtype=torch.float16, device="cuda")
+    n_dev = torch.tensor([n - 7], dtype=torch.int32, device="cuda")
+    core.launch_forward(tp, ta.to(torch.int32), out_f16=out16, d_n_ptr=n_dev)
+    got = out16.float().cpu().numpy()
+    assert np.array_equal(got[: n - 7], ref_out[: n - 7])
+    assert not got[n - 7:].any()
+
+
+def test_non_pow2_table():
+    from gfnerf_b200 import _lib
+    rng = np.random.RandomState(4)
+    local = 48 * 16
+    n, n_vol = 2000, 3
+    _, prim, bias, pts, anchors = hash_inputs(n, n_vol, 10, seed=9)
+    feat = rng.uniform(-1, 1, size=(16 * local, 2)).astype(np.float32)
+    scales_d = torch.empty(16, device="cuda")
+    scales_h = np.zeros(16, np.float32)
+    _lib.check(_lib.lib().gf_hash_level_scales(_lib.ptr(scales_d), scales_h.ctypes.data, _lib.cur_stream()))
+    ref = orc.hash_forward(feat, prim, bias, pts, anchors, scales_h)
+    f16 = torch.from_numpy(feat).cuda().half().contiguous()
+    tp, ta = torch.from_numpy(pts).cuda(), torch.from_numpy(anchors).cuda()
+    tprim, tbias = torch.from_numpy(prim.astype(np.int32)).cuda().contiguous(), torch.from_numpy(bias).cuda()
+    out = torch.empty((n, 32), device="cuda")
+    _lib.check(_lib.lib().gf_hash_forward(n, None, n_vol, local, _lib.ptr(f16), _lib.ptr(tprim), _lib.ptr(tbias),
+                                          _lib.ptr(scales_d), _lib.ptr(tp), _lib.ptr(ta), 1, None, _lib.ptr(out),
+                                          _lib.cur_stream()))
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n,n_vol,log2T,along", [(4096, 5, 12, True), (20000, 11, 14, False), (31, 2, 6, True)])
+def test_backward_matches_oracle(n, n_vol, log2T, along):
+    feat, prim, bias, pts, anchors = hash_inputs(n, n_vol, log2T, seed=n + 1, along_rays=along)
+    core = make_core(feat, prim, bias, log2T)
+    rng = np.random.RandomState(n)
+    g = (rng.normal(size=(n, 32)) * 1e-3).astype(np.float32)
+    g[rng.rand(n, 32) < 0.2] = 0
+    ref = orc.hash_backward(core.local_size_, prim, bias, pts, anchors, g, core.level_scales_host)
+    tp, ta = torch.from_numpy(pts).cuda(), torch.from_numpy(anchors).cuda()
+    out = core.AnchoredQuery(tp, ta)
+    out.backward(torch.from_numpy(g).cuda())
+    got = core.feat_pool_.grad.double().cpu().numpy()
+    scale = np.abs(ref).max()
+    # 1e-5 relative (north star) on every row, with an absolute floor for rows that cancel
+    assert np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 1e-6 * scale)
+    assert np.array_equal(got == 0, ref == 0)
+    # pre-scaled fp16 gradient input (what gf_mlp_backward hands over) gives the same table
+    g16 = (torch.from_numpy(g).cuda() * 128).half().contiguous()
+    gt = torch.zeros_like(core.feat_pool_)
+    core.launch_backward(tp, ta.to(torch.int32), g16, True, gt)
+    assert np.all(np.abs(gt.double().cpu().numpy() - ref) <= 1e-5 * np.abs(ref) + 1e-6 * scale)
+
+
+def test_module_surface_and_state_roundtrip():
+    from gfnerf_b200 import Hash3DAnchored
+    enc = Hash3DAnchored(10, 3)
+    enc.reset()
+    pts = torch.rand(100, 3, device="cuda") * 0.6 + 0.2
+    anc = torch.randint(0, 3, (100,), device="cuda")
+    a = enc([pts, anc])
+    sd = enc.state_dict(prefix="field.base_encoding_init.")
+    assert set(k.split(".")[-1] for k in sd) >= {"feat_pool", "prime_pool", "bias_pool", "n_volumes"}
+    enc2 = Hash3DAnchored(10, 3)
+    enc2.load_state_dict({k: v.clone() for k, v in sd.items()}, prefix="field.base_encoding_init")
+    b = enc2([pts, anc])
+    assert torch.equal(a, b)
+    assert list(enc.parameters())[0] is enc.get_params()[0]
+    enc.zero()
+    assert float(enc([pts, anc]).abs().max()) == 0.0
+    # two forwards before one backward: gradients of both reach the table (reference hazard fixed)
+    enc.reset()
+    y1, y2 = enc([pts, anc]), enc([pts * 0.9, anc])
+    (y1.sum() + y2.sum()).backward()
+    assert enc.get_params()[0].grad.abs().sum() > 0
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (log2T=19, 2^20 points): linearity in the table and adjointness."""
+    from gfnerf_b200.hash_3d_anchored import Hash3DAnchoredCore
+    torch.manual_seed(0)
+    n, n_vol = 1 << 20, 64
+    core = Hash3DAnchoredCore(19, n_vol)
+    core.Reset()
+    pts = (torch.rand(n, 3, device="cuda") * 0.66 + 0.17).contiguous()
+    anc = torch.randint(0, n_vol, (n,), device="cuda")
+    y = core.AnchoredQuery(pts, anc)
+    g = torch.randn_like(y) * 1e-3
+    y.backward(g)
+    # <J^T g, table16> ~= <g, J table16>
+    t16 = core.feat_pool_.detach().half().double()
+    lhs = float((core.feat_pool_.grad.double() * t16).sum())
+    rhs = float((g.double() * y.detach().double()).sum())
+    assert abs(lhs - rhs) <= 2e-3 * abs(rhs) + 1e-9
+    # scaling the table by 2 (exact in fp16) scales the encoding by 2 exactly
+    core.feat_pool_.data.mul_(2)
+    y2 = core.AnchoredQuery(pts, anc)
+    assert torch.equal(y2.detach(), y.detach() * 2)
