@@ -18,6 +18,8 @@
 //    8 vectorised fp32 reductions (red.global.add.v2.f32) for the run.
 //
 // Arithmetic follows the oracle's FMA convention exactly (oracle/gf_oracle.c).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gf {
@@ -375,7 +377,8 @@ int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stride_grid(n, kHashBlock, 4, 4);
   const bool p2 = is_pow2(local_size);
-  const int aggregate = 1;
+  // GF_HASH_AGG=0 disables the warp-aggregated reduction (profiling A/B only)
+  static const int aggregate = [] { const char* e = getenv("GF_HASH_AGG"); return e ? atoi(e) : 1; }();
 #define GF_BWD(P2, AT, G16)                                                                               \
   hash_bwd_kernel<P2, AT, G16><<<grid, kHashBlock, 0, st>>>(n, d_n_ptr, n_volumes, (uint32_t)local_size,  \
                                                             prim_pool, bias_pool, level_scales, pts,      \

@@ -143,4 +143,5 @@ def test_full_size_properties():
     # scaling the table by 2 (exact in fp16) scales the encoding by 2 exactly
     core.feat_pool_.data.mul_(2)
     y2 = core.AnchoredQuery(pts, anc)
-    assert torch.equal(y2.detach(), y.detach() * 2)
+    # (exact except where the fp16 result is subnormal: allow one subnormal step)
+    assert float((y2.detach() - y.detach() * 2).abs().max()) <= 2.0 ** -23
