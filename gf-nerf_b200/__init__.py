@@ -5,5 +5,7 @@ package of that name points its __path__ here).
 """
 from . import _lib  # noqa: F401
 from .hash_3d_anchored import Hash3DAnchored, Hash3DAnchoredCore  # noqa: F401
+from .perssampler import PersSampler, PersSamplerCore  # noqa: F401
+from .engine import GFNeRFEngine  # noqa: F401
 
 __version__ = "0.1.0"

@@ -19,7 +19,7 @@ _vp, _i64, _i32, _f32, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_i
 class SamplerOut(C.Structure):
     """gf_sampler_out of include/gfnerf_b200.h"""
     _fields_ = [(n, _vp) for n in ("world_pts", "warp_pts", "dirs", "dists", "ts", "anchors_i64", "anchors_i32",
-                                   "pts_idx_start_end", "counts", "first_oct_dis", "n_oct")]
+                                   "pts_idx_start_end", "counts", "first_oct_dis", "n_oct", "packed")]
 
 
 _SIGS = {
@@ -31,13 +31,15 @@ _SIGS = {
     "gf_sampler_get_samples": [_i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _f32, _f32, _int, _i64,
                                C.POINTER(SamplerOut), _vp],
     "gf_sampler_scan_counts": [_i64, _vp, _vp, _vp, _vp],
-    "gf_sampler_compact": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gf_sampler_compact": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_sampler_update_oct_nodes": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "gf_sampler_trans_query_frame": [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "gf_composite_forward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "gf_composite_backward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "gf_mlp_forward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "gf_mlp_backward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gf_composite_backward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gf_mlp_ray_bias": [_i64, _int, _vp, _vp, _vp, _vp, _vp],
+    "gf_mlp_forward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gf_mlp_backward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp],
+    "gf_mlp_ray_bias_backward": [_i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_charbonnier": [_i64, _vp, _vp, _f32, _vp, _vp, _vp],
     "gf_adam_step": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _int, _vp],
 }
@@ -56,12 +58,14 @@ def lib():
         L.gf_last_error.restype = C.c_char_p
         L.gf_version.restype = C.c_char_p
         L.gf_launch_count.restype = C.c_int64
-        L.gf_mlp_param_count.restype = C.c_int64
-        L.gf_mlp_param_count.argtypes = [_int]
-        for name, sig in _SIGS.items():
-            fn = getattr(L, name)
+        for name, sig in list(_SIGS.items()) + [("gf_mlp_param_count", [_int])]:
+            try:
+                fn = getattr(L, name)
+            except AttributeError as e:  # a stale build: fail loudly, never fall back
+                raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild with "
+                                   "`python gf-nerf_b200/build.py --force`") from e
             fn.argtypes = sig
-            fn.restype = _int
+            fn.restype = C.c_int64 if name == "gf_mlp_param_count" else _int
         _lib = L
     return _lib
 

@@ -1,0 +1,231 @@
+"""Fused per-ray hot path: one training / render step over a ray batch, compact (CSR) layout.
+
+This is what `GFNeRFModel.get_outputs` + loss + backward + optimizer step amount to for the path of
+SURVEY.md section 8 (reference gfnerf/nerfacto.py:522-619, gfnerf/gf_pipeline.py:146-186,
+nerfstudio/engine/trainer.py:382-443), with every stage a kernel of the C-ABI library and no host
+synchronisation inside the step:
+
+  sample (traverse + march) -> scan -> compact -> hash encode -> ray bias -> MLP -> composite
+  -> Charbonnier -> composite bwd -> MLP bwd -> ray-bias bwd -> hash scatter
+  -> [NCCL all-reduce of table / MLP / embedding gradients] -> Adam (table + fp16 shadow, MLP, embedding)
+  -> octree vote.
+
+The reference evaluates all R*1024 padded slots; here only the V valid samples exist.  Results per
+valid sample are identical (padding contributes weight 0 in the reference because its delta is 0).
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .hash_3d_anchored import Hash3DAnchoredCore
+from .perssampler import CompactSamples, PersSamplerCore
+
+HIDDEN = 64
+APPEARANCE_DIM = 32
+
+
+def mlp_param_count(hidden: int = HIDDEN) -> int:
+    return int(_lib.lib().gf_mlp_param_count(hidden))
+
+
+def init_mlp_params(hidden: int = HIDDEN, generator: torch.Generator = None, device="cpu") -> torch.Tensor:
+    """torch nn.Linear default init (kaiming_uniform(a=sqrt(5)) = U(-1/sqrt(in), 1/sqrt(in)) for weight and
+    bias), in the blob order of include/gfnerf_b200.h -- what MLPNetwork (gfnerf/mlp.py:35-43) constructs."""
+    parts = []
+    for out_f, in_f in ((hidden, 32), (16, hidden), (hidden, 63), (hidden, hidden), (3, hidden)):
+        bound = 1.0 / np.sqrt(in_f)
+        parts.append((torch.rand(out_f * in_f, generator=generator) * 2 - 1) * bound)
+        parts.append((torch.rand(out_f, generator=generator) * 2 - 1) * bound)
+    return torch.cat(parts).float().to(device).contiguous()
+
+
+class _Adam:
+    """State of gf_adam_step for one flat fp32 tensor."""
+
+    def __init__(self, param: torch.Tensor, lr: float, eps: float = 1e-15, betas=(0.9, 0.999)):
+        self.param, self.lr, self.eps, self.betas = param, lr, eps, betas
+        self.grad = torch.zeros_like(param)
+        self.m = torch.zeros_like(param)
+        self.v = torch.zeros_like(param)
+        self.t = 0
+
+    def step(self, shadow=None, grad_div=1.0, lr=None):
+        self.t += 1
+        _lib.check(_lib.lib().gf_adam_step(
+            self.param.numel(), _lib.ptr(self.param), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
+            _lib.ptr(shadow), float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.t,
+            float(grad_div), 1, _lib.cur_stream()), "gf_adam_step")
+
+
+@dataclass
+class StepOutputs:
+    rgb: torch.Tensor            # [R,3]
+    depth: torch.Tensor          # [R]
+    accumulation: torch.Tensor   # [R]
+    loss: Optional[torch.Tensor]  # [1] or None
+    n_samples: torch.Tensor      # int32 [1] (device)
+
+
+class GFNeRFEngine:
+    """Global-stage model state (hash table, MLPs, appearance embedding) + the fused step."""
+
+    def __init__(self, sampler: PersSamplerCore, log2_table_size: int = 19, num_images: int = 1, hidden: int = HIDDEN,
+                 use_appearance_embedding: bool = True, lr_table: float = 1e-2, lr_mlp: float = 1e-2,
+                 seed: int = 0, dist_group=None):
+        self.sampler = sampler
+        self.device = sampler.device
+        self.hidden = hidden
+        gen = torch.Generator().manual_seed(seed)
+        # n_volumes: the reference sizes the prime pool by the number of tree nodes (gfnerf/nerfacto.py:267)
+        # while indexing it with trans_idx (< number of transforms); any bound >= n_trans is equivalent.
+        self.n_volumes = max(int(sampler.n_volumes_), 1)
+        self.enc = Hash3DAnchoredCore(log2_table_size, self.n_volumes, device=self.device, generator=gen)
+        self.enc.feat_pool_.requires_grad_(False)
+        self.enc.Reset()   # U(-0.01, 0.01), gfnerf/nerfacto_field.py:200
+        self.mlp = init_mlp_params(hidden, gen, self.device)
+        self.emb = (torch.randn(num_images, APPEARANCE_DIM, generator=gen).to(self.device)
+                    if use_appearance_embedding else None)
+        self.opt_table = _Adam(self.enc.feat_pool_.detach().view(-1), lr_table)
+        self.opt_mlp = _Adam(self.mlp, lr_mlp)
+        self.opt_emb = _Adam(self.emb.view(-1), lr_mlp) if self.emb is not None else None
+        self.enc.shadow(force=True)
+        self.group = dist_group
+        self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
+        self._ws = {}
+        self.step_count = 0
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+
+    # ---- workspace -----------------------------------------------------------------------
+    def _buf(self, name, shape, dtype, zero=False):
+        n = int(np.prod(shape))
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        t = t[:n].view(*shape)
+        if zero:
+            t.zero_()
+        return t
+
+    # ---- forward pieces --------------------------------------------------------------------
+    def _field_forward(self, cs: CompactSamples, ray_emb):
+        L, st = _lib.lib(), _lib.cur_stream()
+        cap, R = cs.pts01.shape[0], cs.n_rays
+        feat = self._buf("feat", (cap, 32), torch.float16)
+        sigma = self._buf("sigma", (cap,), torch.float32)
+        rgb = self._buf("rgb", (cap, 3), torch.float32)
+        ray_bias = self._buf("ray_bias", (R, self.hidden), torch.float32)
+        self.enc.launch_forward(cs.pts01, cs.anchor, out_f16=feat, d_n_ptr=cs.total, recast=False)
+        _lib.check(L.gf_mlp_ray_bias(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit), _lib.ptr(ray_emb),
+                                     _lib.ptr(ray_bias), st), "gf_mlp_ray_bias")
+        _lib.check(L.gf_mlp_forward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
+                                    _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(sigma), _lib.ptr(rgb), st),
+                   "gf_mlp_forward")
+        return feat, sigma, rgb, ray_bias
+
+    def _composite(self, cs: CompactSamples, sigma, rgb, keep: bool):
+        L, st = _lib.lib(), _lib.cur_stream()
+        cap, R = cs.pts01.shape[0], cs.n_rays
+        weights = self._buf("weights", (cap,), torch.float32) if keep else None
+        alphas = self._buf("alphas", (cap,), torch.float32) if keep else None
+        trans = self._buf("trans", (cap,), torch.float32) if keep else None
+        out_rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
+        depth = torch.empty(R, dtype=torch.float32, device=self.device)
+        acc = torch.empty(R, dtype=torch.float32, device=self.device)
+        tmax = torch.zeros(1, dtype=torch.float32, device=self.device)
+        _lib.check(L.gf_composite_forward(R, _lib.ptr(cs.offsets), _lib.ptr(sigma), _lib.ptr(cs.delta), _lib.ptr(rgb),
+                                          _lib.ptr(cs.t), _lib.ptr(weights), _lib.ptr(alphas), _lib.ptr(trans),
+                                          _lib.ptr(out_rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(tmax), st),
+                   "gf_composite_forward")
+        # DepthRenderer clips to the global [t.min(), t.max()] of the DENSE tensor, whose min is the padding's 0
+        # (nerfstudio/model_components/renderers.py:281)
+        depth = torch.minimum(torch.clamp_min(depth, 0.0), tmax)
+        return out_rgb, depth, acc, weights, alphas, trans
+
+    def _ray_emb(self, rel_camera_indices):
+        if self.emb is None or rel_camera_indices is None:
+            return None
+        return self.emb.index_select(0, rel_camera_indices.to(torch.int64)).contiguous()
+
+    # ---- public API ------------------------------------------------------------------------
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, rel_camera_indices=None, noise=None) -> StepOutputs:
+        """Forward-only (eval) pass: GFNeRFModel.get_outputs without the training feedback."""
+        with torch.cuda.device(self.device):
+            cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise)
+            _, sigma, rgb, _ = self._field_forward(cs, self._ray_emb(rel_camera_indices))
+            out_rgb, depth, acc, _, _, _ = self._composite(cs, sigma, rgb, keep=False)
+            # RGBRenderer in eval mode: nan_to_num + clamp (renderers.py:131-137)
+            out_rgb = torch.nan_to_num(out_rgb).clamp_(0.0, 1.0)
+        return StepOutputs(out_rgb, depth, acc, None, cs.total)
+
+    @torch.no_grad()
+    def train_step(self, rays_o, rays_d, target_rgb, rel_camera_indices=None, noise=None, lr_scale: float = 1.0,
+                   update_octree: bool = True, optimizer_step: bool = True) -> StepOutputs:
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            st = _lib.cur_stream()
+            step = self.step_count
+            cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise)
+            cap, R = cs.pts01.shape[0], cs.n_rays
+            ray_emb = self._ray_emb(rel_camera_indices)
+            feat, sigma, rgb, ray_bias = self._field_forward(cs, ray_emb)
+            out_rgb, depth, acc, weights, alphas, trans = self._composite(cs, sigma, rgb, keep=True)
+            # loss (CharbonnierLoss, nerfstudio/model_components/losses.py:73-84)
+            g_rgb = self._buf("g_rgb", (R, 3), torch.float32)
+            loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+            target = target_rgb.contiguous().float()
+            _lib.check(L.gf_charbonnier(R, _lib.ptr(out_rgb), _lib.ptr(target), 1e-6,
+                                        _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_charbonnier")
+            # backward
+            d_sigma = self._buf("d_sigma", (cap,), torch.float32)
+            d_rgb = self._buf("d_rgb", (cap, 3), torch.float32)
+            _lib.check(L.gf_composite_backward(R, _lib.ptr(cs.offsets), _lib.ptr(sigma), _lib.ptr(cs.delta),
+                                               _lib.ptr(rgb), _lib.ptr(trans), _lib.ptr(g_rgb), None, None,
+                                               _lib.ptr(d_sigma), _lib.ptr(d_rgb), st), "gf_composite_backward")
+            d_feat = self._buf("d_feat", (cap, 32), torch.float16)
+            d_ray_bias = self._buf("d_ray_bias", (R, self.hidden), torch.float32, zero=True)
+            grad_scale = float(2 ** int(np.ceil(np.log2(max(R, 1)))))
+            _lib.check(L.gf_mlp_backward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
+                                         _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(d_sigma), _lib.ptr(d_rgb),
+                                         _lib.ptr(d_feat), _lib.ptr(self.opt_mlp.grad), _lib.ptr(d_ray_bias),
+                                         grad_scale, st), "gf_mlp_backward")
+            d_ray_emb = self._buf("d_ray_emb", (R, APPEARANCE_DIM), torch.float32, zero=True) if ray_emb is not None else None
+            _lib.check(L.gf_mlp_ray_bias_backward(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
+                                                  _lib.ptr(ray_emb), _lib.ptr(d_ray_bias), _lib.ptr(self.opt_mlp.grad),
+                                                  _lib.ptr(d_ray_emb), st), "gf_mlp_ray_bias_backward")
+            if d_ray_emb is not None:
+                self.opt_emb.grad.view(-1, APPEARANCE_DIM).index_add_(0, rel_camera_indices.to(torch.int64), d_ray_emb)
+            self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_table.grad.view(-1, 2),
+                                     d_n_ptr=cs.total)
+            if optimizer_step:
+                self._reduce_and_step(lr_scale)
+            if update_octree:
+                self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
+                self.sampler.UpdateRayMarch(step)
+            self.step_count += 1
+        return StepOutputs(out_rgb, depth, acc, loss, cs.total)
+
+    def _reduce_and_step(self, lr_scale: float):
+        """DDP semantics (mean over ranks) for ALL parameters -- including the hash table, which the reference's
+        DDP wrapper silently skips because feat_pool is not a registered nn.Parameter."""
+        if self.world > 1:
+            import torch.distributed as dist
+            cur = torch.cuda.current_stream(self.device)
+            # small blobs first on the compute stream's successor, the 64 MB table gradient after it
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.opt_mlp.grad, group=self.group)
+                if self.opt_emb is not None:
+                    dist.all_reduce(self.opt_emb.grad, group=self.group)
+                dist.all_reduce(self.opt_table.grad, group=self.group)
+            cur.wait_stream(self.comm_stream)
+        div = float(self.world)
+        self.opt_mlp.step(grad_div=div, lr=self.opt_mlp.lr * lr_scale)
+        if self.opt_emb is not None:
+            self.opt_emb.step(grad_div=div, lr=self.opt_emb.lr * lr_scale)
+        self.opt_table.step(shadow=self.enc._shadow, grad_div=div, lr=self.opt_table.lr * lr_scale)
+        self.enc.mark_shadow_fresh()

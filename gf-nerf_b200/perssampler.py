@@ -1,0 +1,438 @@
+"""PersSampler: host-side mirror of the reference sampler operator.
+
+`PersSamplerCore` mirrors the C++ class behind `torch.classes.my_classes.PersSampler`
+(reference gfnerf/bindings/PtsSampler/PersSampler.cpp:899-1016, PersSampler_cuda.cu:321-477,
+584-677, bindings.cpp:18-299): same constructor arguments (`InitSampler`), method names, return
+orders and state blobs.  `PersSampler` mirrors the nn.Module shell (reference
+gfnerf/perssampler.py:47-447).  Traversal / marching / voting run in the C-ABI library
+(csrc/sampler.cu); octree construction and `ProcOctree` are host work (persoctree.py), as in the
+reference.  There is no CPU fallback for the per-step path.
+
+Besides the reference's dense `[R,1024,...]` API there is `sample_compact`, the CSR layout the
+fused engine uses: only valid samples exist, 36 B each instead of 76 B x 1024 slots per ray.
+"""
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .persoctree import INIT_NODE_STAT, PersOctree
+
+MAX_SAMPLE_PER_RAY = 1024
+
+
+@dataclass
+class CompactSamples:
+    """CSR sample set of one ray batch (device tensors, capacity R*1024; `total` valid entries)."""
+    n_rays: int
+    counts: torch.Tensor        # int32 [R]
+    offsets: torch.Tensor       # int32 [R+1]
+    total: torch.Tensor         # int32 [1] (device)
+    pts01: torch.Tensor         # f32 [cap,3]   (warp+1.5)/3
+    anchor: torch.Tensor        # int32 [cap]   trans_idx
+    node: torch.Tensor          # int32 [cap]   tree node
+    t: torch.Tensor             # f32 [cap]
+    delta: torch.Tensor         # f32 [cap]
+    ray_id: torch.Tensor        # int32 [cap]
+    first_oct_dis: torch.Tensor  # f32 [R]
+    rays_d_unit: torch.Tensor   # f32 [R,3]
+
+
+class PersSamplerCore:
+    def __init__(self):
+        self.octree: Optional[PersOctree] = None
+
+    # ---- construction (PersSampler::PersSampler, PersSampler.cpp:899-952) -------------------
+    def InitSampler(self, split_dist_thres, sub_div_milestones, compact_freq, max_oct_intersect_per_ray, global_near,
+                    scale_by_dis, bbox_levels, sample_l, max_level, c2w, w2c, intri, bounds, mode,
+                    sampled_oct_per_ray, ray_march_fineness, ray_march_init_fineness,
+                    ray_march_fineness_decay_end_iter, device=None, seed: int = 0, octree: PersOctree = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PersSampler needs a CUDA device: the B200 kernels have no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.sub_div_milestones_ = [int(v) for v in sub_div_milestones][::-1]      # reversed, popped from the back
+        self.compact_freq_ = int(compact_freq)
+        self.max_oct_intersect_per_ray_ = int(max_oct_intersect_per_ray)
+        self.global_near_ = float(np.float32(global_near))
+        self.scale_by_dis_ = bool(scale_by_dis)
+        self.sample_l_ = float(np.float32(sample_l))
+        self.mode_ = int(mode)
+        self.sampled_oct_per_ray_ = float(sampled_oct_per_ray)
+        self.ray_march_fineness_ = float(ray_march_fineness)
+        self.ray_march_init_fineness_ = float(ray_march_init_fineness)
+        self.ray_march_fineness_decay_end_iter_ = float(ray_march_fineness_decay_end_iter)
+        to_np = lambda x: x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        self.w2c_ = torch.as_tensor(to_np(w2c), dtype=torch.float32).to(self.device).contiguous()
+        self.intri_ = torch.as_tensor(to_np(intri), dtype=torch.float32).to(self.device).contiguous()
+        self.bound_ = torch.as_tensor(to_np(bounds), dtype=torch.float32).to(self.device).contiguous()
+        if octree is None:
+            octree = PersOctree(int(max_level), float(1 << (int(bbox_levels) - 1)), float(np.float32(split_dist_thres)),
+                                to_np(c2w), to_np(intri), to_np(bounds), seed=seed)
+        self.octree = octree
+        self.n_volumes_ = int(octree.trans.shape[0])
+        self._upload_octree(stats=True)
+        self.search_order_ = torch.from_numpy(octree.search_order.copy()).to(self.device)
+        self._ws = {}
+        self.generator = None   # optional torch.Generator (cuda) for the march noise
+
+    def _upload_octree(self, stats: bool):
+        oc = self.octree
+        self.tree_nodes_gpu_ = torch.from_numpy(oc.tree_nodes_blob()).to(self.device)
+        self.pers_trans_gpu_ = torch.from_numpy(oc.pers_trans_blob()).to(self.device)
+        if stats:
+            self.tree_weight_stats_ = torch.from_numpy(oc.weight_stats.copy()).to(self.device)
+            self.tree_alpha_stats_ = torch.from_numpy(oc.alpha_stats.copy()).to(self.device)
+            self.tree_visit_cnt_ = torch.from_numpy(oc.visit_cnt.copy()).to(self.device)
+
+    @property
+    def n_nodes(self) -> int:
+        return self.tree_nodes_gpu_.numel() // 128
+
+    # ---- workspace ---------------------------------------------------------------------
+    def _buf(self, name, shape, dtype):
+        t = self._ws.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(n, dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    def _noise(self, n_rays: int) -> torch.Tensor:
+        """PersSampler_cuda.cu:380-389: ones in VALIDATE mode, U(0.5,1.5) in TRAIN mode, times the fineness."""
+        n = MAX_SAMPLE_PER_RAY + n_rays + 10
+        if self.mode_ == 1:
+            noise = torch.ones(n, dtype=torch.float32, device=self.device)
+        else:
+            noise = torch.rand(n, dtype=torch.float32, device=self.device, generator=self.generator) - .5 + 1.
+        return noise.mul_(float(np.float32(self.ray_march_fineness_)))
+
+    def _launch(self, rays_o, rays_d_unit, noise, out: "_lib.SamplerOut"):
+        import ctypes as C
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gf_sampler_get_samples(
+                rays_o.shape[0], _lib.ptr(rays_o), _lib.ptr(rays_d_unit), _lib.ptr(noise),
+                _lib.ptr(self.tree_nodes_gpu_), self.n_nodes, _lib.ptr(self.pers_trans_gpu_),
+                self.pers_trans_gpu_.numel() // 576, _lib.ptr(self.search_order_), self.global_near_, self.sample_l_,
+                int(self.scale_by_dis_), self.max_oct_intersect_per_ray_, C.byref(out), _lib.cur_stream()),
+                "gf_sampler_get_samples")
+
+    @staticmethod
+    def _normalise(rays_o, rays_d):
+        rays_o = rays_o.contiguous().float()
+        rays_d = (rays_d / torch.linalg.norm(rays_d, 2, -1, True)).contiguous().float()   # :323
+        return rays_o, rays_d
+
+    # ---- reference API: dense [R,1024,...] (PersSampler::GetSamples, :321-477) ---------------
+    def GetSamples(self, rays_o_raw: torch.Tensor, rays_d_raw: torch.Tensor, bounds_raw: torch.Tensor = None,
+                   noise: torch.Tensor = None) -> List[torch.Tensor]:
+        _lib.require_cuda(rays_o_raw, rays_d_raw)
+        rays_o, rays_d = self._normalise(rays_o_raw, rays_d_raw)
+        R, S, dev = rays_o.shape[0], MAX_SAMPLE_PER_RAY, self.device
+        train = self.mode_ != 1
+        if noise is None:
+            noise = self._noise(R)
+        world = torch.zeros((R, S, 3), dtype=torch.float32, device=dev)
+        warp = torch.zeros((R, S, 3), dtype=torch.float32, device=dev)
+        dirs = torch.zeros((R, S, 3), dtype=torch.float32, device=dev)
+        anchors = torch.zeros((R, S, 3), dtype=torch.int64, device=dev)
+        dists = torch.zeros((R, S), dtype=torch.float32, device=dev)
+        ts = torch.zeros((R, S), dtype=torch.float32, device=dev)
+        start_end = torch.zeros((R, 2), dtype=torch.int64, device=dev)
+        first = torch.zeros((R, 1), dtype=torch.float32, device=dev)
+        counts = torch.zeros(R, dtype=torch.int32, device=dev)
+        n_oct = torch.zeros(R, dtype=torch.int32, device=dev) if train else None
+        out = _lib.SamplerOut(world_pts=_lib.ptr(world), warp_pts=_lib.ptr(warp), dirs=_lib.ptr(dirs),
+                              dists=_lib.ptr(dists), ts=_lib.ptr(ts), anchors_i64=_lib.ptr(anchors),
+                              anchors_i32=None, pts_idx_start_end=_lib.ptr(start_end), counts=_lib.ptr(counts),
+                              first_oct_dis=_lib.ptr(first), n_oct=_lib.ptr(n_oct), packed=None)
+        if R > 0:
+            self._launch(rays_o, rays_d, noise.contiguous(), out)
+        self.last_counts_ = counts
+        if train and R > 0:   # EMA of leaves per ray (:386-387); the only host read, off the critical path
+            self._pending_n_oct = (n_oct, R)
+        return [world, warp, dirs, dists, ts, anchors, start_end, first]
+
+    def flush_stats(self):
+        """Folds the last batch's leaves-per-ray into sampled_oct_per_ray_ (host sync; call when convenient)."""
+        p = getattr(self, "_pending_n_oct", None)
+        if p is not None:
+            n_oct, R = p
+            per_ray = float(n_oct.sum().item()) / float(R)
+            self.sampled_oct_per_ray_ = self.sampled_oct_per_ray_ * .9 + per_ray * .1
+            self._pending_n_oct = None
+
+    # ---- compact API (fused engine) -------------------------------------------------------
+    def sample_compact(self, rays_o_raw, rays_d_raw, noise: torch.Tensor = None, want_n_oct=False) -> CompactSamples:
+        _lib.require_cuda(rays_o_raw, rays_d_raw)
+        rays_o, rays_d = self._normalise(rays_o_raw, rays_d_raw)
+        R, S = rays_o.shape[0], MAX_SAMPLE_PER_RAY
+        cap = max(R * S, 1)
+        if noise is None:
+            noise = self._noise(R)
+        packed = self._buf("packed", (cap, 8), torch.float32)
+        counts = self._buf("counts", (R,), torch.int32)
+        offsets = self._buf("offsets", (R + 1,), torch.int32)
+        total = self._buf("total", (1,), torch.int32)
+        first = self._buf("first", (R,), torch.float32)
+        n_oct = self._buf("n_oct", (R,), torch.int32) if want_n_oct else None
+        cs = CompactSamples(
+            n_rays=R, counts=counts, offsets=offsets, total=total,
+            pts01=self._buf("pts01", (cap, 3), torch.float32), anchor=self._buf("anchor", (cap,), torch.int32),
+            node=self._buf("node", (cap,), torch.int32), t=self._buf("t", (cap,), torch.float32),
+            delta=self._buf("delta", (cap,), torch.float32), ray_id=self._buf("ray_id", (cap,), torch.int32),
+            first_oct_dis=first, rays_d_unit=rays_d)
+        if R == 0:
+            offsets.zero_()
+            total.zero_()
+            return cs
+        out = _lib.SamplerOut(world_pts=None, warp_pts=None, dirs=None, dists=None, ts=None, anchors_i64=None,
+                              anchors_i32=None, pts_idx_start_end=None, counts=_lib.ptr(counts),
+                              first_oct_dis=_lib.ptr(first), n_oct=_lib.ptr(n_oct), packed=_lib.ptr(packed))
+        self._launch(rays_o, rays_d, noise.contiguous(), out)
+        L, st = _lib.lib(), _lib.cur_stream()
+        with torch.cuda.device(self.device):
+            _lib.check(L.gf_sampler_scan_counts(R, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(total), st),
+                       "gf_sampler_scan_counts")
+            _lib.check(L.gf_sampler_compact(R, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(packed),
+                                            _lib.ptr(cs.pts01), _lib.ptr(cs.anchor), _lib.ptr(cs.node), _lib.ptr(cs.t),
+                                            _lib.ptr(cs.delta), _lib.ptr(cs.ray_id), st), "gf_sampler_compact")
+        if want_n_oct:
+            self._pending_n_oct = (n_oct, R)
+        return cs
+
+    # ---- training feedback (PersSampler::UpdateOctNodes, :584-677) ------------------------
+    def _vote(self, n_rays, counts, offsets, c_node, weights, alphas):
+        scratch = self._buf("vote", (3 * self.n_nodes,), torch.int64)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gf_sampler_update_oct_nodes(
+                n_rays, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(c_node), _lib.ptr(weights), _lib.ptr(alphas),
+                _lib.ptr(self.tree_nodes_gpu_), self.n_nodes, _lib.ptr(self.tree_weight_stats_),
+                _lib.ptr(self.tree_alpha_stats_), _lib.ptr(self.tree_visit_cnt_), _lib.ptr(scratch),
+                _lib.cur_stream()), "gf_sampler_update_oct_nodes")
+
+    def _milestones(self, iter_step: int):
+        while self.sub_div_milestones_ and self.sub_div_milestones_[-1] <= iter_step:
+            self.ProcOctree(True, True, self.sub_div_milestones_[-1] <= 0)
+            self.MarkInvisibleNodes()
+            self.ProcOctree(True, False, False)
+            self.sub_div_milestones_.pop()
+        if iter_step % self.compact_freq_ == 0:
+            self.ProcOctree(True, False, False)
+
+    def UpdateOctNodes(self, sampled_anchors, pts_idx_bounds, sampled_weight, sampled_alpha, iter_step: int):
+        """Dense reference signature: anchors i64 [R,1024,3], bounds i64 [R,1024,2], weights/alphas [R,1024,1]."""
+        R = sampled_weight.shape[0]
+        se = pts_idx_bounds[:, 0, :]
+        counts = (se[:, 1] - se[:, 0]).to(torch.int32).contiguous()
+        offsets = (torch.arange(R + 1, device=self.device, dtype=torch.int64) * MAX_SAMPLE_PER_RAY).to(torch.int32)
+        c_node = sampled_anchors.reshape(R * MAX_SAMPLE_PER_RAY, 3)[:, 1].to(torch.int32).contiguous()
+        self._vote(R, counts, offsets, c_node, sampled_weight.reshape(-1).contiguous().float(),
+                   sampled_alpha.reshape(-1).contiguous().float())
+        self._milestones(int(iter_step))
+
+    def update_oct_nodes_compact(self, cs: CompactSamples, weights, alphas, iter_step: int):
+        self._vote(cs.n_rays, cs.counts, cs.offsets, cs.node, weights, alphas)
+        self._milestones(int(iter_step))
+
+    def ProcOctree(self, compact: bool, subdivide: bool, brute_force: bool):
+        """PersOctree::ProcOctree (PersSampler.cpp:154-417): D2H of the node blob + stats, host compaction /
+        subdivision, H2D -- same round trip as the reference."""
+        oc = self.octree
+        oc.load_blobs(self.tree_nodes_gpu_.cpu().numpy(), self.pers_trans_gpu_.cpu().numpy())
+        oc.weight_stats = self.tree_weight_stats_.cpu().numpy()
+        oc.alpha_stats = self.tree_alpha_stats_.cpu().numpy()
+        oc.visit_cnt = self.tree_visit_cnt_.cpu().numpy()
+        oc.proc_octree(compact, subdivide, brute_force)
+        self._upload_octree(stats=True)
+
+    def MarkInvisibleNodes(self):
+        """MarkInvisibleNodesKernel + CheckVisible (PersSampler_cuda.cu:680-742); cold (milestones only), so it
+        is a handful of torch ops over [n_nodes, n_cams] instead of a kernel of its own."""
+        nodes = self.tree_nodes_gpu_.view(-1, 128)
+        cs = nodes[:, :16].contiguous().view(torch.float32)                    # center xyz, side_len
+        center, side = cs[:, :3], cs[:, 3]
+        cam = torch.einsum("cij,nj->nci", self.w2c_[:, :, :3], center) + self.w2c_[None, :, :, 3]   # [n,c,3]
+        radius = (side * 0.707)[:, None]
+        z = -cam[..., 2]
+        out_z = (z < self.bound_[None, :, 0] - radius) | (z > self.bound_[None, :, 1] + radius)
+        inside = torch.linalg.norm(cam, dim=-1) < radius
+        cx, cy = self.intri_[None, :, 0, 2], self.intri_[None, :, 1, 2]
+        fx, fy = self.intri_[None, :, 0, 0], self.intri_[None, :, 1, 1]
+        bx, by = radius / z * fx, radius / z * fy
+        ix, iy = cam[..., 0] / z * fx, cam[..., 1] / z * fy
+        out_img = (ix + bx < -cx) | (ix > cx + bx) | (iy + by < -cy) | (iy > cy + by)
+        visible = (~out_z) & (inside | ~out_img)
+        invisible = visible.sum(-1) < 1
+        tidx = nodes[:, 96:104].contiguous().view(torch.int64).view(-1)
+        tidx[invisible] = -1
+        nodes[:, 96:104] = tidx.view(-1, 1).view(torch.uint8)
+
+    def UpdateBlockIdxs(self, centers: torch.Tensor):
+        """SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-798): nearest block centre per node, then compact."""
+        nodes = self.tree_nodes_gpu_.view(-1, 128)
+        center = nodes[:, :12].contiguous().view(torch.float32)
+        d = torch.linalg.norm(center.double()[:, None] - centers.to(self.device).double()[None], dim=-1)
+        nodes[:, 104:112] = torch.argmin(d, dim=-1).to(torch.int64).view(-1, 1).view(torch.uint8)
+        self.ProcOctree(True, False, False)
+
+    def UpdateMode(self, mode: int):
+        self.mode_ = int(mode)
+
+    def UpdateRayMarch(self, cur_step: int):
+        """PersSampler.cpp:958-967 (fp32 arithmetic)."""
+        if cur_step >= self.ray_march_fineness_decay_end_iter_:
+            self.ray_march_fineness_ = 1.0
+        else:
+            progress = np.float32(cur_step) / np.float32(self.ray_march_fineness_decay_end_iter_)
+            self.ray_march_fineness_ = float(np.exp(np.log(np.float32(1.)) * progress + np.log(
+                np.float32(self.ray_march_init_fineness_)) * (np.float32(1.) - progress)))
+
+    # ---- states (PersSampler.cpp:969-1016) ----------------------------------------------
+    def States(self) -> List[torch.Tensor]:
+        ms = torch.tensor(self.sub_div_milestones_, dtype=torch.int64, device=self.device)
+        return [self.tree_nodes_gpu_, self.pers_trans_gpu_, self.tree_visit_cnt_, ms]
+
+    def LoadStates(self, states: List[torch.Tensor], idx: int) -> int:
+        self.tree_nodes_gpu_ = states[idx].clone().to(self.device).contiguous(); idx += 1
+        self.pers_trans_gpu_ = states[idx].clone().to(self.device).contiguous(); idx += 1
+        self.tree_visit_cnt_ = states[idx].clone().to(self.device).contiguous(); idx += 1
+        self.sub_div_milestones_ = [int(v) for v in states[idx].cpu().tolist()]; idx += 1
+        self.octree.load_blobs(self.tree_nodes_gpu_.cpu().numpy(), self.pers_trans_gpu_.cpu().numpy())
+        n = self.n_nodes
+        self.tree_weight_stats_ = torch.full((n,), INIT_NODE_STAT, dtype=torch.int64, device=self.device)
+        self.tree_alpha_stats_ = torch.full((n,), INIT_NODE_STAT, dtype=torch.int64, device=self.device)
+        self.n_volumes_ = self.pers_trans_gpu_.numel() // 576
+        return idx
+
+    # ---- cold queries (bindings.cpp:42-299) ----------------------------------------------
+    def TransQueryFrame(self, world_positions: torch.Tensor, anchors: torch.Tensor) -> torch.Tensor:
+        """TransQueryFrameKernel (PersSampler_cuda.cu:854-922): anchors are TREE NODE indices."""
+        wp = world_positions.contiguous().float()
+        out = torch.zeros_like(wp)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gf_sampler_trans_query_frame(
+                wp.shape[0], _lib.ptr(self.tree_nodes_gpu_), self.n_nodes, _lib.ptr(self.pers_trans_gpu_),
+                _lib.ptr(anchors.contiguous().to(torch.int64)), _lib.ptr(wp), _lib.ptr(out), _lib.cur_stream()),
+                "gf_sampler_trans_query_frame")
+        return out
+
+    def QueryTreeNodeCenters(self, anchors: torch.Tensor) -> torch.Tensor:
+        center = self.tree_nodes_gpu_.view(-1, 128)[:, :12].contiguous().view(torch.float32)
+        return center[anchors.to(torch.int64).clamp(0, self.n_nodes - 1)]
+
+    def get_n_volumes(self) -> int:
+        return self.n_volumes_
+
+    def get_n_tree_nodes(self) -> int:
+        return self.n_nodes
+
+    def get_sampled_oct_per_ray(self) -> float:
+        return self.sampled_oct_per_ray_
+
+    def get_ray_march_fineness(self) -> float:
+        return self.ray_march_fineness_
+
+    def _node_field(self, lo, hi, dtype):
+        return self.tree_nodes_gpu_.view(-1, 128)[:, lo:hi].contiguous().view(dtype)
+
+    def get_tree_nodes_center_(self):
+        return self._node_field(0, 12, torch.float32).cpu().tolist()
+
+    def get_tree_nodes_side_len_(self):
+        return self._node_field(12, 16, torch.float32).view(-1).cpu().tolist()
+
+    def get_tree_nodes_trans_idx_(self):
+        return self._node_field(96, 104, torch.int64).view(-1).cpu().tolist()
+
+    def get_tree_nodes_block_idx_(self):
+        return self._node_field(104, 112, torch.int64).view(-1).cpu().tolist()
+
+    def get_tree_nodes_is_leaf_node_(self):
+        return [bool(v) for v in self._node_field(88, 89, torch.uint8).view(-1).cpu().tolist()]
+
+
+class PersSampler(nn.Module):
+    """Drop-in for reference gfnerf/perssampler.py:47-447 (`generate_ray_samples` returns the same dense
+    RaySamples structure; see rays.py)."""
+
+    def __init__(self, c2w, intri, bounds, n_split_dataset=10, steps_per_split_dataset=10000,
+                 steps_perssampler_init=30000, split_dist_thres: float = 1.5,
+                 sub_div_milestones=(2000, 4000, 6000, 8000, 10000), compact_freq: int = 1000,
+                 max_oct_intersect_per_ray: int = 1024, global_near: float = 0.01, scale_by_dis: bool = True,
+                 bbox_levels: int = 8, sample_l: float = 1.0 / 256, max_level: int = 16, mode: int = 0,
+                 sampled_oct_per_ray: int = 512, ray_march_fineness: float = 1.0, ray_march_init_fineness=16.0,
+                 ray_march_fineness_decay_end_iter=10000, device=None, seed: int = 0, octree: PersOctree = None):
+        super().__init__()
+        c2w = torch.as_tensor(c2w, dtype=torch.float32)
+        n = c2w.shape[0]
+        w2c = torch.eye(4).unsqueeze(0).repeat(n, 1, 1)
+        w2c[:, :3, :] = c2w
+        w2c = torch.linalg.inv(w2c)[:, :3, :].contiguous()
+        k = max(steps_perssampler_init // 30000, 1)
+        self.max_pts_per_ray = MAX_SAMPLE_PER_RAY
+        self.bounds = torch.as_tensor(bounds, dtype=torch.float32)
+        self.sampler = PersSamplerCore()
+        self.sampler.InitSampler(split_dist_thres, [int(x * k) for x in sub_div_milestones], compact_freq,
+                                 max_oct_intersect_per_ray, global_near, scale_by_dis, bbox_levels, sample_l, max_level,
+                                 c2w, w2c, torch.as_tensor(intri, dtype=torch.float32), self.bounds, mode,
+                                 sampled_oct_per_ray, ray_march_fineness, ray_march_init_fineness,
+                                 int(ray_march_fineness_decay_end_iter * k), device=device, seed=seed, octree=octree)
+        self.n_split_dataset = n_split_dataset
+        self.steps_per_split_dataset = steps_per_split_dataset
+        self.steps_perssampler_init = steps_perssampler_init
+        self._register_state_dict_hook(self.state_dict_hook)
+
+    def state_dict_hook(self, *args):
+        destination, prefix = args[1], args[2]
+        nodes, trans, visit, ms = self.sampler.States()
+        destination[prefix + "tree_nodes_gpu"] = nodes
+        destination[prefix + "pers_trans_gpu"] = trans
+        destination[prefix + "tree_visit_cnt"] = visit
+        destination[prefix + "milestones_ts"] = ms
+        return destination
+
+    def load_states(self, state_dict, prefix=""):
+        pre = "" if prefix == "" else f"{prefix}."
+        self.sampler.LoadStates([state_dict[pre + k] for k in
+                                 ("tree_nodes_gpu", "pers_trans_gpu", "tree_visit_cnt", "milestones_ts")], 0)
+
+    def generate_ray_samples(self, ray_bundle):
+        from .rays import Frustums, RaySamples, WarpedSamples
+        rays_o, rays_d = ray_bundle.origins, ray_bundle.directions
+        S = self.max_pts_per_ray
+        cur_step, cur_split_idx = -1, -1
+        if ray_bundle.steps is not None:
+            cur_step = int(ray_bundle.steps.reshape(-1)[0].item())
+            if cur_step >= self.steps_perssampler_init:
+                cur_split_idx = ((cur_step - self.steps_perssampler_init) // self.steps_per_split_dataset) % self.n_split_dataset
+        bounds = self.bounds[0, :].to(rays_o.device).repeat((rays_o.shape[0], 1))
+        world, warp, dirs, dists, ts, anchors, start_end, first = self.sampler.GetSamples(rays_o, rays_d, bounds)
+        f2 = WarpedSamples(sampled_world_pts=world, sampled_pts=warp, sampled_dirs=dirs, sampled_dists=dists.unsqueeze(-1),
+                           sampled_t=ts.unsqueeze(-1), sampled_anchors=anchors,
+                           pts_idx_start_end=start_end.unsqueeze(1).expand(-1, S, -1),
+                           first_oct_dis=first.unsqueeze(1).expand(-1, S, -1))
+        fr = Frustums(origins=rays_o.unsqueeze(1).expand(-1, S, -1), directions=rays_d.unsqueeze(1).expand(-1, S, -1),
+                      starts=ts.unsqueeze(-1), ends=ts.unsqueeze(-1),
+                      pixel_area=None if ray_bundle.pixel_area is None else ray_bundle.pixel_area.unsqueeze(1).expand(-1, S, -1))
+        cam = None if ray_bundle.camera_indices is None else ray_bundle.camera_indices.unsqueeze(1).expand(-1, S, -1)
+        rel = None if ray_bundle.rel_camera_indices is None else ray_bundle.rel_camera_indices.unsqueeze(1).expand(-1, S, -1)
+        return RaySamples(f2samples=f2, frustums=fr, camera_indices=cam, rel_camera_indices=rel,
+                          deltas=dists.unsqueeze(-1), cur_step=cur_step, cur_split_dataset_idx=cur_split_idx)
+
+    forward = generate_ray_samples
+
+    def update_oct_nodes(self, sampled_anchors, pts_idx_bounds, weights, alphas, step):
+        self.sampler.UpdateOctNodes(sampled_anchors, pts_idx_bounds, weights, alphas, step)
+
+    def update_ray_march(self, step):
+        self.sampler.UpdateRayMarch(step)
+
+    def update_mode(self, mode):
+        self.sampler.UpdateMode(mode)
+
+    def get_n_volumes(self):
+        return self.sampler.get_n_volumes()

@@ -120,6 +120,8 @@ typedef struct {
   int32_t* counts;       /* [R] samples per ray (always written) */
   float* first_oct_dis;  /* [R] */
   int32_t* n_oct;        /* [R] leaves intersected per ray, or NULL */
+  void* packed;          /* [R,1024] 32-byte records {warp xyz, t | dist, trans_idx, node_idx, 0}
+                            (two float4, ints stored bit-wise) for gf_sampler_compact, or NULL */
 } gf_sampler_out;
 
 int gf_sampler_get_samples(int64_t n_rays, const float* rays_o, const float* rays_d_unit,
@@ -136,12 +138,11 @@ int gf_sampler_get_samples(int64_t n_rays, const float* rays_o, const float* ray
 int gf_sampler_scan_counts(int64_t n_rays, const int32_t* counts, int32_t* offsets,
                            int32_t* d_total, void* stream);
 
-/* dense [R,1024,..] -> compact [V,..] gather using offsets; compact outputs:
- * pts01 = (warp+1.5)/3 float[V,3], anchor int32[V], node int32[V], t float[V],
- * delta float[V], ray_id int32[V]. */
+/* packed records [R,1024] -> CSR (sample s of ray r at offsets[r]+k); outputs:
+ * pts01 = (warp+1.5)/3 float[V,3] (nerfacto_field.py:431), anchor = trans_idx int32[V],
+ * node int32[V], t float[V], delta float[V], ray_id int32[V]. */
 int gf_sampler_compact(int64_t n_rays, const int32_t* counts, const int32_t* offsets,
-                       const float* warp_pts, const float* dists, const float* ts,
-                       const int32_t* anchors_i32,
+                       const void* packed,
                        float* c_pts01, int32_t* c_anchor, int32_t* c_node, float* c_t,
                        float* c_delta, int32_t* c_ray, void* stream);
 
@@ -178,11 +179,15 @@ int gf_composite_forward(int64_t n_rays, const int32_t* offsets,
                          float* out_rgb /*[R,3]*/, float* out_depth /*[R]*/, float* out_acc /*[R]*/,
                          float* d_tmax /* [1], atomicMax'ed; caller zeroes */, void* stream);
 
-/* Gradients of out_rgb (g_rgb [R,3]) and optionally out_acc (g_acc [R], may be
- * NULL) w.r.t. sigma and rgb.  d_sigma[V], d_rgb[V,3]. */
+/* rgb / t / out_rgb / out_depth / out_acc may be NULL in gf_composite_forward (weights only).
+ *
+ * Backward: d_sigma[V] (and d_rgb[V,3] if not NULL) from any of: g_rgb [R,3] (gradient of
+ * out_rgb; needs rgb), g_acc [R] (gradient of out_acc), g_w [V] (gradient flowing into the
+ * per-sample weights themselves, the operator-API path where the renderers are torch ops).
+ * trans[V] is the transmittance the forward wrote. */
 int gf_composite_backward(int64_t n_rays, const int32_t* offsets,
                           const float* sigma, const float* delta, const float* rgb,
-                          const float* g_rgb, const float* g_acc,
+                          const float* trans, const float* g_rgb, const float* g_acc, const float* g_w,
                           float* d_sigma, float* d_rgb, void* stream);
 
 /* ---- fused field MLP ----------------------------------------------------
@@ -197,21 +202,39 @@ int gf_composite_backward(int64_t n_rays, const int32_t* offsets,
  *   head.0: W[H,63] b[H] ; head.1: W[H,H] b[H] ; head.2: W[3,H] b[3]
  * (gf_mlp_param_count(H) floats).  Head input order: SH(16) | geo(15) | emb(32).
  */
-int64_t gf_mlp_param_count(int hidden);
+int64_t gf_mlp_param_count(int hidden);   /* -1 if the width is not built */
 
+/* Per-RAY part of the head's first layer (fp32):
+ *   ray_bias[r][j] = b2[j] + W2[j][0:16] . SH4(dir_r) + W2[j][31:63] . emb_r
+ * SH4 = tcnn SphericalHarmonics degree 4 on (dir+1)/2, fp16-rounded (nerfacto_field.py:64-70,
+ * 152-158, 521); emb_r = embedding_appearance(rel_camera_index of ray r) (:530-537), NULL = zeros.
+ * ray_dirs [R,3] unit, ray_emb [R,32], ray_bias [R,H]. */
+int gf_mlp_ray_bias(int64_t n_rays, int hidden, const float* params, const float* ray_dirs,
+                    const float* ray_emb, float* ray_bias, void* stream);
+
+/* feat_f16 __half [n,32] (the hash encoding), ray_id int32 [n] -> sigma [n] = exp(h0 + 1),
+ * rgb [n,3] = sigmoid(head). */
 int gf_mlp_forward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params,
-                   const void* feat_f16 /*[n,32] __half*/, const int32_t* ray_id /*[n]*/,
-                   const float* ray_dirs /*[R,3] unit*/, const float* ray_emb /*[R,32] or NULL (zeros)*/,
-                   float* sigma /*[n]*/, float* rgb /*[n,3]*/, void* stream);
+                   const void* feat_f16, const int32_t* ray_id, const float* ray_bias,
+                   float* sigma, float* rgb, void* stream);
 
-/* d_sigma [n], d_rgb [n,3] -> d_feat_scaled_f16 __half [n,32] (= dL/dfeat * 128, the
- * reference's grad_in), d_params fp32 [param_count] ACCUMULATED, d_ray_emb [R,32]
- * ACCUMULATED (may be NULL).  Hidden activations are recomputed. */
+/* d_sigma [n], d_rgb [n,3] -> d_feat_scaled_f16 __half [n,32] (= dL/dfeat * 128, the reference's
+ * grad_in, Hash3DAnchored_cuda.cu:209), d_params fp32 [param_count] ACCUMULATED (all of it except
+ * the SH / emb columns of W2 and b2), d_ray_bias fp32 [R,H] ACCUMULATED (caller zeroes).
+ * d_params == d_ray_bias == NULL: frozen MLP (focal stage), only d_feat is produced.
+ * Hidden activations are recomputed.  grad_scale: internal loss scale of the fp16 gradient
+ * fragments (a power of two near 1/|d_rgb|, e.g. the ray count); results are unscaled. */
 int gf_mlp_backward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params,
-                    const void* feat_f16, const int32_t* ray_id,
-                    const float* ray_dirs, const float* ray_emb,
+                    const void* feat_f16, const int32_t* ray_id, const float* ray_bias,
                     const float* d_sigma, const float* d_rgb,
-                    void* d_feat_scaled_f16, float* d_params, float* d_ray_emb, void* stream);
+                    void* d_feat_scaled_f16, float* d_params, float* d_ray_bias, float grad_scale,
+                    void* stream);
+
+/* d_ray_bias [R,H] -> d_params (SH / emb columns of W2, b2; ACCUMULATED; may be NULL) and
+ * d_ray_emb [R,32] (ACCUMULATED; may be NULL). */
+int gf_mlp_ray_bias_backward(int64_t n_rays, int hidden, const float* params, const float* ray_dirs,
+                             const float* ray_emb, const float* d_ray_bias, float* d_params,
+                             float* d_ray_emb, void* stream);
 
 /* ---- loss + optimiser tail ------------------------------------------------
  * CharbonnierLoss (nerfstudio/model_components/losses.py:73-84, eps 1e-6,

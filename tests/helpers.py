@@ -59,3 +59,36 @@ def hash_inputs(n, n_volumes, log2T, seed=0, along_rays=True):
         pts = rng.uniform(0.17, 0.83, size=(n, 3))
         anchors = rng.randint(0, n_volumes, size=n)
     return feat, prim, bias, np.clip(pts, 0, 1).astype(np.float32), anchors.astype(np.int64)
+
+
+def load_rig(name="rig8"):
+    """Prebuilt synthetic aerial rig + octree blobs (tools/make_rig_fixture.py)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return {k: d[k] for k in d.files}
+
+
+def rig_octree(rig):
+    """PersOctree object around fixture blobs (no construction)."""
+    from gfnerf_b200 import persoctree as po
+    oc = po.PersOctree.__new__(po.PersOctree)
+    oc.load_blobs(rig["tree_nodes"], rig["pers_trans"])
+    n = oc.nodes.shape[0]
+    oc.weight_stats = np.full(n, po.INIT_NODE_STAT, np.int64)
+    oc.alpha_stats = np.full(n, po.INIT_NODE_STAT, np.int64)
+    oc.visit_cnt = np.zeros(n, np.int64)
+    oc.search_order = po.search_order_table()
+    return oc
+
+
+def make_sampler(rig, mode=1, device=None):
+    from gfnerf_b200.perssampler import PersSamplerCore
+    c2w = rig["c2w"]
+    n = c2w.shape[0]
+    w2c = np.tile(np.eye(4, dtype=np.float32)[None], (n, 1, 1))
+    w2c[:, :3, :] = c2w
+    w2c = np.linalg.inv(w2c)[:, :3, :].astype(np.float32)
+    s = PersSamplerCore()
+    s.InitSampler(1.5, [2000, 4000, 6000, 8000, 10000], 1000, 1024, 0.01, True, 10, 1.0 / 256, 16, c2w, w2c,
+                  rig["intri"], rig["bounds"], mode, 512, 1.0, 16.0, 10000, device=device, octree=rig_octree(rig))
+    return s

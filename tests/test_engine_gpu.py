@@ -1,0 +1,102 @@
+"""GPU end-to-end: the fused step (sample -> encode -> MLP -> composite -> loss -> backward -> Adam) against the
+oracle chain on the same inputs, and convergence on a synthetic target."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests.helpers import load_rig, make_sampler
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(rig, log2T=14, mode=1, seed=0):
+    from gfnerf_b200.engine import GFNeRFEngine
+    s = make_sampler(rig, mode=mode)
+    return GFNeRFEngine(s, log2_table_size=log2T, num_images=rig["c2w"].shape[0], seed=seed)
+
+
+def test_one_step_matches_oracle_chain():
+    from gfnerf_b200.persoctree import rig_rays
+    rig = load_rig("rig8")
+    eng = make_engine(rig)
+    # post-training-like feature scale so that densities are not all ~e
+    eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
+    eng.enc.shadow(force=True)
+    R = 512
+    o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=2)
+    rng = np.random.RandomState(0)
+    target = rng.rand(R, 3).astype(np.float32)
+    table0 = eng.enc.feat_pool_.detach().cpu().numpy().copy()
+    mlp0 = eng.mlp.cpu().numpy().copy()
+    emb0 = eng.emb.cpu().numpy().copy()
+    to, td, tt = (torch.from_numpy(a).cuda() for a in (o, d, target))
+    tcam = torch.from_numpy(cam).cuda()
+    out = eng.train_step(to, td, tt, tcam, optimizer_step=False, update_octree=False)
+    V = int(out.n_samples.item())
+    # ---- oracle chain ----
+    smp = orc.sampler_get_samples(o, d, np.ones(1024 + R + 10, np.float32), rig["tree_nodes"], rig["pers_trans"])
+    counts = smp["counts"]
+    assert V == counts.sum()
+    m = counts[:, None] > np.arange(1024)[None]
+    pts01 = ((smp["warp_pts"][m] + np.float32(1.5)) / np.float32(3.0)).astype(np.float32)
+    anchors = smp["anchors"][m][:, 0]
+    ray_id = np.repeat(np.arange(R), counts).astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    prim, bias = eng.enc.prim_pool_.cpu().numpy(), eng.enc.bias_pool_.cpu().numpy()
+    feat = orc.hash_forward(table0, prim, bias, pts01, anchors, eng.enc.level_scales_host)
+    ray_emb = emb0[cam]
+    sigma, rgb = orc.mlp_forward(mlp0, feat, ray_id, d, ray_emb, 64)
+    comp = orc.composite_forward(offsets, sigma, smp["dists"][m], rgb, smp["ts"][m])
+    loss, g_rgb = orc.charbonnier(comp["rgb"], target)
+    np.testing.assert_allclose(out.rgb.cpu().numpy(), comp["rgb"], rtol=1e-2, atol=2e-3)
+    np.testing.assert_allclose(out.accumulation.cpu().numpy(), comp["acc"], rtol=1e-2, atol=2e-3)
+    assert abs(float(out.loss) - loss) < 1e-2 * loss
+    d_sigma, d_rgb = orc.composite_backward(offsets, sigma, smp["dists"][m], rgb, g_rgb)
+    d_feat, d_params, d_emb = orc.mlp_backward(mlp0, feat, ray_id, d, ray_emb, d_sigma, d_rgb, 64)
+    g_table = orc.hash_backward(eng.enc.local_size_, prim, bias, pts01, anchors, d_feat, eng.enc.level_scales_host)
+    got_t = eng.opt_table.grad.view(-1, 2).double().cpu().numpy()
+    sc = np.abs(g_table).max()
+    err = np.abs(got_t - g_table).max() / sc
+    print("table grad max err / max", err, "nonzero rows", (g_table != 0).any(-1).sum())
+    assert err < 2e-2
+    got_p = eng.opt_mlp.grad.double().cpu().numpy()
+    assert np.abs(got_p - d_params).max() / np.abs(d_params).max() < 2e-2
+    emb_ref = np.zeros_like(emb0, dtype=np.float64)
+    np.add.at(emb_ref, cam, d_emb)
+    got_e = eng.opt_emb.grad.view(-1, 32).double().cpu().numpy()
+    assert np.abs(got_e - emb_ref).max() / np.abs(emb_ref).max() < 2e-2
+    # ---- Adam step on exactly these gradients ----
+    g_t32, g_p32 = eng.opt_table.grad.cpu().numpy().copy(), eng.opt_mlp.grad.cpu().numpy().copy()
+    eng._reduce_and_step(1.0)
+    t_ref, m_, v_ = table0.reshape(-1).copy(), np.zeros(table0.size, np.float32), np.zeros(table0.size, np.float32)
+    orc.adam_step(t_ref, g_t32, m_, v_, 1e-2, 0.9, 0.999, 1e-15, 1)
+    np.testing.assert_allclose(eng.enc.feat_pool_.detach().cpu().numpy().reshape(-1), t_ref, rtol=1e-5, atol=1e-7)
+    p_ref, m_, v_ = mlp0.copy(), np.zeros(mlp0.size, np.float32), np.zeros(mlp0.size, np.float32)
+    orc.adam_step(p_ref, g_p32, m_, v_, 1e-2, 0.9, 0.999, 1e-15, 1)
+    np.testing.assert_allclose(eng.mlp.cpu().numpy(), p_ref, rtol=1e-5, atol=1e-7)
+    assert not eng.opt_table.grad.any() and not eng.opt_mlp.grad.any()          # zeroed for the next step
+    assert torch.equal(eng.enc._shadow, eng.enc.feat_pool_.detach().half())     # fp16 shadow refreshed in the Adam pass
+
+
+def test_training_reduces_loss_and_prunes():
+    from gfnerf_b200.persoctree import rig_rays
+    rig = load_rig("rig8")
+    eng = make_engine(rig, log2T=16, mode=0, seed=1)
+    R = 2048
+    losses = []
+    for it in range(60):
+        o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=100 + it)
+        # synthetic scene: colour is a smooth function of the ray's ground hit point
+        hit = o + d * (o[:, 2:3] / np.maximum(-d[:, 2:3], 1e-3))
+        target = 0.5 + 0.5 * np.sin(hit * np.array([1.3, 0.9, 0.0]) + np.array([0.0, 1.0, 2.0]))
+        out = eng.train_step(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(),
+                             torch.from_numpy(target.astype(np.float32)).cuda(), torch.from_numpy(cam).cuda())
+        losses.append(float(out.loss))
+    print("loss first/last", losses[0], losses[-1])
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5])
+    assert eng.sampler.get_ray_march_fineness() < 16.0
+    r = eng.render(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(cam).cuda())
+    assert r.rgb.shape == (R, 3) and float(r.rgb.min()) >= 0 and float(r.rgb.max()) <= 1
+    assert torch.isfinite(r.depth).all()

@@ -1,0 +1,124 @@
+"""GPU parity: fused field MLP (gf_mlp_*) against the fp32 CPU oracle of the reference field
+(gfnerf/nerfacto_field.py:437-591 with gfnerf/mlp.py).  Tolerance: 1e-2 relative -- the "fp16 MLP" class of the
+north star (fp16 weights / activations, fp32 accumulate)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+H = 64
+
+
+def make_case(n, R, seed, with_emb=True):
+    rng = np.random.RandomState(seed)
+    g = torch.Generator().manual_seed(seed)
+    from gfnerf_b200.engine import init_mlp_params
+    params = init_mlp_params(H, g).numpy()
+    # torch-default init gives tiny outputs for 0.01-scale hash features; scale features up so that every layer is
+    # exercised in a non-trivial range (post-training features are O(0.1 - 1))
+    feat = (rng.normal(0, 0.5, size=(n, 32))).astype(np.float16)
+    cuts = np.sort(rng.choice(np.arange(1, n), size=R - 1, replace=False)) if R > 1 else np.array([], int)
+    ray_id = np.searchsorted(cuts, np.arange(n), side="right").astype(np.int32)
+    dirs = rng.normal(size=(R, 3))
+    dirs = (dirs / np.linalg.norm(dirs, axis=-1, keepdims=True)).astype(np.float32)
+    emb = rng.normal(size=(R, 32)).astype(np.float32) if with_emb else None
+    return params, feat, ray_id, dirs, emb
+
+
+def gpu_forward(params, feat, ray_id, dirs, emb):
+    from gfnerf_b200 import _lib
+    L, st = _lib.lib(), _lib.cur_stream()
+    n, R = feat.shape[0], dirs.shape[0]
+    T = lambda a: None if a is None else torch.from_numpy(a).cuda()
+    tp, tf, tr, td, te = T(params), T(feat), T(ray_id), T(dirs), T(emb)
+    rb = torch.empty((R, H), device="cuda")
+    _lib.check(L.gf_mlp_ray_bias(R, H, _lib.ptr(tp), _lib.ptr(td), _lib.ptr(te), _lib.ptr(rb), st))
+    sigma, rgb = torch.empty(n, device="cuda"), torch.empty((n, 3), device="cuda")
+    _lib.check(L.gf_mlp_forward(n, None, H, _lib.ptr(tp), _lib.ptr(tf), _lib.ptr(tr), _lib.ptr(rb), _lib.ptr(sigma),
+                                _lib.ptr(rgb), st))
+    return (tp, tf, tr, td, te, rb), sigma, rgb
+
+
+def test_param_count_and_unsupported_width():
+    from gfnerf_b200 import _lib
+    assert _lib.lib().gf_mlp_param_count(64) == orc.mlp_param_count(64) == 11603
+    assert _lib.lib().gf_mlp_param_count(48) == -1
+
+
+@pytest.mark.parametrize("n,R,seed,with_emb", [(5000, 37, 0, True), (31, 2, 1, False), (4096, 1, 2, True)])
+def test_forward_matches_oracle(n, R, seed, with_emb):
+    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb)
+    (tp, tf, tr, td, te, rb), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb)
+    # per-ray bias: fp32 against the oracle's SH and the reference weight slices
+    sh = orc.sh4(dirs)
+    w2 = params[3152:3152 + 64 * 63].reshape(64, 63)
+    b2 = params[7184:7184 + 64]
+    ref_rb = sh.astype(np.float64) @ w2[:, :16].T.astype(np.float64) + b2
+    if emb is not None:
+        ref_rb = ref_rb + emb.astype(np.float64) @ w2[:, 31:].T.astype(np.float64)
+    np.testing.assert_allclose(rb.cpu().numpy(), ref_rb, rtol=1e-5, atol=1e-5)
+    ref_sigma, ref_rgb = orc.mlp_forward(params, feat.astype(np.float32), ray_id, dirs, emb, H)
+    np.testing.assert_allclose(sigma.cpu().numpy(), ref_sigma, rtol=1e-2)
+    np.testing.assert_allclose(rgb.cpu().numpy(), ref_rgb, rtol=1e-2, atol=1e-3)
+    print("max rel err sigma", np.max(np.abs(sigma.cpu().numpy() - ref_sigma) / ref_sigma),
+          "max abs err rgb", np.max(np.abs(rgb.cpu().numpy() - ref_rgb)))
+
+
+def test_device_side_count_limits_work():
+    from gfnerf_b200 import _lib
+    params, feat, ray_id, dirs, emb = make_case(1000, 5, 3)
+    (tp, tf, tr, td, te, rb), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb)
+    s2, c2 = torch.zeros(1000, device="cuda"), torch.zeros((1000, 3), device="cuda")
+    n_dev = torch.tensor([613], dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().gf_mlp_forward(1000, _lib.ptr(n_dev), H, _lib.ptr(tp), _lib.ptr(tf), _lib.ptr(tr), _lib.ptr(rb),
+                                         _lib.ptr(s2), _lib.ptr(c2), _lib.cur_stream()))
+    assert torch.equal(s2[:613], sigma[:613]) and not s2[613:].any()
+    assert torch.equal(c2[:613], rgb[:613]) and not c2[613:].any()
+
+
+@pytest.mark.parametrize("n,R,seed,with_emb", [(6000, 41, 5, True), (130, 3, 6, False), (129, 1, 7, True)])
+def test_backward_matches_oracle(n, R, seed, with_emb):
+    from gfnerf_b200 import _lib
+    L, st = _lib.lib(), _lib.cur_stream()
+    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb)
+    (tp, tf, tr, td, te, rb), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb)
+    rng = np.random.RandomState(seed + 100)
+    d_sigma = (rng.normal(size=n) * 1e-4).astype(np.float32)
+    d_rgb = (rng.normal(size=(n, 3)) * 1e-4).astype(np.float32)       # the magnitude a mean over ~8k rays produces
+    ref_dfeat, ref_dparams, ref_demb = orc.mlp_backward(params, feat.astype(np.float32), ray_id, dirs, emb, d_sigma,
+                                                        d_rgb, H)
+    tds, tdc = torch.from_numpy(d_sigma).cuda(), torch.from_numpy(d_rgb).cuda()
+    d_feat = torch.zeros((n, 32), dtype=torch.float16, device="cuda")
+    d_params = torch.zeros(11603, device="cuda")
+    d_rb = torch.zeros((R, H), device="cuda")
+    _lib.check(L.gf_mlp_backward(n, None, H, _lib.ptr(tp), _lib.ptr(tf), _lib.ptr(tr), _lib.ptr(rb), _lib.ptr(tds),
+                                 _lib.ptr(tdc), _lib.ptr(d_feat), _lib.ptr(d_params), _lib.ptr(d_rb), 8192.0, st))
+    d_emb = torch.zeros((R, 32), device="cuda") if with_emb else None
+    _lib.check(L.gf_mlp_ray_bias_backward(R, H, _lib.ptr(tp), _lib.ptr(td), _lib.ptr(te), _lib.ptr(d_rb),
+                                          _lib.ptr(d_params), _lib.ptr(d_emb), st))
+    got_dfeat = d_feat.float().cpu().numpy() / 128.0
+    s = np.abs(ref_dfeat).max()
+    assert np.all(np.abs(got_dfeat - ref_dfeat) <= 1e-2 * np.abs(ref_dfeat) + 4e-3 * s), \
+        np.max(np.abs(got_dfeat - ref_dfeat)) / s
+    got = d_params.cpu().numpy().astype(np.float64)
+    names = [("w0", 0, 2048), ("b0", 2048, 2112), ("w1", 2112, 3136), ("b1", 3136, 3152), ("w2", 3152, 7184),
+             ("b2", 7184, 7248), ("w3", 7248, 11344), ("b3", 11344, 11408), ("w4", 11408, 11600), ("b4", 11600, 11603)]
+    for name, a, b in names:
+        r, g = ref_dparams[a:b], got[a:b]
+        sc = np.abs(r).max() + 1e-30
+        err = np.max(np.abs(g - r)) / sc
+        print(f"d_{name}: max err / max |ref| = {err:.2e}")
+        assert err < 1e-2, name
+    if with_emb:
+        sc = np.abs(ref_demb).max()
+        assert np.max(np.abs(d_emb.cpu().numpy() - ref_demb)) / sc < 1e-2
+    else:
+        w2g = got[3152:7184].reshape(64, 63)
+        assert not w2g[:, 31:].any()        # no embedding: those columns get no gradient
+    # frozen-MLP variant (focal stage): same d_feat, no parameter gradients
+    d_feat2 = torch.zeros_like(d_feat)
+    _lib.check(L.gf_mlp_backward(n, None, H, _lib.ptr(tp), _lib.ptr(tf), _lib.ptr(tr), _lib.ptr(rb), _lib.ptr(tds),
+                                 _lib.ptr(tdc), _lib.ptr(d_feat2), None, None, 8192.0, st))
+    assert torch.equal(d_feat, d_feat2)
