@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- training rays/sec of the GF-NeRF global stage (BASELINE.json config 2/3) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      # CPU restatement of the reference path
+
+A step = one full training iteration of the per-ray hot path on one batch of 8192 synthetic rays per GPU:
+sample (octree traversal + march) -> hash encode -> MLP -> composite -> Charbonnier -> backward of all of it
+-> [NCCL all-reduce of table / MLP / embedding gradients] -> Adam (16.8 M-entry table + MLP + embedding)
+-> octree occupancy vote.  Workload: synthetic aerial rig of SURVEY.md 8(d) (400 cameras, prebuilt octree
+fixture tests/golden/rig20.npz), Hash3DAnchored 16 levels log2T=19, 64-wide MLPs, training-mode march noise.
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events around exactly K steps after W warm-ups, barrier +
+synchronize on both sides, max over ranks.  The per-step working set (table + Adam state 0.3 GB, sample
+buffers ~1 GB) is several times the 126 MB L2, and a pool of distinct ray batches is cycled, so no L2 flush
+is needed between iterations ("inputs larger than L2").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 8192
+LOG2T = 19
+N_BATCHES = 8            # distinct ray batches cycled through
+METRIC = "training rays/sec (fwd+bwd+optimizer), GF-NeRF global stage"
+
+
+def load_rig():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "rig20.npz"))
+    return {k: d[k] for k in d.files}
+
+
+def make_batches(rig, n_rays, n_batches, seed):
+    """(origins, directions, camera index, target rgb) per batch -- host arrays."""
+    from gfnerf_b200.persoctree import rig_rays
+    out = []
+    for b in range(n_batches):
+        o, d, cam = rig_rays(rig["c2w"], rig["intri"], n_rays, seed=seed * 1000 + b)
+        hit = o + d * (o[:, 2:3] / np.maximum(-d[:, 2:3], 1e-3))
+        target = (0.5 + 0.5 * np.sin(hit * np.array([1.3, 0.9, 0.0]) + np.array([0.0, 1.0, 2.0]))).astype(np.float32)
+        out.append((o, d, cam, target))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle chain (a CPU restatement of the reference's kernels; the reference's own native code
+# cannot be built here), all host threads.
+# --------------------------------------------------------------------------------------------
+def oracle_step(orc, rig, state, batch):
+    o, d, cam, target = batch
+    R = o.shape[0]
+    rng = state["rng"]
+    noise = rng.uniform(0.5, 1.5, 1024 + R + 10).astype(np.float32) * np.float32(state["fineness"])
+    smp = orc.sampler_get_samples(o, d, noise, rig["tree_nodes"], rig["pers_trans"])
+    counts = smp["counts"]
+    m = counts[:, None] > np.arange(1024)[None]
+    pts01 = ((smp["warp_pts"][m] + np.float32(1.5)) * (np.float32(1.0) / np.float32(3.0))).astype(np.float32)
+    anchors = smp["anchors"][m][:, 0]
+    ray_id = np.repeat(np.arange(R), counts).astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    feat = orc.hash_forward(state["table"], state["prim"], state["bias"], pts01, anchors, state["scales"])
+    ray_emb = state["emb"][cam]
+    sigma, rgb = orc.mlp_forward(state["mlp"], feat, ray_id, d, ray_emb, 64)
+    delta, t = smp["dists"][m], smp["ts"][m]
+    comp = orc.composite_forward(offsets, sigma, delta, rgb, t)
+    loss, g_rgb = orc.charbonnier(comp["rgb"], target)
+    d_sigma, d_rgb = orc.composite_backward(offsets, sigma, delta, rgb, g_rgb)
+    d_feat, d_params, d_emb = orc.mlp_backward(state["mlp"], feat, ray_id, d, ray_emb, d_sigma, d_rgb, 64)
+    g_table = orc.hash_backward(state["table"].shape[0] // 16, state["prim"], state["bias"], pts01, anchors, d_feat,
+                                state["scales"])
+    state["t"] += 1
+    orc.adam_step(state["table"].reshape(-1), g_table.astype(np.float32).reshape(-1), state["m"], state["v"],
+                  1e-2, 0.9, 0.999, 1e-15, state["t"])
+    return loss, int(counts.sum())
+
+
+def oracle_state(rig, log2T):
+    from oracle import oracle as orc
+    from tests.helpers import fast_primes
+    rng = np.random.RandomState(0)
+    n_vol = rig["pers_trans"].size // 576
+    n = 16 * (1 << log2T) * 2
+    bound = 1 / np.sqrt(np.array([32] * (64 * 33) + [64] * (16 * 65) + [63] * (64 * 64) + [64] * (64 * 65) + [64] * (3 * 65)))
+    return dict(rng=rng, fineness=1.0, table=rng.uniform(-1e-2, 1e-2, size=(n // 2, 2)).astype(np.float32),
+                prim=fast_primes(16 * n_vol * 3, 7).reshape(16, n_vol, 3), bias=np.zeros((16 * n_vol, 3), np.float32),
+                scales=orc.hash_level_scales(), mlp=(rng.uniform(-1, 1, size=11603) * bound).astype(np.float32),
+                emb=rng.normal(size=(rig["c2w"].shape[0], 32)).astype(np.float32),
+                m=np.zeros(n, np.float32), v=np.zeros(n, np.float32), t=0)
+
+
+def time_oracle(rays, steps, warmup, log2T=LOG2T):
+    from oracle import oracle as orc
+    rig = load_rig()
+    state = oracle_state(rig, log2T)
+    batches = make_batches(rig, rays, max(2, min(4, steps)), seed=99)
+    orc.set_num_threads(os.cpu_count() or 1)
+    for w in range(warmup):
+        oracle_step(orc, rig, state, batches[w % len(batches)])
+    t0 = time.perf_counter()
+    n_samples = 0
+    for k in range(steps):
+        _, v = oracle_step(orc, rig, state, batches[k % len(batches)])
+        n_samples += v
+    dt = time.perf_counter() - t0
+    return rays * steps / dt, dt / steps * 1e3, orc.num_threads(), n_samples / steps
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = 256
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    value, ms, cores, v = time_oracle(rays, steps, warmup)
+    sample = f"{rays} rays/step ({v:.0f} samples), {steps} steps after {warmup} warm-ups, same rig / table / MLP shapes"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "rays_per_step": rays, "log2T": LOG2T},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name():
+    return ("GF-NeRF global stage: Hash3DAnchored 16 levels log2T=19 + PersSampler (400-camera synthetic aerial rig), "
+            f"{RAYS_PER_GPU} rays/GPU/step, up to 1024 samples/ray, H=64 MLPs, fwd+bwd+Adam")
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the hot path has no CPU fallback); "
+                           "use --impl reference for the CPU restatement")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    from gfnerf_b200 import _lib
+    from gfnerf_b200.engine import GFNeRFEngine
+    from tests.helpers import make_sampler
+    rig = load_rig()
+    sampler = make_sampler(rig, mode=0, device=dev)
+    sampler.generator = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # steady state of the schedule: the march fineness decays 16 -> 1 over the first 10 k of 130 k iterations
+    # (PersSampler.cpp:958-967); the bench measures the fineness-1 regime the other 120 k iterations run in
+    sampler.ray_march_fineness_decay_end_iter_ = 0.0
+    sampler.ray_march_fineness_ = 1.0
+    eng = GFNeRFEngine(sampler, log2_table_size=LOG2T, num_images=rig["c2w"].shape[0], seed=0, dist_group=group)
+    if world > 1:    # identical parameters on every rank
+        for t in (eng.enc.feat_pool_.data, eng.enc.prim_pool_, eng.mlp, eng.emb):
+            dist.broadcast(t, 0)
+        eng.enc.shadow(force=True)
+
+    host = make_batches(rig, RAYS_PER_GPU, N_BATCHES, seed=1234 + rank)
+    pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
+    resident = [tuple(a.to(dev, non_blocking=True) for a in b) for b in pinned]
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        o, d, cam, tgt = resident[i % N_BATCHES]
+        return eng.train_step(o, d, tgt, cam)
+
+    def step_e2e(i):
+        o, d, cam, tgt = (a.to(dev, non_blocking=True) for a in pinned[i % N_BATCHES])
+        out = eng.train_step(o, d, tgt, cam)
+        return float(out.loss.cpu())          # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_total, launches = timed(step_resident, args.steps, args.warmup)
+    clocks.stop_flag = True
+    ms_step = ms_total / args.steps
+    value = RAYS_PER_GPU * world * args.steps / (ms_total * 1e-3)
+    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    e2e_value = RAYS_PER_GPU * world * args.steps / (ms_e2e * 1e-3)
+
+    # per-kernel device times (same steps, events around every launch), for the roofline of the dominant kernel
+    eng.enable_timers(True)
+    n_prof = min(args.steps, 10)
+    samples = 0
+    for i in range(n_prof):
+        out = step_resident(args.warmup + args.steps + i)
+        samples += int(out.n_samples.item())
+    stages = eng.stage_times()
+    eng.enable_timers(False)
+    v_mean = samples / n_prof
+    stage_ms = {k: t / c for k, (t, c) in stages.items()}
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            j = json.load(f)
+        peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "src": "measured"}
+    # algorithmic bytes / flops per launch (DESIGN.md "roofline accounting")
+    algo = {
+        "hash_fwd": ("hbm", 660.0 * v_mean), "hash_bwd": ("hbm", 660.0 * v_mean),
+        "sample_rays": ("hbm", 32.0 * v_mean + 24.0 * RAYS_PER_GPU), "compact": ("hbm", (32.0 + 36.0) * v_mean),
+        "composite_fwd": ("hbm", (28.0 + 12.0) * v_mean + 20.0 * RAYS_PER_GPU),
+        "composite_bwd": ("hbm", 44.0 * v_mean + 20.0 * RAYS_PER_GPU),
+        "mlp_fwd": ("tensor", 2.0 * 11392.0 * v_mean), "mlp_bwd": ("tensor", 2.0 * 2.0 * 11392.0 * v_mean),
+        "adam_table": ("hbm", 30.0 * 16 * (1 << LOG2T) * 2),
+    }
+    kernels = []
+    for name, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
+        ent = {"kernel": name, "ms": round(ms, 4), "share": round(ms / sum(stage_ms.values()), 4)}
+        if name in algo:
+            bound, work = algo[name]
+            if bound == "hbm":
+                a = work / (ms * 1e-3) / 1e9
+                ent.update({"bound": "hbm", "achieved": round(a, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": round(a / peaks["hbm_gbs"], 4)})
+            else:
+                a = work / (ms * 1e-3) / 1e12
+                ent.update({"bound": "tensor", "achieved": round(a, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": round(a / peaks["bf16_tflops"], 4)})
+        kernels.append(ent)
+    top = next(k for k in kernels if "bound" in k)
+    roofline = {k: top[k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+    roofline.update({"kernel": top["kernel"], "traffic": None, "peak_source": peaks["src"], "ms": top["ms"]})
+    if rank == 0 and args.breakdown:
+        for k in kernels:
+            print(k, file=sys.stderr)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cv, cms, cores, cvs = time_oracle(256, 3, 1)
+        cpu_baseline = {"value": cv, "unit": "rays/s", "cores": cores, "kind": "port",
+                        "sample": f"256 rays/step ({cvs:.0f} samples), 3 steps after 1 warm-up, same rig / table / MLP shapes"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 tables + f16 tensor-core MLP, f32 accumulate / geometry / optimizer",
+            "data": "synthetic",
+            "config": {"workload": workload_name(), "rays_per_gpu": RAYS_PER_GPU, "log2T": LOG2T, "hidden": 64,
+                       "samples_per_step_per_gpu": round(v_mean), "slots_per_step_per_gpu": RAYS_PER_GPU * 1024,
+                       "l2_policy": "inputs larger than L2 (0.3 GB table+optimizer state, ~1 GB sample buffers, "
+                                    f"{N_BATCHES} ray batches cycled)",
+                       "parallelism": f"dp{world}" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "rays/s",
+                    "h2d_bytes_per_step": int(sum(a.numel() * a.element_size() for a in pinned[0])) * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu_baseline,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,7 @@ synchronisation inside the step:
 The reference evaluates all R*1024 padded slots; here only the V valid samples exist.  Results per
 valid sample are identical (padding contributes weight 0 in the reference because its delta is 0).
 """
+import contextlib
 from dataclasses import dataclass
 from typing import Optional
 
@@ -98,6 +99,35 @@ class GFNeRFEngine:
         self.step_count = 0
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
 
+    # ---- per-stage device timing (bench / profiling only) -----------------------------------
+    def enable_timers(self, on: bool = True):
+        """Brackets every stage with CUDA events on the launching stream; read with `stage_times()`."""
+        self._events = [] if on else None
+        self.sampler.stage_hook = self._stage if on else None
+
+    @contextlib.contextmanager
+    def _stage(self, name):
+        ev = getattr(self, "_events", None)
+        if ev is None:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        ev.append((name, e0, e1))
+
+    def stage_times(self, reset: bool = True):
+        """-> {stage: (total ms, calls)} of everything recorded since the last reset (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, e0, e1 in self._events or []:
+            t, c = out.get(name, (0.0, 0))
+            out[name] = (t + e0.elapsed_time(e1), c + 1)
+        if reset and self._events is not None:
+            self._events = []
+        return out
+
     # ---- workspace -----------------------------------------------------------------------
     def _buf(self, name, shape, dtype, zero=False):
         n = int(np.prod(shape))
@@ -118,12 +148,15 @@ class GFNeRFEngine:
         sigma = self._buf("sigma", (cap,), torch.float32)
         rgb = self._buf("rgb", (cap, 3), torch.float32)
         ray_bias = self._buf("ray_bias", (R, self.hidden), torch.float32)
-        self.enc.launch_forward(cs.pts01, cs.anchor, out_f16=feat, d_n_ptr=cs.total, recast=False)
-        _lib.check(L.gf_mlp_ray_bias(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit), _lib.ptr(ray_emb),
-                                     _lib.ptr(ray_bias), st), "gf_mlp_ray_bias")
-        _lib.check(L.gf_mlp_forward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
-                                    _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(sigma), _lib.ptr(rgb), st),
-                   "gf_mlp_forward")
+        with self._stage("hash_fwd"):
+            self.enc.launch_forward(cs.pts01, cs.anchor, out_f16=feat, d_n_ptr=cs.total, recast=False)
+        with self._stage("ray_bias"):
+            _lib.check(L.gf_mlp_ray_bias(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
+                                         _lib.ptr(ray_emb), _lib.ptr(ray_bias), st), "gf_mlp_ray_bias")
+        with self._stage("mlp_fwd"):
+            _lib.check(L.gf_mlp_forward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
+                                        _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(sigma), _lib.ptr(rgb), st),
+                       "gf_mlp_forward")
         return feat, sigma, rgb, ray_bias
 
     def _composite(self, cs: CompactSamples, sigma, rgb, keep: bool):
@@ -136,10 +169,11 @@ class GFNeRFEngine:
         depth = torch.empty(R, dtype=torch.float32, device=self.device)
         acc = torch.empty(R, dtype=torch.float32, device=self.device)
         tmax = torch.zeros(1, dtype=torch.float32, device=self.device)
-        _lib.check(L.gf_composite_forward(R, _lib.ptr(cs.offsets), _lib.ptr(sigma), _lib.ptr(cs.delta), _lib.ptr(rgb),
-                                          _lib.ptr(cs.t), _lib.ptr(weights), _lib.ptr(alphas), _lib.ptr(trans),
-                                          _lib.ptr(out_rgb), _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(tmax), st),
-                   "gf_composite_forward")
+        with self._stage("composite_fwd"):
+            _lib.check(L.gf_composite_forward(R, _lib.ptr(cs.offsets), _lib.ptr(sigma), _lib.ptr(cs.delta),
+                                              _lib.ptr(rgb), _lib.ptr(cs.t), _lib.ptr(weights), _lib.ptr(alphas),
+                                              _lib.ptr(trans), _lib.ptr(out_rgb), _lib.ptr(depth), _lib.ptr(acc),
+                                              _lib.ptr(tmax), st), "gf_composite_forward")
         # DepthRenderer clips to the global [t.min(), t.max()] of the DENSE tensor, whose min is the padding's 0
         # (nerfstudio/model_components/renderers.py:281)
         depth = torch.minimum(torch.clamp_min(depth, 0.0), tmax)
@@ -178,34 +212,42 @@ class GFNeRFEngine:
             g_rgb = self._buf("g_rgb", (R, 3), torch.float32)
             loss = torch.zeros(1, dtype=torch.float32, device=self.device)
             target = target_rgb.contiguous().float()
-            _lib.check(L.gf_charbonnier(R, _lib.ptr(out_rgb), _lib.ptr(target), 1e-6,
-                                        _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_charbonnier")
+            with self._stage("loss"):
+                _lib.check(L.gf_charbonnier(R, _lib.ptr(out_rgb), _lib.ptr(target), 1e-6,
+                                            _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_charbonnier")
             # backward
             d_sigma = self._buf("d_sigma", (cap,), torch.float32)
             d_rgb = self._buf("d_rgb", (cap, 3), torch.float32)
-            _lib.check(L.gf_composite_backward(R, _lib.ptr(cs.offsets), _lib.ptr(sigma), _lib.ptr(cs.delta),
-                                               _lib.ptr(rgb), _lib.ptr(trans), _lib.ptr(g_rgb), None, None,
-                                               _lib.ptr(d_sigma), _lib.ptr(d_rgb), st), "gf_composite_backward")
+            with self._stage("composite_bwd"):
+                _lib.check(L.gf_composite_backward(R, _lib.ptr(cs.offsets), _lib.ptr(sigma), _lib.ptr(cs.delta),
+                                                   _lib.ptr(rgb), _lib.ptr(trans), _lib.ptr(g_rgb), None, None,
+                                                   _lib.ptr(d_sigma), _lib.ptr(d_rgb), st), "gf_composite_backward")
             d_feat = self._buf("d_feat", (cap, 32), torch.float16)
             d_ray_bias = self._buf("d_ray_bias", (R, self.hidden), torch.float32, zero=True)
             grad_scale = float(2 ** int(np.ceil(np.log2(max(R, 1)))))
-            _lib.check(L.gf_mlp_backward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
-                                         _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(d_sigma), _lib.ptr(d_rgb),
-                                         _lib.ptr(d_feat), _lib.ptr(self.opt_mlp.grad), _lib.ptr(d_ray_bias),
-                                         grad_scale, st), "gf_mlp_backward")
+            with self._stage("mlp_bwd"):
+                _lib.check(L.gf_mlp_backward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
+                                             _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(d_sigma),
+                                             _lib.ptr(d_rgb), _lib.ptr(d_feat), _lib.ptr(self.opt_mlp.grad),
+                                             _lib.ptr(d_ray_bias), grad_scale, st), "gf_mlp_backward")
             d_ray_emb = self._buf("d_ray_emb", (R, APPEARANCE_DIM), torch.float32, zero=True) if ray_emb is not None else None
-            _lib.check(L.gf_mlp_ray_bias_backward(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
-                                                  _lib.ptr(ray_emb), _lib.ptr(d_ray_bias), _lib.ptr(self.opt_mlp.grad),
-                                                  _lib.ptr(d_ray_emb), st), "gf_mlp_ray_bias_backward")
-            if d_ray_emb is not None:
-                self.opt_emb.grad.view(-1, APPEARANCE_DIM).index_add_(0, rel_camera_indices.to(torch.int64), d_ray_emb)
-            self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_table.grad.view(-1, 2),
-                                     d_n_ptr=cs.total)
+            with self._stage("ray_bias_bwd"):
+                _lib.check(L.gf_mlp_ray_bias_backward(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
+                                                      _lib.ptr(ray_emb), _lib.ptr(d_ray_bias),
+                                                      _lib.ptr(self.opt_mlp.grad), _lib.ptr(d_ray_emb), st),
+                           "gf_mlp_ray_bias_backward")
+                if d_ray_emb is not None:
+                    self.opt_emb.grad.view(-1, APPEARANCE_DIM).index_add_(0, rel_camera_indices.to(torch.int64),
+                                                                          d_ray_emb)
+            with self._stage("hash_bwd"):
+                self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_table.grad.view(-1, 2),
+                                         d_n_ptr=cs.total)
             if optimizer_step:
                 self._reduce_and_step(lr_scale)
             if update_octree:
-                self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
-                self.sampler.UpdateRayMarch(step)
+                with self._stage("octree_vote"):
+                    self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
+                    self.sampler.UpdateRayMarch(step)
             self.step_count += 1
         return StepOutputs(out_rgb, depth, acc, loss, cs.total)
 
@@ -224,8 +266,10 @@ class GFNeRFEngine:
                 dist.all_reduce(self.opt_table.grad, group=self.group)
             cur.wait_stream(self.comm_stream)
         div = float(self.world)
-        self.opt_mlp.step(grad_div=div, lr=self.opt_mlp.lr * lr_scale)
-        if self.opt_emb is not None:
-            self.opt_emb.step(grad_div=div, lr=self.opt_emb.lr * lr_scale)
-        self.opt_table.step(shadow=self.enc._shadow, grad_div=div, lr=self.opt_table.lr * lr_scale)
+        with self._stage("adam_small"):
+            self.opt_mlp.step(grad_div=div, lr=self.opt_mlp.lr * lr_scale)
+            if self.opt_emb is not None:
+                self.opt_emb.step(grad_div=div, lr=self.opt_emb.lr * lr_scale)
+        with self._stage("adam_table"):
+            self.opt_table.step(shadow=self.enc._shadow, grad_div=div, lr=self.opt_table.lr * lr_scale)
         self.enc.mark_shadow_fresh()

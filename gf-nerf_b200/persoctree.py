@@ -32,6 +32,16 @@ TRANS_INFO_DTYPE = np.dtype({
 })
 
 
+def _byte_copy(arr: np.ndarray) -> np.ndarray:
+    """copy of a padded structured array that keeps the padding bytes (zero) instead of leaving them undefined"""
+    return np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy().view(arr.dtype)
+
+
+def _take(arr: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(arr.shape[0], arr.dtype.itemsize)
+    return raw[mask].copy().reshape(-1).view(arr.dtype)
+
+
 def search_order_table() -> np.ndarray:
     """uint8[64]: children in front-to-back order for each ray octant (PersSampler.cpp:137-151).
 
@@ -288,15 +298,16 @@ class PersOctree:
         return np.ascontiguousarray(self.trans).view(np.uint8).reshape(-1).copy()
 
     def load_blobs(self, tree_nodes: np.ndarray, pers_trans: np.ndarray):
-        self.nodes = np.ascontiguousarray(tree_nodes, np.uint8).view(TREE_NODE_DTYPE).copy()
-        self.trans = np.ascontiguousarray(pers_trans, np.uint8).view(TRANS_INFO_DTYPE).copy()
+        # byte copies: a field-wise copy of a padded structured array would leave the padding undefined
+        self.nodes = np.ascontiguousarray(tree_nodes, np.uint8).reshape(-1).copy().view(TREE_NODE_DTYPE)
+        self.trans = np.ascontiguousarray(pers_trans, np.uint8).reshape(-1).copy().view(TRANS_INFO_DTYPE)
 
     # ------------------------------------------------------------------ maintenance
     def proc_octree(self, compact: bool, subdivide: bool, brute_force: bool) -> None:
         """ProcOctree (:154-417): prune invalid leaves, collapse childless / single-child interior nodes,
         renumber (order of first appearance), then split every visited leaf into 8 (depth-first order).
         `nodes`, `weight_stats`, `alpha_stats`, `visit_cnt` must hold the device's current values."""
-        nb = self.nodes.copy()
+        nb = _byte_copy(self.nodes)
         n_before = nb.shape[0]
         w_before, a_before, visit = self.weight_stats, self.alpha_stats, self.visit_cnt
         childs, parent, leaf, tidx = nb["childs"], nb["parent"], nb["is_leaf_node"], nb["trans_idx"]
@@ -335,7 +346,7 @@ class PersOctree:
         new_idx[keep] = np.arange(int(keep.sum()))
         inv_idx = np.nonzero(keep)[0]
         assert new_idx[0] == 0
-        nn = nb[keep].copy()
+        nn = _take(nb, keep)
         pm = nn["parent"] >= 0
         nn["parent"][pm] = new_idx[nn["parent"][pm]]
         cm = nn["childs"] >= 0
@@ -347,7 +358,9 @@ class PersOctree:
 
             def rec(u, pa):
                 new_u = len(out_nodes)
-                node = src[u].copy()
+                node = np.zeros((), TREE_NODE_DTYPE)
+                for f in TREE_NODE_DTYPE.names:
+                    node[f] = src[u][f]
                 node["parent"] = pa
                 out_nodes.append(node)
                 out_w.append(int(nw[u]))
@@ -388,7 +401,10 @@ class PersOctree:
                 rec(0, -1)
             finally:
                 sys.setrecursionlimit(lim)
-            nn = np.array(out_nodes, TREE_NODE_DTYPE)
+            nn = np.zeros(len(out_nodes), TREE_NODE_DTYPE)
+            for i_, nd_ in enumerate(out_nodes):
+                for f in TREE_NODE_DTYPE.names:
+                    nn[i_][f] = nd_[f]
             nw, na = np.array(out_w, np.int64), np.array(out_a, np.int64)
         self.nodes = nn
         self.weight_stats, self.alpha_stats = nw, na

@@ -192,14 +192,20 @@ class PersSamplerCore:
         out = _lib.SamplerOut(world_pts=None, warp_pts=None, dirs=None, dists=None, ts=None, anchors_i64=None,
                               anchors_i32=None, pts_idx_start_end=None, counts=_lib.ptr(counts),
                               first_oct_dis=_lib.ptr(first), n_oct=_lib.ptr(n_oct), packed=_lib.ptr(packed))
-        self._launch(rays_o, rays_d, noise.contiguous(), out)
+        import contextlib
+        hook = getattr(self, "stage_hook", None) or (lambda name: contextlib.nullcontext())
+        with hook("sample_rays"):
+            self._launch(rays_o, rays_d, noise.contiguous(), out)
         L, st = _lib.lib(), _lib.cur_stream()
         with torch.cuda.device(self.device):
-            _lib.check(L.gf_sampler_scan_counts(R, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(total), st),
-                       "gf_sampler_scan_counts")
-            _lib.check(L.gf_sampler_compact(R, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(packed),
-                                            _lib.ptr(cs.pts01), _lib.ptr(cs.anchor), _lib.ptr(cs.node), _lib.ptr(cs.t),
-                                            _lib.ptr(cs.delta), _lib.ptr(cs.ray_id), st), "gf_sampler_compact")
+            with hook("scan"):
+                _lib.check(L.gf_sampler_scan_counts(R, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(total), st),
+                           "gf_sampler_scan_counts")
+            with hook("compact"):
+                _lib.check(L.gf_sampler_compact(R, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(packed),
+                                                _lib.ptr(cs.pts01), _lib.ptr(cs.anchor), _lib.ptr(cs.node),
+                                                _lib.ptr(cs.t), _lib.ptr(cs.delta), _lib.ptr(cs.ray_id), st),
+                           "gf_sampler_compact")
         if want_n_oct:
             self._pending_n_oct = (n_oct, R)
         return cs

@@ -161,6 +161,9 @@ void orc_hash_backward(int64_t n, int32_t n_volumes, int64_t local_size, const i
                        const float* bias_pool, const float* scales, const float* pts,
                        const int64_t* anchors, const float* grad_out, double* grad_table) {
   memset(grad_table, 0, sizeof(double) * (size_t)(N_LEVELS * local_size * N_CHANNELS));
+  /* every addend is a multiple of 2^-31 (fp16 value / 128) and the sums stay far below 2^21, so the fp64
+     accumulation is exact and the result does not depend on the order the threads add in */
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; i++) {
     int64_t vol = anchors[i];
     for (int l = 0; l < N_LEVELS; l++) {
@@ -173,8 +176,11 @@ void orc_hash_backward(int64_t n, int32_t n_volumes, int64_t local_size, const i
       if (g0 != 0.f || g1 != 0.f) {
         double* tab = grad_table + (int64_t)l * local_size * N_CHANNELS;
         for (int d = 0; d < 8; d++) {
-          tab[(int64_t)c.pos[d] * 2 + 0] += (double)h2f(f2h(g0 * c.w[d])) / 128.0;
-          tab[(int64_t)c.pos[d] * 2 + 1] += (double)h2f(f2h(g1 * c.w[d])) / 128.0;
+          double a0 = (double)h2f(f2h(g0 * c.w[d])) / 128.0, a1 = (double)h2f(f2h(g1 * c.w[d])) / 128.0;
+#pragma omp atomic
+          tab[(int64_t)c.pos[d] * 2 + 0] += a0;
+#pragma omp atomic
+          tab[(int64_t)c.pos[d] * 2 + 1] += a1;
         }
       }
     }
@@ -754,7 +760,10 @@ void orc_mlp_backward(int64_t n, int H, const float* params, const float* feat, 
   mlp_params m = mlp_split(params, H);
   int64_t np = orc_mlp_param_count(H);
   memset(d_params, 0, sizeof(double) * (size_t)np);
-  double* gw0 = d_params;
+#pragma omp parallel
+  {
+  double* acc_p = (double*)calloc((size_t)np, sizeof(double));
+  double* gw0 = acc_p;
   double* gb0 = gw0 + H * 32;
   double* gw1 = gb0 + H;
   double* gb1 = gw1 + 16 * H;
@@ -764,6 +773,7 @@ void orc_mlp_backward(int64_t n, int H, const float* params, const float* feat, 
   double* gb3 = gw3 + H * H;
   double* gw4 = gb3 + H;
   double* gb4 = gw4 + 3 * H;
+#pragma omp for schedule(static)
   for (int64_t i = 0; i < n; i++) {
     float h1[256], h[16], in2[63], h2[256], h3[256], o[3];
     const float* x = feat + 32 * i;
@@ -814,7 +824,10 @@ void orc_mlp_backward(int64_t n, int H, const float* params, const float* feat, 
       }
     }
     if (d_ray_emb)
-      for (int k = 0; k < 32; k++) d_ray_emb[32 * r + k] += gin2[31 + k];
+      for (int k = 0; k < 32; k++) {
+#pragma omp atomic
+        d_ray_emb[32 * r + k] += gin2[31 + k];
+      }
     float pre = h[0] + 1.f;
     float cl = pre < -15.f ? -15.f : (pre > 15.f ? 15.f : pre);
     gh[0] = (double)d_sigma[i] * exp((double)cl);
@@ -839,6 +852,10 @@ void orc_mlp_backward(int64_t n, int H, const float* params, const float* feat, 
       }
     }
     for (int j = 0; j < 32; j++) d_feat[32 * i + j] = (float)gx[j];
+  }
+#pragma omp critical
+  for (int64_t k = 0; k < np; k++) d_params[k] += acc_p[k];
+  free(acc_p);
   }
 }
 

@@ -36,6 +36,46 @@ def lcg_primes(count, seed=1234):
     return np.array(out, np.int32)
 
 
+def _is_prime_mr(x):
+    """deterministic Miller-Rabin (bases 2, 7, 61: exact below 4.7e9), vectorised; x odd int64 array, 3 < x < 2^31"""
+    x = x.astype(np.uint64)
+    d = x - np.uint64(1)
+    s = np.zeros(x.shape, np.int64)
+    while True:
+        even = (d & np.uint64(1)) == 0
+        if not even.any():
+            break
+        d = np.where(even, d >> np.uint64(1), d)
+        s += even
+    res = np.ones(x.shape, bool)
+    for a in (2, 7, 61):
+        y = np.ones_like(x)
+        base = np.full_like(x, a) % x
+        e = d.copy()
+        while e.any():
+            odd = (e & np.uint64(1)) == 1
+            y = np.where(odd, (y * base) % x, y)
+            base = (base * base) % x
+            e >>= np.uint64(1)
+        ok = (y == 1) | (y == x - np.uint64(1))
+        for r in range(1, int(s.max())):
+            y = (y * y) % x
+            ok |= (y == x - np.uint64(1)) & (r < s)
+        res &= ok
+    return res
+
+
+def fast_primes(count, seed=1234):
+    """`count` random primes in [2^28, 2^30) (fixture prime pools), seeded."""
+    rng = np.random.RandomState(seed)
+    out = np.empty(0, np.int64)
+    while out.size < count:
+        cand = rng.randint(1 << 28, 1 << 30, size=(count - out.size) * 12 + 64).astype(np.int64) | 1
+        cand = cand[(cand % 3 != 0) & (cand % 5 != 0) & (cand % 7 != 0)]
+        out = np.concatenate([out, cand[_is_prime_mr(cand)]])
+    return out[:count].astype(np.int32)
+
+
 def hash_inputs(n, n_volumes, log2T, seed=0, along_rays=True):
     rng = np.random.RandomState(seed)
     local = 1 << log2T

@@ -58,7 +58,8 @@ def test_forward_backward_match_oracle(R, max_len, seed):
                                                 _lib.ptr(d_sigma), _lib.ptr(d_rgb), _lib.cur_stream()))
     rs, rc = orc.composite_backward(offsets, sigma, delta, rgb, g_rgb, g_acc)
     scale = np.abs(rs).max()
-    np.testing.assert_allclose(d_rgb.cpu().numpy(), rc, rtol=1e-5, atol=1e-7)
+    # w = alpha * exp(-prefix): the fp32 prefix sum's absolute error becomes a relative error of w deep in the ray
+    np.testing.assert_allclose(d_rgb.cpu().numpy(), rc, rtol=1e-5, atol=1e-6 * np.abs(rc).max())
     # d_sigma is a difference of two sums: 1e-5 relative to the ray's gradient scale
     assert np.all(np.abs(d_sigma.cpu().numpy() - rs) <= 1e-5 * np.abs(rs) + 2e-6 * scale)
 
@@ -107,7 +108,7 @@ def test_against_torch_autograd_of_reference_formula():
                                                 _lib.ptr(got["trans"]), _lib.ptr(tg), _lib.ptr(ta), None,
                                                 _lib.ptr(d_sigma), _lib.ptr(d_rgb), _lib.cur_stream()))
     rs = sg.grad.numpy()[..., 0][m]
-    np.testing.assert_allclose(d_rgb.cpu().numpy(), cl.grad.numpy()[m], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(d_rgb.cpu().numpy(), cl.grad.numpy()[m], rtol=2e-5, atol=2e-6 * np.abs(cl.grad.numpy()).max())
     assert np.all(np.abs(d_sigma.cpu().numpy() - rs) <= 2e-5 * np.abs(rs) + 4e-6 * np.abs(rs).max())
     # weights-only call (operator API) and gradient through g_w
     w2 = torch.empty(V, device="cuda")

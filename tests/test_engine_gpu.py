@@ -39,7 +39,8 @@ def test_one_step_matches_oracle_chain():
     counts = smp["counts"]
     assert V == counts.sum()
     m = counts[:, None] > np.arange(1024)[None]
-    pts01 = ((smp["warp_pts"][m] + np.float32(1.5)) / np.float32(3.0)).astype(np.float32)
+    # (sampled_pts + 1.5) / 3.0 as torch's CUDA kernel evaluates it (x * (1/3) in fp32)
+    pts01 = ((smp["warp_pts"][m] + np.float32(1.5)) * (np.float32(1.0) / np.float32(3.0))).astype(np.float32)
     anchors = smp["anchors"][m][:, 0]
     ray_id = np.repeat(np.arange(R), counts).astype(np.int32)
     offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)

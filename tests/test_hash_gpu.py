@@ -130,6 +130,9 @@ def test_full_size_properties():
     n, n_vol = 1 << 20, 64
     core = Hash3DAnchoredCore(19, n_vol)
     core.Reset()
+    # fp16-exact, fp16-normal table entries: then x2 is exact through the fp16 shadow
+    q = core.feat_pool_.data.half().float()
+    core.feat_pool_.data.copy_(torch.where(q.abs() < 2.0 ** -13, torch.full_like(q, 2.0 ** -13), q))
     pts = (torch.rand(n, 3, device="cuda") * 0.66 + 0.17).contiguous()
     anc = torch.randint(0, n_vol, (n,), device="cuda")
     y = core.AnchoredQuery(pts, anc)

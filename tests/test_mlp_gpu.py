@@ -27,6 +27,32 @@ def make_case(n, R, seed, with_emb=True):
     return params, feat, ray_id, dirs, emb
 
 
+def emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma, d_rgb):
+    """numpy restatement of the reference field's backward (orc.mlp_backward) with fp16 rounding at the points where
+    the kernel holds fp16 (weights, activations and gradient fragments); fp32 accumulation."""
+    def split(p):
+        o, out = 0, []
+        for a, b in ((H, 32), (16, H), (H, 63), (H, H), (3, H)):
+            out.append(p[o:o + a * b].reshape(a, b)); o += a * b
+            out.append(p[o:o + a]); o += a
+        return out
+    Q = lambda x: x.astype(np.float16).astype(np.float32)
+    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = split(params)
+    x = feat.astype(np.float32)
+    h1 = Q(np.maximum(x @ Q(w0).T + b0, 0))
+    h = h1 @ Q(w1).T + b1
+    rb = orc.sh4(dirs) @ w2[:, :16].T + b2 + (emb @ w2[:, 31:].T if emb is not None else 0)
+    h2 = Q(np.maximum(Q(h)[:, 1:] @ Q(w2[:, 16:31]).T + rb[ray_id], 0))
+    h3 = Q(np.maximum(h2 @ Q(w3).T + b3, 0))
+    o = h3 @ Q(w4).T + b4
+    sg = 1 / (1 + np.exp(-o))
+    gh3 = (Q(d_rgb * sg * (1 - sg)) @ Q(w4)) * (h3 > 0)
+    gh2 = (Q(gh3) @ Q(w3)) * (h2 > 0)
+    gh = np.concatenate([(d_sigma * np.exp(np.clip(h[:, 0] + 1, -15, 15)))[:, None], Q(gh2) @ Q(w2[:, 16:31])], 1)
+    gh1 = (Q(gh) @ Q(w1)) * (h1 > 0)
+    return Q(gh1) @ Q(w0)
+
+
 def gpu_forward(params, feat, ray_id, dirs, emb):
     from gfnerf_b200 import _lib
     L, st = _lib.lib(), _lib.cur_stream()
@@ -99,9 +125,20 @@ def test_backward_matches_oracle(n, R, seed, with_emb):
     _lib.check(L.gf_mlp_ray_bias_backward(R, H, _lib.ptr(tp), _lib.ptr(td), _lib.ptr(te), _lib.ptr(d_rb),
                                           _lib.ptr(d_params), _lib.ptr(d_emb), st))
     got_dfeat = d_feat.float().cpu().numpy() / 128.0
+    # (1) against the fp32 reference: an fp16 forward flips the ReLU mask of hidden units whose pre-activation is
+    # within fp16 rounding of zero, which changes single rows by one unit's worth of gradient (any fp16 MLP does
+    # this, tcnn's included); so the per-sample gradient is gated in relative L2 on the large case.
     s = np.abs(ref_dfeat).max()
-    assert np.all(np.abs(got_dfeat - ref_dfeat) <= 1e-2 * np.abs(ref_dfeat) + 4e-3 * s), \
-        np.max(np.abs(got_dfeat - ref_dfeat)) / s
+    diff = np.abs(got_dfeat - ref_dfeat)
+    rel_l2 = np.linalg.norm(diff) / np.linalg.norm(ref_dfeat)
+    print(f"d_feat vs fp32 oracle: rel L2 {rel_l2:.2e}, max {diff.max() / s:.2e} of max")
+    if n >= 1000:
+        assert rel_l2 < 1e-2
+    # (2) against the same reference with the kernel's fp16 quantisation points emulated in numpy: tight
+    emu = emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma * 8192.0, d_rgb * 8192.0) / 8192.0
+    d2 = np.abs(got_dfeat - emu)
+    print(f"d_feat vs fp16-emulating oracle: max {d2.max() / s:.2e} of max")
+    assert np.all(d2 <= 2e-3 * np.abs(emu) + 2e-3 * s + 2.0 ** -24 / 128)
     got = d_params.cpu().numpy().astype(np.float64)
     names = [("w0", 0, 2048), ("b0", 2048, 2112), ("w1", 2112, 3136), ("b1", 3136, 3152), ("w2", 3152, 7184),
              ("b2", 7184, 7248), ("w3", 7248, 11344), ("b3", 11344, 11408), ("w4", 11408, 11600), ("b4", 11600, 11603)]

@@ -78,7 +78,7 @@ def test_rays_that_miss_and_empty_batch():
     rig = load_rig("rig8")
     s = make_sampler(rig, mode=1)
     # rays far outside the root box pointing away: no intersection at all (the reference reads OOB here)
-    o = np.array([[600., 600., 600.], [0., 0., 2.]], np.float32)
+    o = np.array([[600., 600., 600.], [0.3, 0.2, 2.]], np.float32)
     d = np.array([[1., 0., 0.], [0., 0., -1.]], np.float32)
     out = s.GetSamples(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda())
     se = out[6].cpu().numpy()
