@@ -50,7 +50,23 @@ def emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma, d_rgb):
     gh2 = (Q(gh3) @ Q(w3)) * (h2 > 0)
     gh = np.concatenate([(d_sigma * np.exp(np.clip(h[:, 0] + 1, -15, 15)))[:, None], Q(gh2) @ Q(w2[:, 16:31])], 1)
     gh1 = (Q(gh) @ Q(w1)) * (h1 > 0)
-    return Q(gh1) @ Q(w0)
+    go = Q(d_rgb * sg * (1 - sg))
+    # weight gradients from the fp16 gradient / activation tiles (fp32 accumulate); W2's SH / emb columns and b2 come
+    # from the fp32 per-ray sums of g h2
+    R = dirs.shape[0]
+    G = np.zeros((R, H), np.float64)
+    np.add.at(G, ray_id, gh2.astype(np.float64))
+    per_ray_in = np.concatenate([orc.sh4(dirs), np.zeros((R, 15), np.float32), emb if emb is not None else np.zeros((R, 32), np.float32)], 1)
+    dw2 = G.T @ per_ray_in
+    dw2[:, 16:31] = Q(gh2).T.astype(np.float64) @ Q(h)[:, 1:]
+    dp = np.concatenate([
+        (Q(gh1).T.astype(np.float64) @ x).reshape(-1), Q(gh1).sum(0, dtype=np.float64),
+        (Q(gh).T.astype(np.float64) @ h1).reshape(-1), Q(gh).sum(0, dtype=np.float64),
+        dw2.reshape(-1), G.sum(0),
+        (Q(gh3).T.astype(np.float64) @ h2).reshape(-1), Q(gh3).sum(0, dtype=np.float64),
+        (go.T.astype(np.float64) @ h3).reshape(-1), go.sum(0, dtype=np.float64)])
+    demb = G @ w2[:, 31:].astype(np.float64) if emb is not None else None
+    return Q(gh1) @ Q(w0), dp, demb
 
 
 def gpu_forward(params, feat, ray_id, dirs, emb):
@@ -135,7 +151,8 @@ def test_backward_matches_oracle(n, R, seed, with_emb):
     if n >= 1000:
         assert rel_l2 < 1e-2
     # (2) against the same reference with the kernel's fp16 quantisation points emulated in numpy: tight
-    emu = emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma * 8192.0, d_rgb * 8192.0) / 8192.0
+    emu, emu_dp, emu_demb = emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma * 8192.0, d_rgb * 8192.0)
+    emu, emu_dp = emu / 8192.0, emu_dp / 8192.0
     d2 = np.abs(got_dfeat - emu)
     print(f"d_feat vs fp16-emulating oracle: max {d2.max() / s:.2e} of max")
     assert np.all(d2 <= 2e-3 * np.abs(emu) + 2e-3 * s + 2.0 ** -24 / 128)
@@ -143,14 +160,20 @@ def test_backward_matches_oracle(n, R, seed, with_emb):
     names = [("w0", 0, 2048), ("b0", 2048, 2112), ("w1", 2112, 3136), ("b1", 3136, 3152), ("w2", 3152, 7184),
              ("b2", 7184, 7248), ("w3", 7248, 11344), ("b3", 11344, 11408), ("w4", 11408, 11600), ("b4", 11600, 11603)]
     for name, a, b in names:
-        r, g = ref_dparams[a:b], got[a:b]
+        r, e, g = ref_dparams[a:b], emu_dp[a:b], got[a:b]
         sc = np.abs(r).max() + 1e-30
-        err = np.max(np.abs(g - r)) / sc
-        print(f"d_{name}: max err / max |ref| = {err:.2e}")
-        assert err < 1e-2, name
+        err_ref, err_emu = np.max(np.abs(g - r)) / sc, np.max(np.abs(g - e)) / sc
+        l2 = np.linalg.norm(g - r) / (np.linalg.norm(r) + 1e-30)
+        print(f"d_{name}: vs fp32 oracle max {err_ref:.2e} / rel L2 {l2:.2e}; vs fp16-emulating oracle max {err_emu:.2e}")
+        assert err_emu < 2e-3, name           # the kernel computes exactly the fp16-MLP gradient
+        if n >= 1000:
+            assert l2 < 3e-2, name            # fp16 weight rounding flips ~1e-3 of the ReLU masks: 1-2 % in rel. L2
     if with_emb:
         sc = np.abs(ref_demb).max()
-        assert np.max(np.abs(d_emb.cpu().numpy() - ref_demb)) / sc < 1e-2
+        got_e = d_emb.cpu().numpy()
+        assert np.max(np.abs(got_e - emu_demb / 8192.0)) / sc < 2e-3
+        if n >= 1000:
+            assert np.linalg.norm(got_e - ref_demb) / np.linalg.norm(ref_demb) < 3e-2
     else:
         w2g = got[3152:7184].reshape(64, 63)
         assert not w2g[:, 31:].any()        # no embedding: those columns get no gradient
