@@ -20,8 +20,8 @@
  * (-fmad=true, its default and the reference's build) applies to the
  * reference's expression order -- verified for the hash blend by compiling the
  * expression with nvcc 12.9 (DESIGN.md "FMA convention"): a*b + c*d + e*f ...
- * becomes t = c*d; t = fma(a,b,t); t = fma(e,f,t) ...  Dot products written by
- * Eigen in the reference are restated as sequential FMA chains in index order.
+ * becomes t = c*d; t = fma(a,b,t); t = fma(e,f,t) ...  Fixed-size Eigen products of
+ * the reference follow Eigen 3.4's evaluation order (see the PersSampler section).
  * Build with -ffp-contract=off so that only the explicit fmaf() calls fuse.
  *
  * Reference paths below are relative to gfnerf/bindings/ unless they start with
@@ -325,13 +325,27 @@ static inline float norm3(float x, float y, float z) {
   return sqrtf(fmaf(x, x, fmaf(y, y, z * z)));
 }
 
-/* W_i (2x4) * [xyz;1], PersSampler_cuda.cu:163,178 */
+/*
+ * Evaluation order of the reference's fixed-size Eigen expressions (Eigen 3.4.0, scalar device path;
+ * restated from the structure of Eigen's Redux.h / ProductEvaluators.h / GeneralProduct.h, from memory --
+ * Eigen itself is not in this image, so this stays part of "PARITY UNPINNED"):
+ *   - small products (2x4 * 4x1, 1x2 * 2x3, 3x3 * 3x1, and 3x12 * 12x3 which falls under
+ *     EIGEN_GEMM_TO_COEFFBASED_THRESHOLD) are coefficient-based: lhs.row(i).cwiseProduct(rhs.col(j)).sum(),
+ *     and a fully unrolled sum() splits its range in halves recursively (redux_novec_unroller):
+ *       len 2: a0 + a1;  len 3: a0 + (a1 + a2);  len 4: (a0 + a1) + (a2 + a3);
+ *       len 12: ((a0 + (a1 + a2)) + (a3 + (a4 + a5))) + ((a6 + (a7 + a8)) + (a9 + (a10 + a11)))
+ *   - 3x12 * 12x1 (depth 12 > 8 with a vector rhs) is a GEMV: sequential accumulation over k from 0.
+ * nvcc contraction (-fmad=true) of every `product + product` is  t = second product (rounded); fma(first, t),
+ * of `product + sum` is fma(product, sum)  -- the rule verified for the hash blend (DESIGN.md "FMA convention").
+ */
+
+/* W_i (2x4) * [xyz;1], PersSampler_cuda.cu:163,178 : (w0 x + w1 y) + (w2 z + w3 * 1) */
 static inline void proj_xz(const float w[2][4], const float* p, float* xz) {
   for (int r = 0; r < 2; r++)
-    xz[r] = fmaf(w[r][2], p[2], fmaf(w[r][1], p[1], fmaf(w[r][0], p[0], w[r][3])));
+    xz[r] = fmaf(w[r][0], p[0], w[r][1] * p[1]) + fmaf(w[r][2], p[2], w[r][3]);
 }
 
-/* QueryFrameTransform, PersSampler_cuda.cu:155-170 */
+/* QueryFrameTransform, PersSampler_cuda.cu:155-170 (weight * transed_vals: GEMV, sequential) */
 static inline void query_frame_transform(const trans_info* tr, const float* p, float* out) {
   float v[N_PROS];
   for (int i = 0; i < N_PROS; i++) {
@@ -346,7 +360,12 @@ static inline void query_frame_transform(const trans_info* tr, const float* p, f
   }
 }
 
-/* QueryFrameTransformJac, PersSampler_cuda.cu:172-188 */
+/* a0 + (a1 + a2) with a_k = w[k] * t[k*stride] */
+static inline float tri_sum(const float* w, const float* t, int stride) {
+  return fmaf(w[0], t[0], fmaf(w[1], t[stride], w[2] * t[2 * stride]));
+}
+
+/* QueryFrameTransformJac, PersSampler_cuda.cu:172-188 (weight * transed_jac: coefficient-based, tree sum) */
 static inline void query_frame_transform_jac(const trans_info* tr, const float* p, float jac[3][3]) {
   float tj[N_PROS][3];
   for (int i = 0; i < N_PROS; i++) {
@@ -354,13 +373,14 @@ static inline void query_frame_transform_jac(const trans_info* tr, const float* 
     proj_xz(tr->w2xz[i], p, xz);
     float dv0 = 1.f / xz[1];
     float dv1 = -xz[0] / (xz[1] * xz[1]);
-    for (int c = 0; c < 3; c++) tj[i][c] = fmaf(dv1, tr->w2xz[i][1][c], dv0 * tr->w2xz[i][0][c]);
+    for (int c = 0; c < 3; c++) tj[i][c] = fmaf(dv0, tr->w2xz[i][0][c], dv1 * tr->w2xz[i][1][c]);
   }
   for (int r = 0; r < 3; r++)
     for (int c = 0; c < 3; c++) {
-      float acc = tr->weight[r][0] * tj[0][c];
-      for (int k = 1; k < N_PROS; k++) acc = fmaf(tr->weight[r][k], tj[k][c], acc);
-      jac[r][c] = acc;
+      const float* w = tr->weight[r];
+      float q0 = tri_sum(w, &tj[0][c], 3), q1 = tri_sum(w + 3, &tj[3][c], 3);
+      float q2 = tri_sum(w + 6, &tj[6][c], 3), q3 = tri_sum(w + 9, &tj[9][c], 3);
+      jac[r][c] = (q0 + q1) + (q2 + q3);
     }
 }
 
@@ -420,7 +440,7 @@ void orc_sampler_get_samples(int64_t n_rays, const float* rays_o, const float* r
           float jac[3][3];
           query_frame_transform_jac(tr, cur_xyz, jac);
           float proj[3];
-          for (int r = 0; r < 3; r++) proj[r] = fmaf(jac[r][2], d[2], fmaf(jac[r][1], d[1], jac[r][0] * d[0]));
+          for (int r = 0; r < 3; r++) proj[r] = fmaf(jac[r][0], d[0], fmaf(jac[r][1], d[1], jac[r][2] * d[2]));   /* len 3: a0 + (a1 + a2) */
           float pn = norm3(proj[0], proj[1], proj[2]) + 1e-6f;
           float exp_march_step_warp = sample_l * rn[pts_ptr];
           exp_march_step = exp_march_step_warp / pn;
