@@ -120,7 +120,7 @@ typedef struct {
   int32_t* counts;       /* [R] samples per ray (always written) */
   float* first_oct_dis;  /* [R] */
   int32_t* n_oct;        /* [R] leaves intersected per ray, or NULL */
-  void* packed;          /* [R,1024] 32-byte records {warp xyz, t | dist, trans_idx, node_idx, 0}
+  void* packed;          /* [R,1024] 32-byte records {warp x, y, z, unused | t, dist, trans_idx, node_idx}
                             (two float4, ints stored bit-wise) for gf_sampler_compact, or NULL */
 } gf_sampler_out;
 
