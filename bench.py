@@ -211,8 +211,7 @@ def main():
     sampler.ray_march_fineness_ = 1.0
     eng = GFNeRFEngine(sampler, log2_table_size=LOG2T, num_images=rig["c2w"].shape[0], seed=0, dist_group=group)
     if world > 1:    # identical parameters on every rank
-        for t in (eng.enc.feat_pool_.data, eng.enc.prim_pool_, eng.mlp, eng.emb):
-            dist.broadcast(t, 0)
+        eng.sync.broadcast_([eng.enc.feat_pool_.data, eng.enc.prim_pool_, eng.mlp, eng.emb])
         eng.enc.shadow(force=True)
 
     host = make_batches(rig, RAYS_PER_GPU, N_BATCHES, seed=1234 + rank)
@@ -237,12 +236,14 @@ def main():
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
+        eng.flush()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        eng.flush()            # the last step's (deferred, N > 1) optimizer step belongs to the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

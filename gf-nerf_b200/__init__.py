@@ -7,5 +7,10 @@ from . import _lib  # noqa: F401
 from .hash_3d_anchored import Hash3DAnchored, Hash3DAnchoredCore  # noqa: F401
 from .perssampler import PersSampler, PersSamplerCore  # noqa: F401
 from .engine import GFNeRFEngine  # noqa: F401
+from .field import FieldHeadNames, GFNeRFField  # noqa: F401
+from .mlp import MLPNetwork  # noqa: F401
+from .model import GFNeRFModel  # noqa: F401
+from .rays import Frustums, RayBundle, RaySamples, WarpedSamples  # noqa: F401
+from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer  # noqa: F401
 
 __version__ = "0.1.0"

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .ddp import FlatBucket, GradSync
 from .hash_3d_anchored import Hash3DAnchoredCore
 from .perssampler import CompactSamples, PersSamplerCore
 
@@ -46,9 +47,9 @@ def init_mlp_params(hidden: int = HIDDEN, generator: torch.Generator = None, dev
 class _Adam:
     """State of gf_adam_step for one flat fp32 tensor."""
 
-    def __init__(self, param: torch.Tensor, lr: float, eps: float = 1e-15, betas=(0.9, 0.999)):
+    def __init__(self, param: torch.Tensor, lr: float, eps: float = 1e-15, betas=(0.9, 0.999), grad=None):
         self.param, self.lr, self.eps, self.betas = param, lr, eps, betas
-        self.grad = torch.zeros_like(param)
+        self.grad = torch.zeros_like(param) if grad is None else grad
         self.m = torch.zeros_like(param)
         self.v = torch.zeros_like(param)
         self.t = 0
@@ -90,14 +91,19 @@ class GFNeRFEngine:
         self.emb = (torch.randn(num_images, APPEARANCE_DIM, generator=gen).to(self.device)
                     if use_appearance_embedding else None)
         self.opt_table = _Adam(self.enc.feat_pool_.detach().view(-1), lr_table)
-        self.opt_mlp = _Adam(self.mlp, lr_mlp)
-        self.opt_emb = _Adam(self.emb.view(-1), lr_mlp) if self.emb is not None else None
+        # MLP + embedding gradients live in one flat bucket: one collective for both
+        small = FlatBucket([self.mlp.shape] + ([self.emb.shape] if self.emb is not None else []), device=self.device)
+        self.opt_mlp = _Adam(self.mlp, lr_mlp, grad=small.views[0])
+        self.opt_emb = _Adam(self.emb.view(-1), lr_mlp, grad=small.views[1].view(-1)) if self.emb is not None else None
+        self._small_grads = small.flat
         self.enc.shadow(force=True)
-        self.group = dist_group
-        self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
+        self.sync = GradSync(dist_group, self.device)
+        self.world = self.sync.world
+        if self.world > 1:
+            sampler.vote_reduce = self.sync.max_
         self._ws = {}
         self.step_count = 0
-        self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._deferred = None   # lr_scale of an optimizer step whose gradient reduce is still in flight
 
     # ---- per-stage device timing (bench / profiling only) -----------------------------------
     def enable_timers(self, on: bool = True):
@@ -190,6 +196,7 @@ class GFNeRFEngine:
         """Forward-only (eval) pass: GFNeRFModel.get_outputs without the training feedback."""
         with torch.cuda.device(self.device):
             cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise)
+            self.flush()
             _, sigma, rgb, _ = self._field_forward(cs, self._ray_emb(rel_camera_indices))
             out_rgb, depth, acc, _, _, _ = self._composite(cs, sigma, rgb, keep=False)
             # RGBRenderer in eval mode: nan_to_num + clamp (renderers.py:131-137)
@@ -204,6 +211,7 @@ class GFNeRFEngine:
             st = _lib.cur_stream()
             step = self.step_count
             cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise)
+            self.flush()   # a deferred optimizer step of the previous iteration lands here
             cap, R = cs.pts01.shape[0], cs.n_rays
             ray_emb = self._ray_emb(rel_camera_indices)
             feat, sigma, rgb, ray_bias = self._field_forward(cs, ray_emb)
@@ -215,6 +223,12 @@ class GFNeRFEngine:
             with self._stage("loss"):
                 _lib.check(L.gf_charbonnier(R, _lib.ptr(out_rgb), _lib.ptr(target), 1e-6,
                                             _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_charbonnier")
+            # training feedback (gfnerf/nerfacto.py:598-616).  It only needs the forward's weights, so it is issued
+            # here: its (tiny) MAX all-reduce over ranks must not queue behind the gradient all-reduce below
+            if update_octree:
+                with self._stage("octree_vote"):
+                    self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
+                    self.sampler.UpdateRayMarch(step)
             # backward
             d_sigma = self._buf("d_sigma", (cap,), torch.float32)
             d_rgb = self._buf("d_rgb", (cap, 3), torch.float32)
@@ -244,27 +258,29 @@ class GFNeRFEngine:
                                          d_n_ptr=cs.total)
             if optimizer_step:
                 self._reduce_and_step(lr_scale)
-            if update_octree:
-                with self._stage("octree_vote"):
-                    self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
-                    self.sampler.UpdateRayMarch(step)
             self.step_count += 1
         return StepOutputs(out_rgb, depth, acc, loss, cs.total)
 
     def _reduce_and_step(self, lr_scale: float):
         """DDP semantics (mean over ranks) for ALL parameters -- including the hash table, which the reference's
-        DDP wrapper silently skips because feat_pool is not a registered nn.Parameter."""
+        DDP wrapper silently skips because feat_pool is not a registered nn.Parameter.
+        With more than one rank the all-reduce is launched on the comm stream and the Adam step is DEFERRED to the
+        point where the parameters are next needed (after the next batch's ray sampling, which reads neither the
+        table nor the MLP), so NVLink time hides behind the sampler kernel."""
         if self.world > 1:
-            import torch.distributed as dist
-            cur = torch.cuda.current_stream(self.device)
-            # small blobs first on the compute stream's successor, the 64 MB table gradient after it
-            self.comm_stream.wait_stream(cur)
-            with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(self.opt_mlp.grad, group=self.group)
-                if self.opt_emb is not None:
-                    dist.all_reduce(self.opt_emb.grad, group=self.group)
-                dist.all_reduce(self.opt_table.grad, group=self.group)
-            cur.wait_stream(self.comm_stream)
+            self.sync.start_sum([self._small_grads, self.opt_table.grad])
+            self._deferred = lr_scale
+        else:
+            self._apply_adam(lr_scale)
+
+    def flush(self):
+        """Completes a deferred optimizer step (call before reading parameters, checkpointing or timing)."""
+        if self._deferred is not None:
+            self.sync.wait()
+            self._apply_adam(self._deferred)
+            self._deferred = None
+
+    def _apply_adam(self, lr_scale: float):
         div = float(self.world)
         with self._stage("adam_small"):
             self.opt_mlp.step(grad_div=div, lr=self.opt_mlp.lr * lr_scale)

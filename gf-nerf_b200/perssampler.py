@@ -212,13 +212,21 @@ class PersSamplerCore:
 
     # ---- training feedback (PersSampler::UpdateOctNodes, :584-677) ------------------------
     def _vote(self, n_rays, counts, offsets, c_node, weights, alphas):
+        """Vote (MarkVistNodeKernel), [MAX-reduce the votes over the data-parallel ranks], apply (stat update +
+        MarkInvalidNodes).  `vote_reduce` is set by the engine when world_size > 1; without it this is exactly
+        gf_sampler_update_oct_nodes."""
         scratch = self._buf("vote", (3 * self.n_nodes,), torch.int64)
+        L, st = _lib.lib(), _lib.cur_stream()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().gf_sampler_update_oct_nodes(
+            _lib.check(L.gf_sampler_vote(
                 n_rays, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(c_node), _lib.ptr(weights), _lib.ptr(alphas),
+                self.n_nodes, _lib.ptr(self.tree_visit_cnt_), _lib.ptr(scratch), st), "gf_sampler_vote")
+            reduce = getattr(self, "vote_reduce", None)
+            if reduce is not None:
+                reduce([scratch, self.tree_visit_cnt_])
+            _lib.check(L.gf_sampler_apply_votes(
                 _lib.ptr(self.tree_nodes_gpu_), self.n_nodes, _lib.ptr(self.tree_weight_stats_),
-                _lib.ptr(self.tree_alpha_stats_), _lib.ptr(self.tree_visit_cnt_), _lib.ptr(scratch),
-                _lib.cur_stream()), "gf_sampler_update_oct_nodes")
+                _lib.ptr(self.tree_alpha_stats_), _lib.ptr(scratch), st), "gf_sampler_apply_votes")
 
     def _milestones(self, iter_step: int):
         while self.sub_div_milestones_ and self.sub_div_milestones_[-1] <= iter_step:
@@ -431,14 +439,26 @@ class PersSampler(nn.Module):
 
     forward = generate_ray_samples
 
-    def update_oct_nodes(self, sampled_anchors, pts_idx_bounds, weights, alphas, step):
-        self.sampler.UpdateOctNodes(sampled_anchors, pts_idx_bounds, weights, alphas, step)
+    def update_oct_nodes(self, sampled_anchors, pts_idx_bounds, sampled_weights, sampled_alpha, iter_step):
+        self.sampler.UpdateOctNodes(sampled_anchors, pts_idx_bounds, sampled_weights, sampled_alpha, iter_step)
 
-    def update_ray_march(self, step):
-        self.sampler.UpdateRayMarch(step)
+    def update_ray_march(self, cur_step: int):
+        self.sampler.UpdateRayMarch(cur_step)
 
-    def update_mode(self, mode):
+    def update_mode(self, mode: int):
         self.sampler.UpdateMode(mode)
+
+    def update_block_idx(self, block_centers):
+        self.sampler.UpdateBlockIdxs(block_centers)
+
+    def trans_query_frame(self, world_positions_flat, anchors_flat):
+        return self.sampler.TransQueryFrame(world_positions_flat, anchors_flat)
+
+    def query_tree_nodes_centers(self, anchors):
+        return self.sampler.QueryTreeNodeCenters(anchors)
+
+    def states(self):
+        return self.sampler.States()
 
     def get_n_volumes(self):
         return self.sampler.get_n_volumes()

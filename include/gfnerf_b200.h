@@ -157,6 +157,17 @@ int gf_sampler_update_oct_nodes(int64_t n_rays, const int32_t* counts, const int
                                 int64_t* weight_stats, int64_t* alpha_stats, int64_t* visit_cnt,
                                 int64_t* scratch, void* stream);
 
+/* The two halves of gf_sampler_update_oct_nodes, for data-parallel training: every rank votes on its own rays
+ * (gf_sampler_vote fills scratch = {weight adders, alpha adders, visited mark} and atomicMax'es visit_cnt), the
+ * ranks MAX-reduce scratch and visit_cnt (the votes are atomicMax'es in the reference, so the max over ranks is
+ * what one process voting on all rays would have produced), then every rank applies the same votes
+ * (gf_sampler_apply_votes) and the replicated octrees stay identical. */
+int gf_sampler_vote(int64_t n_rays, const int32_t* counts, const int32_t* offsets, const int32_t* c_node,
+                    const float* weights, const float* alphas, int64_t n_nodes, int64_t* visit_cnt,
+                    int64_t* scratch, void* stream);
+int gf_sampler_apply_votes(void* tree_nodes, int64_t n_nodes, int64_t* weight_stats, int64_t* alpha_stats,
+                           const int64_t* scratch, void* stream);
+
 /* QueryFrameTransform for arbitrary points (TransQueryFrameKernel, :854-922) */
 int gf_sampler_trans_query_frame(int64_t n_pts, const void* tree_nodes, int64_t n_nodes,
                                  const void* pers_trans, const int64_t* anchors,

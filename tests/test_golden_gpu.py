@@ -50,8 +50,9 @@ def test_composite_matches_reference_renderers():
     close(acc, g["out_acc"], 1e-5, "accumulation")
     close(torch.minimum(depth.clamp_min(0.0), tmax), g["out_depth"], 1e-5, "depth")
     d_sigma, d_rgb = torch.empty(V, device="cuda"), torch.empty((V, 3), device="cuda")
+    g_rgb, g_acc = T(g["g_rgb"]), T(g["g_acc"])     # keep the tensors alive across the call
     _lib.check(L.gf_composite_backward(R, _lib.ptr(offsets), _lib.ptr(sigma), _lib.ptr(delta), _lib.ptr(rgb),
-                                       _lib.ptr(tr), _lib.ptr(T(g["g_rgb"])), _lib.ptr(T(g["g_acc"])), None,
+                                       _lib.ptr(tr), _lib.ptr(g_rgb), _lib.ptr(g_acc), None,
                                        _lib.ptr(d_sigma), _lib.ptr(d_rgb), st))
     close(d_sigma, g["d_sigma"][m], 2e-5, "d_sigma")
     close(d_rgb, g["d_rgb"][m], 1e-5, "d_rgb")
@@ -74,8 +75,9 @@ def test_mlp_matches_reference_mlpnetwork():
     d_params = torch.zeros(g["params"].size, device="cuda")
     d_rb = torch.zeros((R, H), device="cuda")
     d_emb = torch.zeros((R, 32), device="cuda")
+    g_sigma, g_rgb = T(g["g_sigma"]), T(g["g_rgb"])
     _lib.check(L.gf_mlp_backward(n, None, H, _lib.ptr(p), _lib.ptr(feat), _lib.ptr(ray_id), _lib.ptr(rb),
-                                 _lib.ptr(T(g["g_sigma"])), _lib.ptr(T(g["g_rgb"])), _lib.ptr(d_feat), _lib.ptr(d_params),
+                                 _lib.ptr(g_sigma), _lib.ptr(g_rgb), _lib.ptr(d_feat), _lib.ptr(d_params),
                                  _lib.ptr(d_rb), 16.0, st))
     _lib.check(L.gf_mlp_ray_bias_backward(R, H, _lib.ptr(p), _lib.ptr(dirs), _lib.ptr(emb), _lib.ptr(d_rb),
                                           _lib.ptr(d_params), _lib.ptr(d_emb), st))
@@ -91,7 +93,8 @@ def test_charbonnier_and_adam_match_reference():
     g = load("ref_loss_adam")
     R = g["pred"].shape[0]
     g_rgb, loss = torch.empty((R, 3), device="cuda"), torch.zeros(1, device="cuda")
-    _lib.check(L.gf_charbonnier(R, _lib.ptr(T(g["pred"])), _lib.ptr(T(g["target"])), 1e-6, _lib.ptr(g_rgb),
+    pred, target = T(g["pred"]), T(g["target"])
+    _lib.check(L.gf_charbonnier(R, _lib.ptr(pred), _lib.ptr(target), 1e-6, _lib.ptr(g_rgb),
                                 _lib.ptr(loss), st))
     assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
     close(g_rgb, g["g_pred"], 1e-5, "dL/drgb")

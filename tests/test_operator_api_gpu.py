@@ -1,0 +1,152 @@
+"""GPU: the nerfstudio-side operator API (PersSampler module -> GFNeRFField -> RaySamples.get_weights_f2nerf ->
+renderers, i.e. GFNeRFModel.get_outputs of gfnerf/nerfacto.py:522-619 on dense [R,1024] tensors with torch autograd)
+against the fused engine on the same rays and parameters; the focal (block) stage; state-dict compatibility."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_rig, make_sampler, rig_octree
+
+pytestmark = pytest.mark.gpu
+
+
+def build(rig, log2T=14, seed=0):
+    import gfnerf_b200 as gf
+    from gfnerf_b200.engine import GFNeRFEngine
+    eng = GFNeRFEngine(make_sampler(rig, mode=1), log2_table_size=log2T, num_images=rig["c2w"].shape[0], seed=seed)
+    eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
+    eng.enc.shadow(force=True)
+    ps = gf.PersSampler(rig["c2w"], rig["intri"], rig["bounds"], bbox_levels=10, mode=1, octree=rig_octree(rig))
+    field = gf.GFNeRFField(torch.zeros(2, 3), rig["c2w"].shape[0], log2_hashmap_size=log2T,
+                           use_appearance_embedding=True, n_volumes=eng.n_volumes).cuda()
+    # identical parameters: table, primes, MLP blob, embedding
+    field.base_encoding_init.load_states(eng.enc.States(), 0)
+    o = 0
+    for lin in field.base_network.linears() + field.mlp_head.linears():
+        for p in (lin.weight, lin.bias):
+            p.data.copy_(eng.mlp[o:o + p.numel()].view_as(p))
+            o += p.numel()
+    assert o == eng.mlp.numel()
+    field.embedding_appearance.embedding.weight.data.copy_(eng.emb)
+    model = gf.GFNeRFModel(ps, field).cuda()
+    return eng, model
+
+
+def bundle(rig, R, seed):
+    import gfnerf_b200 as gf
+    from gfnerf_b200.persoctree import rig_rays
+    o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=seed)
+    T = lambda a: torch.from_numpy(a).cuda()
+    rb = gf.RayBundle(origins=T(o), directions=T(d), lookat_directions=T(d), pixel_area=torch.ones(R, 1).cuda(),
+                      camera_indices=T(cam).view(-1, 1), rel_camera_indices=T(cam).view(-1, 1),
+                      steps=torch.zeros(R, 1).cuda())
+    return rb, T(o), T(d), T(cam)
+
+
+def test_operator_path_equals_fused_engine():
+    rig = load_rig("rig8")
+    eng, model = build(rig)
+    R = 384
+    rb, o, d, cam = bundle(rig, R, seed=5)
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    # fused engine: forward + backward, no optimizer step
+    out = eng.train_step(o, d, target, cam, optimizer_step=False, update_octree=False)
+    # operator API with autograd
+    model.eval()                       # no octree feedback; renderers differ only by the eval clamp
+    res = model.get_outputs(rb)
+    assert res["rgb"].shape == (R, 3) and res["depth"].shape == (R, 1) and res["accumulation"].shape == (R, 1)
+    assert torch.allclose(res["rgb"], out.rgb.clamp(0, 1), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(res["accumulation"][:, 0], out.accumulation, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(res["depth"][:, 0], out.depth, rtol=1e-4, atol=1e-5)
+    assert float(res["oct_depth"].min()) > 0
+    model.train()
+    model.persampler.sampler.UpdateMode(1)
+    rb.steps = None                    # keeps the octree untouched in train mode
+    res = model.get_outputs(rb)
+    diff = res["rgb"] - target
+    loss = torch.sqrt(diff * diff + 1e-12).sum() / R          # CharbonnierLoss, losses.py:73-84
+    loss.backward()
+    assert abs(float(loss) - float(out.loss)) < 1e-4 * float(out.loss)
+    f = model.field
+    g_table = f.base_encoding_init.hash_3d.feat_pool_.grad
+    ref = eng.opt_table.grad.view_as(g_table)
+    assert float((g_table - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    got = torch.cat([torch.cat([l.weight.grad.reshape(-1), l.bias.grad.reshape(-1)])
+                     for l in f.base_network.linears() + f.mlp_head.linears()])
+    assert float((got - eng.opt_mlp.grad).abs().max()) <= 2e-3 * float(eng.opt_mlp.grad.abs().max())
+    ge = f.embedding_appearance.embedding.weight.grad
+    assert float((ge - eng.opt_emb.grad.view_as(ge)).abs().max()) <= 2e-3 * float(eng.opt_emb.grad.abs().max())
+
+
+def test_block_stage_trains_only_the_residual_table():
+    rig = load_rig("rig8")
+    _, model = build(rig)
+    f = model.field
+    R = 256
+    rb, *_ = bundle(rig, R, seed=9)
+    rb.steps = None
+    model.train()
+    base = model.get_outputs(rb)["rgb"].detach()
+    f.add_table(3)
+    f.set_stage("block_stage", active_block=3)
+    # a zero residual table leaves the output unchanged (nerfacto_field.py:477-489)
+    out = model.get_outputs(rb)["rgb"]
+    assert torch.equal(out.detach(), base)
+    out.sum().backward()
+    res = f.base_encoding_3.hash_3d.feat_pool_
+    assert res.grad is not None and float(res.grad.abs().max()) > 0
+    assert f.base_encoding_init.hash_3d.feat_pool_.grad is None
+    assert all(l.weight.grad is None for l in f.base_network.linears() + f.mlp_head.linears())
+    assert f.embedding_appearance.embedding.weight.grad is None
+    # a non-zero residual changes the result
+    res.data.uniform_(-0.3, 0.3)
+    assert not torch.equal(model.get_outputs(rb)["rgb"].detach(), base)
+    # table swap to disk and back (save_table / del_table / load_table, nerfacto_field.py:310-403)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        from pathlib import Path
+        f.encodings_ckpt_dir = Path(d)
+        keep = res.detach().clone()
+        f.save_table(3)
+        f.del_table(3)
+        assert not hasattr(f, "base_encoding_3")
+        f.load_table(3)
+        assert torch.equal(f.base_encoding_3.hash_3d.feat_pool_.detach(), keep)
+
+
+def test_state_dict_keys_match_reference_names():
+    rig = load_rig("rig8")
+    _, model = build(rig)
+    keys = set(model.state_dict().keys())
+    for k in ("field.base_network.model.0.weight", "field.base_network.model.2.bias", "field.mlp_head.model.4.weight",
+              "field.embedding_appearance.embedding.weight", "field.base_encoding_init.feat_pool",
+              "field.base_encoding_init.prime_pool", "field.base_encoding_init.bias_pool",
+              "field.base_encoding_init.n_volumes", "persampler.tree_nodes_gpu", "persampler.pers_trans_gpu",
+              "persampler.tree_visit_cnt", "persampler.milestones_ts"):
+        assert k in keys, (k, sorted(keys))
+
+
+def test_get_weights_f2nerf_matches_torch_formula_with_autograd():
+    import gfnerf_b200 as gf
+    R, S = 37, 1024
+    g = torch.Generator().manual_seed(0)
+    counts = torch.randint(0, S + 1, (R,), generator=g)
+    mask = (torch.arange(S)[None] < counts[:, None]).float()
+    delta = (torch.rand(R, S, generator=g) * 0.02 * mask).cuda().unsqueeze(-1)
+    dens = (torch.rand(R, S, generator=g) * 30).cuda().unsqueeze(-1).requires_grad_(True)
+    z = torch.zeros(R, S, 3).cuda()
+    rs = gf.RaySamples(frustums=gf.Frustums(z, z, delta, delta), deltas=delta)
+    w, a, T = rs.get_weights_f2nerf(dens)
+    gw = torch.randn(R, S, 1, generator=g).cuda()
+    (w * gw).sum().backward()
+    got = dens.grad.clone()
+    dens.grad = None
+    dd = delta * dens                                          # nerfstudio/cameras/rays.py:188-200
+    al = 1 - torch.exp(-dd)
+    tr = torch.cumsum(dd[..., :-1, :], dim=-2)
+    tr = torch.exp(-torch.cat([torch.zeros(R, 1, 1).cuda(), tr], dim=-2))
+    w_ref = torch.nan_to_num(al * tr)
+    (w_ref * gw).sum().backward()
+    assert torch.allclose(w, w_ref, rtol=1e-5, atol=1e-7) and torch.allclose(a, al, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(T, tr, rtol=1e-5, atol=1e-7)
+    assert float((got - dens.grad).abs().max()) <= 1e-5 * float(dens.grad.abs().max())
