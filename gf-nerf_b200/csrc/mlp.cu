@@ -25,6 +25,8 @@
 //
 // Weights are fp16 in shared memory (converted from the fp32 blob at kernel start), fp32
 // accumulation: the "fp16 MLP" precision class of the north star (1e-2 relative).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gf {
@@ -704,6 +706,9 @@ mlp_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __re
 
 using namespace gf;
 
+int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
+                         const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, cudaStream_t st);
+
 extern "C" {
 
 int64_t gf_mlp_param_count(int hidden) { return hidden == kH ? (int64_t)kParamCount : -1; }
@@ -738,6 +743,10 @@ int gf_mlp_forward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* p
   GF_REQUIRE(n >= 0, "gf_mlp_forward: bad sizes");
   if (n == 0) return GF_OK;
   GF_REQUIRE(params && feat_f16 && ray_id && ray_bias && sigma && rgb, "gf_mlp_forward: null pointer");
+  // GF_MLP_TC=0 selects the mma.sync kernel (profiling A/B only); default: tcgen05 / TMEM kernel (mlp_tc.cu)
+  static const int use_tc = [] { const char* e = getenv("GF_MLP_TC"); return e ? atoi(e) : 1; }();
+  if (use_tc)
+    return gf_launch_mlp_fwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, sigma, rgb, (cudaStream_t)stream);
   constexpr int MT = 2;
   const int64_t tiles = div_up(n, 16 * MT);
   const int grid = (int)std::min<int64_t>(div_up(tiles, kFwdBlock / 32), (int64_t)sm_count() * 2);
