@@ -709,6 +709,10 @@ using namespace gf;
 int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
                          const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, cudaStream_t st);
 
+int gf_launch_mlp_bwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
+                         const int32_t* ray_id, const float* ray_bias, const float* d_sigma, const float* d_rgb,
+                         void* d_feat, float* d_params, float* d_ray_bias, float gscale, cudaStream_t st);
+
 extern "C" {
 
 int64_t gf_mlp_param_count(int hidden) { return hidden == kH ? (int64_t)kParamCount : -1; }
@@ -765,6 +769,10 @@ int gf_mlp_backward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* 
              "gf_mlp_backward: null pointer");
   GF_REQUIRE((d_params == nullptr) == (d_ray_bias == nullptr),
              "gf_mlp_backward: d_params and d_ray_bias go together (both NULL = frozen MLP)");
+  static const int use_tc = [] { const char* e = getenv("GF_MLP_TC"); return e ? atoi(e) : 1; }();
+  if (use_tc)
+    return gf_launch_mlp_bwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, d_sigma, d_rgb, d_feat_scaled_f16,
+                                d_params, d_ray_bias, grad_scale, (cudaStream_t)stream);
   static bool attr_set = false;
   if (!attr_set) {
     GF_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));

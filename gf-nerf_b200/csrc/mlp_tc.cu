@@ -85,13 +85,17 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ p, unsig
   }
 }
 
-// one layer: D[kColD .. +N) = A[kColA .. +K/2) . B^T, K/16 MMAs, then commit to the mbarrier
+// one layer: D[kColD .. +N) = A[kColA .. +K/2) . B^T as K/16 MMAs (the caller commits)
 template <int N, int K>
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_smem, uint32_t bar) {
+__device__ __forceinline__ void issue_fwd(uint32_t tmem, uint32_t b_smem) {
   constexpr uint32_t idesc = instr_desc(kTile, N);
 #pragma unroll
   for (int k = 0; k < K / 16; k++)
     mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc(b_smem + 2 * k * kLbo, kLbo, sbo_of(K)), idesc, k > 0);
+}
+template <int N, int K>
+__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_smem, uint32_t bar) {
+  issue_fwd<N, K>(tmem, b_smem);
   mma_commit(bar);
 }
 
@@ -270,6 +274,422 @@ mlp_fwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
+
+// =============================================================================================================
+// backward
+// =============================================================================================================
+// 256 threads per CTA: thread (warp w, lane l) is row 32 (w & 3) + l of the tile (its TMEM lane) and owns the column
+// half hf = w >> 2 of every 64-wide activation / gradient matrix.  Per tile: the five forward layers are recomputed
+// (the post-ReLU activations stay in registers as the ReLU masks), then five dgrad layers run as TS-form MMAs whose A
+// operand is the gradient the previous epilogue wrote to TMEM and whose B operand is the SAME shared-memory weight
+// tile as the forward, read transposed through an MN-major descriptor.
+// Weight gradients (WGRAD): every activation / gradient tile is also written to shared memory ([sample][feature]
+// fp16, core-matrix layout) and dW = G^T . ACT is an SS-form MMA with BOTH operands MN-major (K = the 128 samples),
+// accumulating over all tiles of the CTA in TMEM; bias gradients ride along as an extra all-ones feature column of
+// the activation tiles.  tcgen05.commit covers every MMA issued before it, so a tile buffer is free again one
+// dgrad round after the weight-gradient MMAs that read it were issued: G3 / G2 / G1 / Gh reuse the H3 / H2 / H1 /
+// Go buffers.  One atomicAdd per parameter per CTA at the end.
+//
+// TMEM columns (WGRAD): D 0..63 | A 64..95 | dW3' 96..167 (64 x 72) | dW0' 168..207 (64 x 40) | dW2g 208..223
+// (64 x 16) | dW1^T 224..239 (128 x 16) | dW4^T 240..255 (128 x 16)  = 256 -> two CTAs per SM.
+constexpr int kBwdThreads = 256;
+constexpr uint32_t kColW3 = 96, kColW0 = 168, kColW2 = 208, kColW1 = 224, kColW4 = 240;
+constexpr uint32_t kOffRay = 19200;                     // int32 ray id of each row
+constexpr uint32_t kOffX = kOffRay + 512;                // [128][32 + 8]   SBO 640
+constexpr uint32_t kSboX = 640, kSboH = 1152, kSboG = 1024, kSboS = 256;
+constexpr uint32_t kOffH1 = kOffX + 16 * kSboX;          // [128][64 + 8]   SBO 1152 (G1 reuses it with SBO 1024)
+constexpr uint32_t kOffH2 = kOffH1 + 16 * kSboH;
+constexpr uint32_t kOffH3 = kOffH2 + 16 * kSboH;
+constexpr uint32_t kOffHh = kOffH3 + 16 * kSboH;         // [128][16]       SBO 256
+constexpr uint32_t kOffGo = kOffHh + 16 * kSboS;         // [128][16]       SBO 256 (Gh reuses it)
+constexpr uint32_t kBwdSmem = kOffGo + 16 * kSboS + 1024;  // + slack: the M = 128 reads of H3' run past the tile
+static_assert(kOffRay >= kFwdSmem && kOffX % 128 == 0, "backward smem layout");
+
+// 16-byte chunk j (features 8 j .. 8 j + 7) of row r of a [sample][feature] tile
+__device__ __forceinline__ uint4* tile_chunk(unsigned char* buf, uint32_t sbo, int r, int j) {
+  return reinterpret_cast<uint4*>(buf + (r >> 3) * sbo + j * 128 + (r & 7) * 16);
+}
+template <int NCH>
+__device__ __forceinline__ void store_chunks(unsigned char* buf, uint32_t sbo, int r, int j0, const uint32_t* a) {
+#pragma unroll
+  for (int q = 0; q < NCH; q++)
+    *tile_chunk(buf, sbo, r, j0 + q) = make_uint4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+}
+__device__ __forceinline__ void store_ones(unsigned char* buf, uint32_t sbo, int r, int j) {
+  *tile_chunk(buf, sbo, r, j) = make_uint4(0x00003C00u, 0u, 0u, 0u);  // feature 8 j = 1.0, the rest 0
+}
+
+// gradient accumulators (fp32 bits in v[0..32)) masked by relu'(h) (h as 16 packed fp16 pairs) -> 16 packed pairs
+__device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const uint32_t (&h)[16], uint32_t (&out)[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const float lo = (h[q] & 0xFFFFu) ? __uint_as_float(v[2 * q]) : 0.f;
+    const float hi = (h[q] >> 16) ? __uint_as_float(v[2 * q + 1]) : 0.f;
+    out[q] = pack_h2(lo, hi);
+  }
+}
+
+// dgrad layer: D[128 x N] = G[128 x K] (TMEM) . W[K x N], W = the forward tile [K = out][N = in] read MN-major
+template <int N, int K>
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem, uint32_t w_smem, uint32_t sbo_fwd) {
+  constexpr uint32_t idesc = instr_desc(kTile, N, 0, 1);
+#pragma unroll
+  for (int k = 0; k < K / 16; k++)
+    mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc(w_smem + 2 * k * sbo_fwd, sbo_fwd, 128), idesc, k > 0);
+}
+// wgrad: D[M x N] (+)= P^T . Q over the tile's 128 samples; P, Q = [sample][feature] tiles (SBO sp / sq), MN-major
+template <int M, int N>
+__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t p_smem, uint32_t sp, uint32_t q_smem, uint32_t sq,
+                                            bool first_tile) {
+  constexpr uint32_t idesc = instr_desc(M, N, 1, 1);
+#pragma unroll
+  for (int k = 0; k < kTile / 16; k++)
+    mma_ss(d_tmem, smem_desc(p_smem + 2 * k * sp, sp, 128), smem_desc(q_smem + 2 * k * sq, sq, 128), idesc,
+           (k > 0 || !first_tile) ? 1u : 0u);
+}
+
+// publish this thread's TMEM / shared-memory writes, let one thread issue the MMAs, wait for their completion
+#define GF_TC_SYNC_ISSUE(ISSUE) \
+  tmem_wait_st();               \
+  tc_fence_before();            \
+  fence_proxy_async();          \
+  __syncthreads();              \
+  if (tid == 0) {               \
+    tc_fence_after();           \
+    ISSUE;                      \
+    mma_commit(bar);            \
+  }
+#define GF_TC_WAIT()     \
+  mbar_wait(bar, phase); \
+  phase ^= 1;            \
+  tc_fence_after();
+
+template <bool WGRAD>
+__global__ void __launch_bounds__(kBwdThreads, 2)
+mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __restrict__ params,
+                  const __half* __restrict__ feat, const int32_t* __restrict__ ray_id,
+                  const float* __restrict__ ray_bias, const float* __restrict__ d_sigma,
+                  const float* __restrict__ d_rgb, __half* __restrict__ d_feat, float* __restrict__ d_params,
+                  float* __restrict__ d_ray_bias, float gscale) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr uint32_t kCols = WGRAD ? 256u : 128u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = 32 * (warp & 3) + lane;  // row of the tile = TMEM lane
+  const int hf = warp >> 2;              // column half
+  const float inv_gscale = 1.f / gscale;
+  stage_weights(params, smem);
+  const uint32_t bar = smem_u32(smem + kOffBar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(smem_u32(smem + kOffTmem), kCols);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
+  const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t sB = smem_u32(smem);
+  const float* bs = reinterpret_cast<const float*>(smem + kOffBias);
+  int* s_ray = reinterpret_cast<int*>(smem + kOffRay);
+  if (d_n_ptr) {
+    const int64_t dn = *d_n_ptr;
+    n = dn < n ? dn : n;
+  }
+  uint32_t phase = 0;
+  bool first_tile = true;
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * kTile + r;
+    const bool valid = row < n;
+    const int ray = valid ? __ldg(ray_id + row) : -1;
+    uint32_t h1p[16], h2p[16], h3p[16];  // post-ReLU activations of this thread's column half (the ReLU masks)
+    float pre = 0.f;                      // density logit + 1 (hf == 0)
+    // ---- input: features 16 hf .. 16 hf + 15 of this row -> A columns [8 hf, 8 hf + 8) (+ X tile) -------------
+    {
+      uint32_t x[8];
+      const uint4* src = reinterpret_cast<const uint4*>(feat + row * 32 + 16 * hf);
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const uint4 u = valid ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+        x[4 * q] = u.x; x[4 * q + 1] = u.y; x[4 * q + 2] = u.z; x[4 * q + 3] = u.w;
+        if (WGRAD) *tile_chunk(smem + kOffX, kSboX, r, 2 * hf + q) = u;
+      }
+      tmem_st8(lane_addr + kColA + 8 * hf, x);
+      if (WGRAD && hf == 0) {
+        store_ones(smem + kOffX, kSboX, r, 4);
+        s_ray[r] = ray;
+      }
+    }
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 32>(tmem, sB + kOffB0)))
+    GF_TC_WAIT()
+    // ---- h1 = relu(acc + b0) -------------------------------------------------------------------------------
+    {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + kColD + 32 * hf, v);
+      tmem_wait_ld();
+      bias_relu_pack32(v, bs + 32 * hf, h1p);
+      tmem_st16(lane_addr + kColA + 16 * hf, h1p);
+      if (WGRAD) {
+        store_chunks<4>(smem + kOffH1, kSboH, r, 4 * hf, h1p);
+        if (hf == 0) store_ones(smem + kOffH1, kSboH, r, 8);
+      }
+    }
+    GF_TC_SYNC_ISSUE((issue_fwd<16, 64>(tmem, sB + kOffB1)))
+    GF_TC_WAIT()
+    // ---- h = acc + b1; density logit; geo features -> A (16 fp16) --------------------------------------------
+    if (hf == 0) {
+      uint32_t v[16], a[8];
+      tmem_ld16(lane_addr + kColD, v);
+      tmem_wait_ld();
+      float h[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) h[j] = __uint_as_float(v[j]) + bs[64 + j];
+      pre = h[0] + 1.f;
+      h[0] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] = pack_h2(h[2 * j], h[2 * j + 1]);
+      tmem_st8(lane_addr + kColA, a);
+      if (WGRAD) store_chunks<2>(smem + kOffHh, kSboS, r, 0, a);
+    }
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 16>(tmem, sB + kOffB2)))
+    const float* rb = ray_bias + (int64_t)(valid ? ray : 0) * kH + 32 * hf;
+    GF_TC_WAIT()
+    // ---- h2 = relu(acc + ray_bias[ray]) ----------------------------------------------------------------------
+    {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + kColD + 32 * hf, v);
+      tmem_wait_ld();
+      bias_relu_pack32(v, rb, h2p);
+      tmem_st16(lane_addr + kColA + 16 * hf, h2p);
+      if (WGRAD) {
+        store_chunks<4>(smem + kOffH2, kSboH, r, 4 * hf, h2p);
+        if (hf == 0) store_ones(smem + kOffH2, kSboH, r, 8);
+      }
+    }
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 64>(tmem, sB + kOffB3)))
+    GF_TC_WAIT()
+    // ---- h3 = relu(acc + b3) -------------------------------------------------------------------------------
+    {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + kColD + 32 * hf, v);
+      tmem_wait_ld();
+      bias_relu_pack32(v, bs + 80 + 32 * hf, h3p);
+      tmem_st16(lane_addr + kColA + 16 * hf, h3p);
+      if (WGRAD) {
+        store_chunks<4>(smem + kOffH3, kSboH, r, 4 * hf, h3p);
+        if (hf == 0) store_ones(smem + kOffH3, kSboH, r, 8);
+      }
+    }
+    GF_TC_SYNC_ISSUE((issue_fwd<16, 64>(tmem, sB + kOffB4)))
+    GF_TC_WAIT()
+    // ---- g o = d rgb * s (1 - s)  (all gradients carry the factor gscale while they are fp16) ------------------
+    if (hf == 0) {
+      uint32_t v[4], a[8];
+      tmem_ld4(lane_addr + kColD, v);
+      tmem_wait_ld();
+      float go[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float sg = sigmoidf_(__uint_as_float(v[c]) + bs[144 + c]);
+          go[c] = __ldg(d_rgb + 3 * row + c) * gscale * sg * (1.f - sg);
+        }
+      }
+      a[0] = pack_h2(go[0], go[1]);
+      a[1] = pack_h2(go[2], 0.f);
+#pragma unroll
+      for (int j = 2; j < 8; j++) a[j] = 0u;
+      tmem_st8(lane_addr + kColA, a);
+      if (WGRAD) store_chunks<2>(smem + kOffGo, kSboS, r, 0, a);
+    }
+    // g h3 = g o . W4 ; dW4^T (+ b4 row) += H3'^T . Go
+    GF_TC_SYNC_ISSUE((issue_dgrad<64, 16>(tmem, sB + kOffB4, sbo_of(64)),
+                      WGRAD ? issue_wgrad<128, 16>(tmem + kColW4, sB + kOffH3, kSboH, sB + kOffGo, kSboS, first_tile)
+                            : (void)0))
+    GF_TC_WAIT()
+    {
+      uint32_t v[32], g[16];
+      tmem_ld32(lane_addr + kColD + 32 * hf, v);
+      tmem_wait_ld();
+      mask_pack32(v, h3p, g);
+      tmem_st16(lane_addr + kColA + 16 * hf, g);
+      if (WGRAD) store_chunks<4>(smem + kOffH3, kSboG, r, 4 * hf, g);  // G3 over H3 (its readers have completed)
+    }
+    // g h2 = g h3 . W3 ; dW3 (+ b3 column) += G3^T . H2'
+    GF_TC_SYNC_ISSUE((issue_dgrad<64, 64>(tmem, sB + kOffB3, sbo_of(64)),
+                      WGRAD ? issue_wgrad<64, 72>(tmem + kColW3, sB + kOffH3, kSboG, sB + kOffH2, kSboH, first_tile)
+                            : (void)0))
+    GF_TC_WAIT()
+    {
+      uint32_t v[32], g[16];
+      tmem_ld32(lane_addr + kColD + 32 * hf, v);
+      tmem_wait_ld();
+      mask_pack32(v, h2p, g);
+      tmem_st16(lane_addr + kColA + 16 * hf, g);
+      if (WGRAD) store_chunks<4>(smem + kOffH2, kSboG, r, 4 * hf, g);  // G2 over H2
+    }
+    // g h[1:16] = g h2 . W2[:, geo] ; dW2[:, geo] += G2^T . Hh
+    GF_TC_SYNC_ISSUE((issue_dgrad<16, 64>(tmem, sB + kOffB2, sbo_of(16)),
+                      WGRAD ? issue_wgrad<64, 16>(tmem + kColW2, sB + kOffH2, kSboG, sB + kOffHh, kSboS, first_tile)
+                            : (void)0))
+    if (WGRAD) {
+      // d ray_bias[ray] += column sums of g h2 over the rows of that ray (rows of a ray are contiguous): thread =
+      // (column, quarter of the rows), reading the G2 tile the MMAs are reading too
+      const int c = tid & 63, q0 = 32 * (tid >> 6);
+      const unsigned char* g2 = smem + kOffH2 + (c >> 3) * 128 + (c & 7) * 2;
+      float acc = 0.f;
+      int cur = -1;
+      for (int s2 = q0; s2 < q0 + 32; s2++) {
+        const int rr = s_ray[s2];
+        if (rr != cur) {
+          if (cur >= 0 && acc != 0.f) atomicAdd(d_ray_bias + (int64_t)cur * kH + c, acc * inv_gscale);
+          cur = rr;
+          acc = 0.f;
+        }
+        acc += __half2float(*reinterpret_cast<const __half*>(g2 + (s2 >> 3) * kSboG + (s2 & 7) * 16));
+      }
+      if (cur >= 0 && acc != 0.f) atomicAdd(d_ray_bias + (int64_t)cur * kH + c, acc * inv_gscale);
+    }
+    GF_TC_WAIT()
+    // ---- g h = [ d sigma * exp(clamp(h0 + 1)) | acc[1:16] ] ---------------------------------------------------
+    if (hf == 0) {
+      uint32_t v[16], a[8];
+      tmem_ld16(lane_addr + kColD, v);
+      tmem_wait_ld();
+      // _TruncExp.backward: g * exp(clamp(x, -15, 15))  (nerfstudio/field_components/activations.py:33-36)
+      const float g0 = valid ? __ldg(d_sigma + row) * gscale * expf(fminf(fmaxf(pre, -15.f), 15.f)) : 0.f;
+      a[0] = pack_h2(g0, __uint_as_float(v[1]));
+#pragma unroll
+      for (int j = 1; j < 8; j++) a[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      tmem_st8(lane_addr + kColA, a);
+      if (WGRAD) store_chunks<2>(smem + kOffGo, kSboS, r, 0, a);  // Gh over Go
+    }
+    // g h1 = g h . W1 ; dW1^T (+ b1 row) += H1'^T . Gh
+    GF_TC_SYNC_ISSUE((issue_dgrad<64, 16>(tmem, sB + kOffB1, sbo_of(64)),
+                      WGRAD ? issue_wgrad<128, 16>(tmem + kColW1, sB + kOffH1, kSboH, sB + kOffGo, kSboS, first_tile)
+                            : (void)0))
+    GF_TC_WAIT()
+    {
+      uint32_t v[32], g[16];
+      tmem_ld32(lane_addr + kColD + 32 * hf, v);
+      tmem_wait_ld();
+      mask_pack32(v, h1p, g);
+      tmem_st16(lane_addr + kColA + 16 * hf, g);
+      if (WGRAD) store_chunks<4>(smem + kOffH1, kSboG, r, 4 * hf, g);  // G1 over H1
+    }
+    // g x = g h1 . W0 ; dW0 (+ b0 column) += G1^T . X'
+    GF_TC_SYNC_ISSUE((issue_dgrad<32, 64>(tmem, sB + kOffB0, sbo_of(32)),
+                      WGRAD ? issue_wgrad<64, 40>(tmem + kColW0, sB + kOffH1, kSboG, sB + kOffX, kSboX, first_tile)
+                            : (void)0))
+    GF_TC_WAIT()
+    // ---- d feat, handed to the hash backward as fp16(g * 128) (Hash3DAnchored_cuda.cu:209) ---------------------
+    {
+      uint32_t v[16];
+      tmem_ld16(lane_addr + kColD + 16 * hf, v);
+      tmem_wait_ld();
+      if (valid) {
+        const float sc = GF_GRAD_SCALE * inv_gscale;
+        uint4* dst = reinterpret_cast<uint4*>(d_feat + row * 32 + 16 * hf);
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+          dst[q] = make_uint4(pack_h2(__uint_as_float(v[8 * q]) * sc, __uint_as_float(v[8 * q + 1]) * sc),
+                              pack_h2(__uint_as_float(v[8 * q + 2]) * sc, __uint_as_float(v[8 * q + 3]) * sc),
+                              pack_h2(__uint_as_float(v[8 * q + 4]) * sc, __uint_as_float(v[8 * q + 5]) * sc),
+                              pack_h2(__uint_as_float(v[8 * q + 6]) * sc, __uint_as_float(v[8 * q + 7]) * sc));
+      }
+    }
+    tc_fence_before();
+    first_tile = false;
+  }
+  if (WGRAD && !first_tile) {
+    // ---- flush the weight-gradient accumulators: one atomicAdd per parameter per CTA ------------------------------
+    // (every MMA has completed: the last GF_TC_WAIT covered them)
+    if (hf == 0) {
+      const int q4 = warp & 3;
+      // M = 64 accumulators live in lanes 0..15 of every 32-lane quadrant: row o = 16 q4 + lane (lane < 16)
+      const int o = 16 * q4 + lane;
+      const bool own = lane < 16;
+      uint32_t v[32];
+      // dW3 [o][0..63], b3[o] = column 64
+#pragma unroll
+      for (int part = 0; part < 2; part++) {
+        tmem_ld32(lane_addr + kColW3 + 32 * part, v);
+        tmem_wait_ld();
+        if (own)
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float g = __uint_as_float(v[i]);
+            if (g != 0.f) atomicAdd(d_params + kW3 + o * kH + 32 * part + i, g * inv_gscale);
+          }
+      }
+      {
+        uint32_t w[8];
+        tmem_ld8(lane_addr + kColW3 + 64, w);
+        tmem_wait_ld();
+        if (own && __uint_as_float(w[0]) != 0.f) atomicAdd(d_params + kB3 + o, __uint_as_float(w[0]) * inv_gscale);
+      }
+      // dW0 [o][0..31], b0[o] = column 32
+      tmem_ld32(lane_addr + kColW0, v);
+      tmem_wait_ld();
+      if (own)
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float g = __uint_as_float(v[i]);
+          if (g != 0.f) atomicAdd(d_params + kW0 + o * 32 + i, g * inv_gscale);
+        }
+      {
+        uint32_t w[8];
+        tmem_ld8(lane_addr + kColW0 + 32, w);
+        tmem_wait_ld();
+        if (own && __uint_as_float(w[0]) != 0.f) atomicAdd(d_params + kB0 + o, __uint_as_float(w[0]) * inv_gscale);
+      }
+      // dW2 [o][geo c], c = 1..15 -> column 15 + c of W2
+      {
+        uint32_t w[16];
+        tmem_ld16(lane_addr + kColW2, w);
+        tmem_wait_ld();
+        if (own)
+#pragma unroll
+          for (int c = 1; c < 16; c++) {
+            const float g = __uint_as_float(w[c]);
+            if (g != 0.f) atomicAdd(d_params + kW2 + o * 63 + 15 + c, g * inv_gscale);
+          }
+      }
+      // dW1^T, dW4^T: M = 128, lane = input feature i (rows 0..63), row 64 = the bias
+      {
+        uint32_t w[16];
+        tmem_ld16(lane_addr + kColW1, w);
+        tmem_wait_ld();
+        const int i = r;
+        if (i <= 64)
+#pragma unroll
+          for (int oo = 0; oo < 16; oo++) {
+            const float g = __uint_as_float(w[oo]);
+            if (g != 0.f) atomicAdd(i < 64 ? d_params + kW1 + oo * kH + i : d_params + kB1 + oo, g * inv_gscale);
+          }
+        tmem_ld16(lane_addr + kColW4, w);
+        tmem_wait_ld();
+        if (i <= 64)
+#pragma unroll
+          for (int oo = 0; oo < 3; oo++) {
+            const float g = __uint_as_float(w[oo]);
+            if (g != 0.f) atomicAdd(i < 64 ? d_params + kW4 + oo * kH + i : d_params + kB4 + oo, g * inv_gscale);
+          }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kCols);
+}
+#undef GF_TC_SYNC_ISSUE
+#undef GF_TC_WAIT
+
 }  // namespace tc
 }  // namespace gf
 
@@ -286,4 +706,31 @@ int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params,
   tc::mlp_fwd_tc_kernel<<<grid, tc::kThreads, 46 * 1024, st>>>(n, d_n_ptr, params, (const __half*)feat_f16, ray_id,
                                                                  ray_bias, sigma, rgb);
   return check_launch("mlp_fwd_tc_kernel");
+}
+
+int gf_launch_mlp_bwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
+                         const int32_t* ray_id, const float* ray_bias, const float* d_sigma, const float* d_rgb,
+                         void* d_feat, float* d_params, float* d_ray_bias, float gscale, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GF_CUDA(cudaFuncSetAttribute(tc::mlp_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tc::kBwdSmem));
+    GF_CUDA(cudaFuncSetAttribute(tc::mlp_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024));
+    attr_set = true;
+  }
+  const int64_t tiles = div_up(n, tc::kTile);
+  if (d_params) {
+    // 92 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
+    tc::mlp_bwd_tc_kernel<true><<<grid, tc::kBwdThreads, tc::kBwdSmem, st>>>(
+        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, d_sigma, d_rgb, (__half*)d_feat, d_params,
+        d_ray_bias, gscale);
+  } else {
+    // frozen MLP (focal stage): dgrad only, 128 TMEM columns; 60 KB of dynamic smem caps residency at 3 CTAs per SM
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 3);
+    tc::mlp_bwd_tc_kernel<false><<<grid, tc::kBwdThreads, 60 * 1024, st>>>(
+        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, d_sigma, d_rgb, (__half*)d_feat, nullptr,
+        nullptr, gscale);
+  }
+  return check_launch("mlp_bwd_tc_kernel");
 }
