@@ -1,24 +1,33 @@
-// Fused field MLP on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// Fused field MLP on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a: forward and backward.
 //
-// Same function as the register-chained kernels of mlp.cu (the two MLPNetwork stacks of
-// gfnerf/nerfacto_field.py:174-179,217-227 + trunc_exp + sigmoid, SH / embedding folded into a per-ray bias),
-// re-mapped to the Blackwell execution model:
+// The two MLPNetwork stacks of the reference field (gfnerf/mlp.py:25-57 as built at
+// gfnerf/nerfacto_field.py:174-179,217-227), trunc_exp(x + 1) (:499), the sigmoid head, and everything autograd
+// does for them; SH(dir) and the appearance embedding enter as a per-ray bias of the head's first layer
+// (ray_bias kernels in mlp.cu).  Mapping to the Blackwell execution model:
 //
-//  * a CTA of 128 threads owns a tile of 128 samples; THREAD r IS ROW r of every activation matrix and owns
-//    TMEM lane r (tcgen05.ld/st shape 32x32b: warp w <-> lanes 32w..32w+31);
-//  * every layer is D[128 x N] = A[128 x K] . W^T issued by ONE thread as K/16 tcgen05.mma (M = 128,
-//    kind::f16, fp32 accumulate in TMEM);
+//  * a CTA of 256 threads owns a tile of 128 samples.  Thread (warp w, lane l) IS ROW 32 (w & 3) + l of every
+//    activation / gradient matrix -- it owns TMEM lane r (tcgen05.ld/st shape 32x32b, warp w <-> lane quadrant
+//    w & 3) -- and the column half hf = w >> 2 of the 64-wide matrices;
+//  * every layer is D[128 x N] = A[128 x K] . B^T issued by ONE thread as K/16 tcgen05.mma (M = 128, kind::f16,
+//    fp32 accumulate in TMEM) plus one more MMA that adds the bias: A = a constant [128 x 16] tile whose first
+//    column is 1, B = [N x 16] with the bias in its first column;
 //  * the A operand never touches shared memory: the epilogue of layer l (tcgen05.ld of the fp32 accumulator row,
-//    + bias, ReLU, pack to fp16 pairs) writes the next layer's A straight back into TMEM with tcgen05.st and the
-//    next MMA reads it from there (TS form, A K-major in TMEM: two fp16 per 32-bit column);
-//  * weights (B operands) are staged once per CTA into shared memory as fp16 in the canonical no-swizzle
-//    K-major core-matrix layout and addressed through shared-memory matrix descriptors;
-//  * completion: tcgen05.commit -> mbarrier; the 128 threads wait on it with try_wait.parity.
-//  * TMEM budget per CTA: accumulator 64 columns + A operand 32 columns -> 128 allocated, so four CTAs
-//    (four tiles in flight) share an SM's 512 columns; persistent grid of 4 x 148 CTAs.
+//    fp16 pack, ReLU) writes the next layer's A straight back into TMEM with tcgen05.st and the next MMA reads it
+//    from there (TS form: A K-major in TMEM, two fp16 per 32-bit column);
+//  * weights are staged once per CTA into shared memory as fp16 in the canonical no-swizzle K-major core-matrix
+//    layout and addressed through shared-memory matrix descriptors; the backward's dgrad layers read the SAME tiles
+//    transposed through MN-major descriptors;
+//  * weight gradients: the activation / gradient tiles are also written to shared memory ([sample][feature]
+//    fp16, core-matrix layout) and dW = G^T . ACT is an SS-form MMA with BOTH operands MN-major (K = the 128
+//    samples), accumulated over all tiles of the CTA in TMEM; bias gradients ride along as an all-ones feature
+//    column of the activation tiles.  tcgen05.commit covers every MMA issued before it, so a tile buffer is free
+//    again one dgrad round after the weight-gradient MMAs that read it were issued: G3 / G2 / G1 / Gh reuse the
+//    H3 / H2 / H1 / Go buffers.  One atomicAdd per parameter per CTA at the end;
+//  * completion: tcgen05.commit -> mbarrier; the 256 threads wait on it with try_wait.parity.
 //
-// Per sample the kernel reads 64 B of features + 4 B ray id (+ the ray's 256-B bias row, L1-resident along a ray)
-// and writes 16 B; the 2 x 11 392 FLOP of the five layers run on the tensor pipe.
+// TMEM columns: D 0..63 | A 64..95 | (backward with weight gradients) dW3' 96..167 (64 x 72) | dW0' 168..207
+// (64 x 40) | dW2g 208..223 (64 x 16) | dW1^T 224..239 (128 x 16) | dW4^T 240..255 (128 x 16).
+// Forward / frozen-MLP backward allocate 128 columns (4 CTAs per SM), the full backward 256 (2 CTAs per SM).
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -30,40 +39,62 @@ constexpr int kH = 64;
 constexpr int kW0 = 0, kB0 = kW0 + kH * 32, kW1 = kB0 + kH, kB1 = kW1 + 16 * kH, kW2 = kB1 + 16,
               kB2 = kW2 + kH * 63, kW3 = kB2 + kH, kB3 = kW3 + kH * kH, kW4 = kB3 + kH, kB4 = kW4 + 3 * kH;
 
-constexpr int kTile = 128;     // samples per CTA tile = MMA M
-constexpr int kThreads = 128;
+constexpr int kTile = 128;  // samples per CTA tile = MMA M
+constexpr int kThreads = 256;
 
-// B operands in shared memory: [N rows][K] fp16, K-major, no swizzle: element (n, k) at
+enum Mode { kFwd = 0, kBwdFrozen = 1, kBwdFull = 2 };
+
+// ---- shared memory ------------------------------------------------------------------------------------
+// B operands: [N rows][K] fp16, K-major, no swizzle: element (n, k) at
 //   (n / 8) * SBO + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2,   SBO = (K / 8) * 128
 constexpr uint32_t kLbo = 128;
 constexpr uint32_t sbo_of(int K) { return (uint32_t)(K / 8) * 128u; }
-constexpr uint32_t kOffB0 = 0;                                   // N 64, K 32
-constexpr uint32_t kOffB1 = kOffB0 + 64 * 32 * 2;                // N 16, K 64
-constexpr uint32_t kOffB2 = kOffB1 + 16 * 64 * 2;                // N 64, K 16 (geo columns of the head's layer 0)
-constexpr uint32_t kOffB3 = kOffB2 + 64 * 16 * 2;                // N 64, K 64
-constexpr uint32_t kOffB4 = kOffB3 + 64 * 64 * 2;                // N 16 (3 real rows), K 64
-constexpr uint32_t kOffBias = kOffB4 + 16 * 64 * 2;              // b0[64] | b1[16] | b3[64] | b4[16]  (fp32)
-constexpr uint32_t kOffBar = kOffBias + 160 * 4;
+constexpr uint32_t kOffB0 = 0;                        // N 64, K 32
+constexpr uint32_t kOffB1 = kOffB0 + 64 * 32 * 2;     // N 16, K 64
+constexpr uint32_t kOffB2 = kOffB1 + 16 * 64 * 2;     // N 64, K 16 (geo columns of the head's layer 0)
+constexpr uint32_t kOffB3 = kOffB2 + 64 * 16 * 2;     // N 64, K 64
+constexpr uint32_t kOffB4 = kOffB3 + 64 * 64 * 2;     // N 16 (3 real rows), K 64
+constexpr uint32_t kOffBb0 = kOffB4 + 16 * 64 * 2;    // bias tiles [N][16]: column 0 = bias
+constexpr uint32_t kOffBb1 = kOffBb0 + 64 * 16 * 2;
+constexpr uint32_t kOffBb3 = kOffBb1 + 16 * 16 * 2;
+constexpr uint32_t kOffBb4 = kOffBb3 + 64 * 16 * 2;
+constexpr uint32_t kOffOnes = kOffBb4 + 16 * 16 * 2;  // A tile [128][16]: column 0 = 1
+constexpr uint32_t kOffBar = kOffOnes + 128 * 16 * 2;
 constexpr uint32_t kOffTmem = kOffBar + 8;
-constexpr uint32_t kFwdSmem = kOffTmem + 8;
+constexpr uint32_t kOffRay = kOffTmem + 8;             // int32 ray id of each row (full backward)
+constexpr uint32_t kSmemBase = (kOffRay + 512 + 127) / 128 * 128;
+// [sample][feature] tiles of the full backward
+constexpr uint32_t kSboX = 640, kSboH = 1152, kSboG = 1024, kSboS = 256;
+constexpr uint32_t kOffX = kSmemBase;                  // [128][32 + 8]   SBO 640
+constexpr uint32_t kOffH1 = kOffX + 16 * kSboX;        // [128][64 + 8]   SBO 1152 (G1 reuses it with SBO 1024)
+constexpr uint32_t kOffH2 = kOffH1 + 16 * kSboH;
+constexpr uint32_t kOffH3 = kOffH2 + 16 * kSboH;
+constexpr uint32_t kOffHh = kOffH3 + 16 * kSboH;       // [128][16]       SBO 256
+constexpr uint32_t kOffGo = kOffHh + 16 * kSboS;       // [128][16]       SBO 256 (Gh reuses it)
+constexpr uint32_t kSmemFull = kOffGo + 16 * kSboS + 1024;  // + slack: the M = 128 reads of H3' run past its tile
 
-constexpr uint32_t kTmemCols = 128;
-constexpr uint32_t kColD = 0;    // accumulator, up to 64 fp32 columns
-constexpr uint32_t kColA = 64;   // A operand, up to 32 columns (64 fp16)
+// ---- tensor memory --------------------------------------------------------------------------------------
+constexpr uint32_t kColD = 0, kColA = 64;
+constexpr uint32_t kColW3 = 96, kColW0 = 168, kColW2 = 208, kColW1 = 224, kColW4 = 240;
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t relu_h2(uint32_t v) {
+  __half2 h = __hmax2(*reinterpret_cast<__half2*>(&v), __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 __device__ __forceinline__ void put_b(unsigned char* smem, uint32_t off, int K, int n, int k, float v) {
   *reinterpret_cast<__half*>(smem + off + (n >> 3) * sbo_of(K) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) =
       __float2half_rn(v);
 }
 
-// fp32 parameter blob -> fp16 B tiles + fp32 biases
+// fp32 parameter blob -> fp16 weight / bias tiles, the all-ones A tile
 __device__ __forceinline__ void stage_weights(const float* __restrict__ p, unsigned char* smem) {
-  for (uint32_t i = threadIdx.x; i < kOffBias / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < kOffBar / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
   __syncthreads();
   for (int i = threadIdx.x; i < kH * 32; i += blockDim.x) put_b(smem, kOffB0, 32, i >> 5, i & 31, __ldg(p + kW0 + i));
   for (int i = threadIdx.x; i < 16 * kH; i += blockDim.x) put_b(smem, kOffB1, 64, i >> 6, i & 63, __ldg(p + kW1 + i));
@@ -74,261 +105,25 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ p, unsig
   }
   for (int i = threadIdx.x; i < kH * kH; i += blockDim.x) put_b(smem, kOffB3, 64, i >> 6, i & 63, __ldg(p + kW3 + i));
   for (int i = threadIdx.x; i < 3 * kH; i += blockDim.x) put_b(smem, kOffB4, 64, i >> 6, i & 63, __ldg(p + kW4 + i));
-  float* bs = reinterpret_cast<float*>(smem + kOffBias);
-  for (int i = threadIdx.x; i < 160; i += blockDim.x) {
-    float v;
-    if (i < 64) v = __ldg(p + kB0 + i);
-    else if (i < 80) v = __ldg(p + kB1 + i - 64);
-    else if (i < 144) v = __ldg(p + kB3 + i - 80);
-    else v = (i - 144) < 3 ? __ldg(p + kB4 + i - 144) : 0.f;
-    bs[i] = v;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    put_b(smem, kOffBb0, 16, i, 0, __ldg(p + kB0 + i));
+    put_b(smem, kOffBb3, 16, i, 0, __ldg(p + kB3 + i));
+    if (i < 16) put_b(smem, kOffBb1, 16, i, 0, __ldg(p + kB1 + i));
+    if (i < 3) put_b(smem, kOffBb4, 16, i, 0, __ldg(p + kB4 + i));
   }
+  for (int i = threadIdx.x; i < kTile; i += blockDim.x) put_b(smem, kOffOnes, 16, i, 0, 1.f);
 }
 
-// one layer: D[kColD .. +N) = A[kColA .. +K/2) . B^T as K/16 MMAs (the caller commits)
-template <int N, int K>
-__device__ __forceinline__ void issue_fwd(uint32_t tmem, uint32_t b_smem) {
+// forward layer: D[kColD .. +N) = A[kColA .. +K/2) . B^T (+ bias): K/16 TS-form MMAs + one SS-form bias MMA
+template <int N, int K, bool BIAS>
+__device__ __forceinline__ void issue_fwd(uint32_t tmem, uint32_t sB, uint32_t off_w, uint32_t off_bias) {
   constexpr uint32_t idesc = instr_desc(kTile, N);
 #pragma unroll
   for (int k = 0; k < K / 16; k++)
-    mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc(b_smem + 2 * k * kLbo, kLbo, sbo_of(K)), idesc, k > 0);
+    mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc(sB + off_w + 2 * k * kLbo, kLbo, sbo_of(K)), idesc, k > 0);
+  if (BIAS)
+    mma_ss(tmem + kColD, smem_desc(sB + kOffOnes, kLbo, sbo_of(16)), smem_desc(sB + off_bias, kLbo, sbo_of(16)), idesc, 1u);
 }
-template <int N, int K>
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t b_smem, uint32_t bar) {
-  issue_fwd<N, K>(tmem, b_smem);
-  mma_commit(bar);
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
-
-// acc (fp32 bits in v[0..32)) + bias[0..32) -> ReLU -> 16 packed fp16 pairs
-__device__ __forceinline__ void bias_relu_pack32(const uint32_t (&v)[32], const float* bias, uint32_t* out16) {
-#pragma unroll
-  for (int q = 0; q < 8; q++) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
-    out16[2 * q] = pack_h2(fmaxf(__uint_as_float(v[4 * q]) + b.x, 0.f), fmaxf(__uint_as_float(v[4 * q + 1]) + b.y, 0.f));
-    out16[2 * q + 1] =
-        pack_h2(fmaxf(__uint_as_float(v[4 * q + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[4 * q + 3]) + b.w, 0.f));
-  }
-}
-
-__global__ void __launch_bounds__(kThreads)
-mlp_fwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __restrict__ params,
-                  const __half* __restrict__ feat, const int32_t* __restrict__ ray_id,
-                  const float* __restrict__ ray_bias, float* __restrict__ sigma, float* __restrict__ rgb) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
-  stage_weights(params, smem);
-  const uint32_t bar = smem_u32(smem + kOffBar);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc(smem_u32(smem + kOffTmem), kTmemCols);
-  }
-  fence_proxy_async();  // the weight tiles were written through the generic proxy; the MMA reads them through the async proxy
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lane quadrant
-  const uint32_t sB = smem_u32(smem);
-  const float* bs = reinterpret_cast<const float*>(smem + kOffBias);
-  if (d_n_ptr) {
-    const int64_t dn = *d_n_ptr;
-    n = dn < n ? dn : n;
-  }
-  uint32_t phase = 0;
-  const int64_t n_tiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row = tile * kTile + tid;
-    const bool valid = row < n;
-    // ---- layer 0 input: this sample's 32 fp16 features -> A[.., 0:16 columns) ------------------------------
-    {
-      uint32_t x[16];
-      const uint4* src = reinterpret_cast<const uint4*>(feat + row * 32);
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const uint4 u = valid ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
-        x[4 * q] = u.x; x[4 * q + 1] = u.y; x[4 * q + 2] = u.z; x[4 * q + 3] = u.w;
-      }
-      tmem_st16(lane_addr + kColA, x);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer<64, 32>(tmem, sB + kOffB0, bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue 0: h1 = relu(acc + b0) -> A (64 fp16 = 32 columns) -----------------------------------------
-    {
-      uint32_t v[32], a[32];
-      tmem_ld32(lane_addr + kColD, v);
-      tmem_wait_ld();
-      bias_relu_pack32(v, bs, a);
-      tmem_ld32(lane_addr + kColD + 32, v);
-      tmem_wait_ld();
-      bias_relu_pack32(v, bs + 32, a + 16);
-      tmem_st32(lane_addr + kColA, a);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer<16, 64>(tmem, sB + kOffB1, bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue 1: h = acc + b1; sigma = exp(h0 + 1); geo features -> A (16 fp16 = 8 columns) --------------
-    {
-      uint32_t v[16], a[8];
-      tmem_ld16(lane_addr + kColD, v);
-      tmem_wait_ld();
-      float h[16];
-#pragma unroll
-      for (int j = 0; j < 16; j++) h[j] = __uint_as_float(v[j]) + bs[64 + j];
-      if (valid) sigma[row] = expf(h[0] + 1.f);  // trunc_exp(h0 + 1), nerfacto_field.py:499
-      h[0] = 0.f;                                 // column 0 of the geo tile has zero weights
-#pragma unroll
-      for (int j = 0; j < 8; j++) a[j] = pack_h2(h[2 * j], h[2 * j + 1]);
-      tmem_st8(lane_addr + kColA, a);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer<64, 16>(tmem, sB + kOffB2, bar);
-    }
-    // the ray's bias row (b2 + W2[:, SH] SH(d) + W2[:, emb] emb) while the MMA runs
-    const float* rb = ray_bias + (int64_t)(valid ? __ldg(ray_id + row) : 0) * kH;
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue 2: h2 = relu(acc + ray_bias[ray]) -------------------------------------------------------
-    {
-      uint32_t v[32], a[32];
-      tmem_ld32(lane_addr + kColD, v);
-      tmem_wait_ld();
-      bias_relu_pack32(v, rb, a);
-      tmem_ld32(lane_addr + kColD + 32, v);
-      tmem_wait_ld();
-      bias_relu_pack32(v, rb + 32, a + 16);
-      tmem_st32(lane_addr + kColA, a);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer<64, 64>(tmem, sB + kOffB3, bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue 3: h3 = relu(acc + b3) -------------------------------------------------------------------
-    {
-      uint32_t v[32], a[32];
-      tmem_ld32(lane_addr + kColD, v);
-      tmem_wait_ld();
-      bias_relu_pack32(v, bs + 80, a);
-      tmem_ld32(lane_addr + kColD + 32, v);
-      tmem_wait_ld();
-      bias_relu_pack32(v, bs + 112, a + 16);
-      tmem_st32(lane_addr + kColA, a);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer<16, 64>(tmem, sB + kOffB4, bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue 4: rgb = sigmoid(acc + b4) ------------------------------------------------------------------
-    {
-      uint32_t v[4];
-      tmem_ld4(lane_addr + kColD, v);
-      tmem_wait_ld();
-      if (valid) {
-        rgb[3 * row] = sigmoidf_(__uint_as_float(v[0]) + bs[144]);
-        rgb[3 * row + 1] = sigmoidf_(__uint_as_float(v[1]) + bs[145]);
-        rgb[3 * row + 2] = sigmoidf_(__uint_as_float(v[2]) + bs[146]);
-      }
-    }
-    // the next tile's tcgen05.st into A and MMA into D are ordered behind this tile's loads by the
-    // fence + __syncthreads at the top of the next iteration
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
-}
-
-
-// =============================================================================================================
-// backward
-// =============================================================================================================
-// 256 threads per CTA: thread (warp w, lane l) is row 32 (w & 3) + l of the tile (its TMEM lane) and owns the column
-// half hf = w >> 2 of every 64-wide activation / gradient matrix.  Per tile: the five forward layers are recomputed
-// (the post-ReLU activations stay in registers as the ReLU masks), then five dgrad layers run as TS-form MMAs whose A
-// operand is the gradient the previous epilogue wrote to TMEM and whose B operand is the SAME shared-memory weight
-// tile as the forward, read transposed through an MN-major descriptor.
-// Weight gradients (WGRAD): every activation / gradient tile is also written to shared memory ([sample][feature]
-// fp16, core-matrix layout) and dW = G^T . ACT is an SS-form MMA with BOTH operands MN-major (K = the 128 samples),
-// accumulating over all tiles of the CTA in TMEM; bias gradients ride along as an extra all-ones feature column of
-// the activation tiles.  tcgen05.commit covers every MMA issued before it, so a tile buffer is free again one
-// dgrad round after the weight-gradient MMAs that read it were issued: G3 / G2 / G1 / Gh reuse the H3 / H2 / H1 /
-// Go buffers.  One atomicAdd per parameter per CTA at the end.
-//
-// TMEM columns (WGRAD): D 0..63 | A 64..95 | dW3' 96..167 (64 x 72) | dW0' 168..207 (64 x 40) | dW2g 208..223
-// (64 x 16) | dW1^T 224..239 (128 x 16) | dW4^T 240..255 (128 x 16)  = 256 -> two CTAs per SM.
-constexpr int kBwdThreads = 256;
-constexpr uint32_t kColW3 = 96, kColW0 = 168, kColW2 = 208, kColW1 = 224, kColW4 = 240;
-constexpr uint32_t kOffRay = 19200;                     // int32 ray id of each row
-constexpr uint32_t kOffX = kOffRay + 512;                // [128][32 + 8]   SBO 640
-constexpr uint32_t kSboX = 640, kSboH = 1152, kSboG = 1024, kSboS = 256;
-constexpr uint32_t kOffH1 = kOffX + 16 * kSboX;          // [128][64 + 8]   SBO 1152 (G1 reuses it with SBO 1024)
-constexpr uint32_t kOffH2 = kOffH1 + 16 * kSboH;
-constexpr uint32_t kOffH3 = kOffH2 + 16 * kSboH;
-constexpr uint32_t kOffHh = kOffH3 + 16 * kSboH;         // [128][16]       SBO 256
-constexpr uint32_t kOffGo = kOffHh + 16 * kSboS;         // [128][16]       SBO 256 (Gh reuses it)
-constexpr uint32_t kBwdSmem = kOffGo + 16 * kSboS + 1024;  // + slack: the M = 128 reads of H3' run past the tile
-static_assert(kOffRay >= kFwdSmem && kOffX % 128 == 0, "backward smem layout");
-
-// 16-byte chunk j (features 8 j .. 8 j + 7) of row r of a [sample][feature] tile
-__device__ __forceinline__ uint4* tile_chunk(unsigned char* buf, uint32_t sbo, int r, int j) {
-  return reinterpret_cast<uint4*>(buf + (r >> 3) * sbo + j * 128 + (r & 7) * 16);
-}
-template <int NCH>
-__device__ __forceinline__ void store_chunks(unsigned char* buf, uint32_t sbo, int r, int j0, const uint32_t* a) {
-#pragma unroll
-  for (int q = 0; q < NCH; q++)
-    *tile_chunk(buf, sbo, r, j0 + q) = make_uint4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-}
-__device__ __forceinline__ void store_ones(unsigned char* buf, uint32_t sbo, int r, int j) {
-  *tile_chunk(buf, sbo, r, j) = make_uint4(0x00003C00u, 0u, 0u, 0u);  // feature 8 j = 1.0, the rest 0
-}
-
-// gradient accumulators (fp32 bits in v[0..32)) masked by relu'(h) (h as 16 packed fp16 pairs) -> 16 packed pairs
-__device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const uint32_t (&h)[16], uint32_t (&out)[16]) {
-#pragma unroll
-  for (int q = 0; q < 16; q++) {
-    const float lo = (h[q] & 0xFFFFu) ? __uint_as_float(v[2 * q]) : 0.f;
-    const float hi = (h[q] >> 16) ? __uint_as_float(v[2 * q + 1]) : 0.f;
-    out[q] = pack_h2(lo, hi);
-  }
-}
-
 // dgrad layer: D[128 x N] = G[128 x K] (TMEM) . W[K x N], W = the forward tile [K = out][N = in] read MN-major
 template <int N, int K>
 __device__ __forceinline__ void issue_dgrad(uint32_t tmem, uint32_t w_smem, uint32_t sbo_fwd) {
@@ -348,6 +143,43 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t p_smem, ui
            (k > 0 || !first_tile) ? 1u : 0u);
 }
 
+// 16-byte chunk j (features 8 j .. 8 j + 7) of row r of a [sample][feature] tile
+__device__ __forceinline__ uint4* tile_chunk(unsigned char* buf, uint32_t sbo, int r, int j) {
+  return reinterpret_cast<uint4*>(buf + (r >> 3) * sbo + j * 128 + (r & 7) * 16);
+}
+template <int NCH>
+__device__ __forceinline__ void store_chunks(unsigned char* buf, uint32_t sbo, int r, int j0, const uint32_t* a) {
+#pragma unroll
+  for (int q = 0; q < NCH; q++)
+    *tile_chunk(buf, sbo, r, j0 + q) = make_uint4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+}
+__device__ __forceinline__ void store_ones(unsigned char* buf, uint32_t sbo, int r, int j) {
+  *tile_chunk(buf, sbo, r, j) = make_uint4(0x00003C00u, 0u, 0u, 0u);  // feature 8 j = 1.0, the rest 0
+}
+
+// accumulator row (fp32 bits, bias already added by the MMA) -> ReLU -> 16 packed fp16 pairs
+__device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], uint32_t (&out)[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) out[q] = relu_h2(pack_h2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
+}
+// the same with an fp32 per-row bias (the ray's bias row of the head's first layer)
+__device__ __forceinline__ void bias_relu_pack32(const uint32_t (&v)[32], const float* bias, uint32_t (&out)[16]) {
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    out[2 * q] = relu_h2(pack_h2(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y));
+    out[2 * q + 1] = relu_h2(pack_h2(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w));
+  }
+}
+// gradient row masked by relu'(h) (h = the post-ReLU activation as 16 packed fp16 pairs) -> 16 packed pairs
+__device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const uint32_t (&h)[16], uint32_t (&out)[16]) {
+  const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    out[q] = pack_h2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])) &
+             __hgt2_mask(*reinterpret_cast<const __half2*>(&h[q]), zero);
+}
+
 // publish this thread's TMEM / shared-memory writes, let one thread issue the MMAs, wait for their completion
 #define GF_TC_SYNC_ISSUE(ISSUE) \
   tmem_wait_st();               \
@@ -364,19 +196,21 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t p_smem, ui
   phase ^= 1;            \
   tc_fence_after();
 
-template <bool WGRAD>
-__global__ void __launch_bounds__(kBwdThreads, 2)
-mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __restrict__ params,
-                  const __half* __restrict__ feat, const int32_t* __restrict__ ray_id,
-                  const float* __restrict__ ray_bias, const float* __restrict__ d_sigma,
-                  const float* __restrict__ d_rgb, __half* __restrict__ d_feat, float* __restrict__ d_params,
-                  float* __restrict__ d_ray_bias, float gscale) {
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, MODE == kFwd ? 3 : 2)
+mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __restrict__ params,
+              const __half* __restrict__ feat, const int32_t* __restrict__ ray_id,
+              const float* __restrict__ ray_bias, float* __restrict__ sigma, float* __restrict__ rgb,
+              const float* __restrict__ d_sigma, const float* __restrict__ d_rgb, __half* __restrict__ d_feat,
+              float* __restrict__ d_params, float* __restrict__ d_ray_bias, float gscale) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr bool WGRAD = MODE == kBwdFull;
+  constexpr bool BWD = MODE != kFwd;
   constexpr uint32_t kCols = WGRAD ? 256u : 128u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = 32 * (warp & 3) + lane;  // row of the tile = TMEM lane
   const int hf = warp >> 2;              // column half
-  const float inv_gscale = 1.f / gscale;
+  const float inv_gscale = BWD ? 1.f / gscale : 1.f;
   stage_weights(params, smem);
   const uint32_t bar = smem_u32(smem + kOffBar);
   if (tid == 0) {
@@ -387,14 +221,13 @@ mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
     __syncwarp();
     tmem_alloc(smem_u32(smem + kOffTmem), kCols);
   }
-  fence_proxy_async();
+  fence_proxy_async();  // the tiles were written through the generic proxy; the MMA reads them through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
   const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
   const uint32_t sB = smem_u32(smem);
-  const float* bs = reinterpret_cast<const float*>(smem + kOffBias);
   int* s_ray = reinterpret_cast<int*>(smem + kOffRay);
   if (d_n_ptr) {
     const int64_t dn = *d_n_ptr;
@@ -425,38 +258,37 @@ mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
         s_ray[r] = ray;
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 32>(tmem, sB + kOffB0)))
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 32, true>(tmem, sB, kOffB0, kOffBb0)))
     GF_TC_WAIT()
-    // ---- h1 = relu(acc + b0) -------------------------------------------------------------------------------
+    // ---- h1 = relu(acc) ----------------------------------------------------------------------------------
     {
       uint32_t v[32];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
-      bias_relu_pack32(v, bs + 32 * hf, h1p);
+      relu_pack32(v, h1p);
       tmem_st16(lane_addr + kColA + 16 * hf, h1p);
       if (WGRAD) {
         store_chunks<4>(smem + kOffH1, kSboH, r, 4 * hf, h1p);
         if (hf == 0) store_ones(smem + kOffH1, kSboH, r, 8);
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<16, 64>(tmem, sB + kOffB1)))
+    GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sB, kOffB1, kOffBb1)))
     GF_TC_WAIT()
-    // ---- h = acc + b1; density logit; geo features -> A (16 fp16) --------------------------------------------
+    // ---- h = acc; density = exp(h0 + 1); geo features -> A (16 fp16) ------------------------------------------
     if (hf == 0) {
       uint32_t v[16], a[8];
       tmem_ld16(lane_addr + kColD, v);
       tmem_wait_ld();
-      float h[16];
+      pre = __uint_as_float(v[0]) + 1.f;
+      if (MODE == kFwd && valid) sigma[row] = expf(pre);  // trunc_exp(h0 + 1), nerfacto_field.py:499
+      a[0] = pack_h2(0.f, __uint_as_float(v[1]));          // column 0 of the geo tile has zero weights
 #pragma unroll
-      for (int j = 0; j < 16; j++) h[j] = __uint_as_float(v[j]) + bs[64 + j];
-      pre = h[0] + 1.f;
-      h[0] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; j++) a[j] = pack_h2(h[2 * j], h[2 * j + 1]);
+      for (int j = 1; j < 8; j++) a[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
       tmem_st8(lane_addr + kColA, a);
       if (WGRAD) store_chunks<2>(smem + kOffHh, kSboS, r, 0, a);
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 16>(tmem, sB + kOffB2)))
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 16, false>(tmem, sB, kOffB2, 0u)))
+    // the ray's bias row (b2 + W2[:, SH] SH(d) + W2[:, emb] emb)
     const float* rb = ray_bias + (int64_t)(valid ? ray : 0) * kH + 32 * hf;
     GF_TC_WAIT()
     // ---- h2 = relu(acc + ray_bias[ray]) ----------------------------------------------------------------------
@@ -471,22 +303,37 @@ mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
         if (hf == 0) store_ones(smem + kOffH2, kSboH, r, 8);
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 64>(tmem, sB + kOffB3)))
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 64, true>(tmem, sB, kOffB3, kOffBb3)))
     GF_TC_WAIT()
-    // ---- h3 = relu(acc + b3) -------------------------------------------------------------------------------
+    // ---- h3 = relu(acc) ----------------------------------------------------------------------------------
     {
       uint32_t v[32];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
-      bias_relu_pack32(v, bs + 80 + 32 * hf, h3p);
+      relu_pack32(v, h3p);
       tmem_st16(lane_addr + kColA + 16 * hf, h3p);
       if (WGRAD) {
         store_chunks<4>(smem + kOffH3, kSboH, r, 4 * hf, h3p);
         if (hf == 0) store_ones(smem + kOffH3, kSboH, r, 8);
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<16, 64>(tmem, sB + kOffB4)))
+    GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sB, kOffB4, kOffBb4)))
     GF_TC_WAIT()
+    if (MODE == kFwd) {
+      // ---- rgb = sigmoid(acc) --------------------------------------------------------------------------------
+      if (hf == 0) {
+        uint32_t v[4];
+        tmem_ld4(lane_addr + kColD, v);
+        tmem_wait_ld();
+        if (valid) {
+          rgb[3 * row] = sigmoidf_(__uint_as_float(v[0]));
+          rgb[3 * row + 1] = sigmoidf_(__uint_as_float(v[1]));
+          rgb[3 * row + 2] = sigmoidf_(__uint_as_float(v[2]));
+        }
+      }
+      tc_fence_before();
+      continue;
+    }
     // ---- g o = d rgb * s (1 - s)  (all gradients carry the factor gscale while they are fp16) ------------------
     if (hf == 0) {
       uint32_t v[4], a[8];
@@ -496,7 +343,7 @@ mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
       if (valid) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          const float sg = sigmoidf_(__uint_as_float(v[c]) + bs[144 + c]);
+          const float sg = sigmoidf_(__uint_as_float(v[c]));
           go[c] = __ldg(d_rgb + 3 * row + c) * gscale * sg * (1.f - sg);
         }
       }
@@ -538,22 +385,70 @@ mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
                       WGRAD ? issue_wgrad<64, 16>(tmem + kColW2, sB + kOffH2, kSboG, sB + kOffHh, kSboS, first_tile)
                             : (void)0))
     if (WGRAD) {
-      // d ray_bias[ray] += column sums of g h2 over the rows of that ray (rows of a ray are contiguous): thread =
-      // (column, quarter of the rows), reading the G2 tile the MMAs are reading too
-      const int c = tid & 63, q0 = 32 * (tid >> 6);
-      const unsigned char* g2 = smem + kOffH2 + (c >> 3) * 128 + (c & 7) * 2;
-      float acc = 0.f;
-      int cur = -1;
-      for (int s2 = q0; s2 < q0 + 32; s2++) {
-        const int rr = s_ray[s2];
-        if (rr != cur) {
-          if (cur >= 0 && acc != 0.f) atomicAdd(d_ray_bias + (int64_t)cur * kH + c, acc * inv_gscale);
-          cur = rr;
-          acc = 0.f;
+      // d ray_bias[ray] += column sums of g h2 over the rows of that ray (rows of a ray are contiguous), from the
+      // G2 tile the MMAs are reading too.  Warp w sums rows 16 w .. 16 w + 15: lane = (row group of 4, chunk of 8
+      // columns); 4 rows in fp16 pairs, then across the row groups with shuffles, fp32 from there.
+      const int s0 = 16 * warp;
+      if (s_ray[s0] == s_ray[s0 + 15]) {  // one ray (or all rows past the end): the common case
+        const int j = lane & 7, rg = lane >> 3;
+        __half2 acc[4];
+        {
+          const uint4 u = *tile_chunk(smem + kOffH2, kSboG, s0 + 4 * rg, j);
+          acc[0] = *reinterpret_cast<const __half2*>(&u.x);
+          acc[1] = *reinterpret_cast<const __half2*>(&u.y);
+          acc[2] = *reinterpret_cast<const __half2*>(&u.z);
+          acc[3] = *reinterpret_cast<const __half2*>(&u.w);
         }
-        acc += __half2float(*reinterpret_cast<const __half*>(g2 + (s2 >> 3) * kSboG + (s2 & 7) * 16));
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+          const uint4 u = *tile_chunk(smem + kOffH2, kSboG, s0 + 4 * rg + k, j);
+          acc[0] = __hadd2(acc[0], *reinterpret_cast<const __half2*>(&u.x));
+          acc[1] = __hadd2(acc[1], *reinterpret_cast<const __half2*>(&u.y));
+          acc[2] = __hadd2(acc[2], *reinterpret_cast<const __half2*>(&u.z));
+          acc[3] = __hadd2(acc[3], *reinterpret_cast<const __half2*>(&u.w));
+        }
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float2 t = __half22float2(acc[k]);
+          f[2 * k] = t.x;
+          f[2 * k + 1] = t.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          f[k] += __shfl_xor_sync(0xffffffffu, f[k], 8);
+          f[k] += __shfl_xor_sync(0xffffffffu, f[k], 16);
+        }
+        const int rr = s_ray[s0];
+        if (rg == 0 && rr >= 0) {
+          float* dst = d_ray_bias + (int64_t)rr * kH + 8 * j;
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (f[k] != 0.f) atomicAdd(dst + k, f[k] * inv_gscale);
+        }
+      } else {  // a ray boundary inside these 16 rows: lane = column pair, serial over the rows
+        const unsigned char* g2 = smem + kOffH2 + (lane >> 2) * 128 + (lane & 3) * 4;
+        float a0 = 0.f, a1 = 0.f;
+        int cur = -1;
+        for (int s2 = s0; s2 < s0 + 16; s2++) {
+          const int rr = s_ray[s2];
+          if (rr != cur) {
+            if (cur >= 0) {
+              atomicAdd(d_ray_bias + (int64_t)cur * kH + 2 * lane, a0 * inv_gscale);
+              atomicAdd(d_ray_bias + (int64_t)cur * kH + 2 * lane + 1, a1 * inv_gscale);
+            }
+            cur = rr;
+            a0 = a1 = 0.f;
+          }
+          const float2 t = __half22float2(*reinterpret_cast<const __half2*>(g2 + (s2 >> 3) * kSboG + (s2 & 7) * 16));
+          a0 += t.x;
+          a1 += t.y;
+        }
+        if (cur >= 0) {
+          atomicAdd(d_ray_bias + (int64_t)cur * kH + 2 * lane, a0 * inv_gscale);
+          atomicAdd(d_ray_bias + (int64_t)cur * kH + 2 * lane + 1, a1 * inv_gscale);
+        }
       }
-      if (cur >= 0 && acc != 0.f) atomicAdd(d_ray_bias + (int64_t)cur * kH + c, acc * inv_gscale);
     }
     GF_TC_WAIT()
     // ---- g h = [ d sigma * exp(clamp(h0 + 1)) | acc[1:16] ] ---------------------------------------------------
@@ -610,9 +505,8 @@ mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
     // ---- flush the weight-gradient accumulators: one atomicAdd per parameter per CTA ------------------------------
     // (every MMA has completed: the last GF_TC_WAIT covered them)
     if (hf == 0) {
-      const int q4 = warp & 3;
-      // M = 64 accumulators live in lanes 0..15 of every 32-lane quadrant: row o = 16 q4 + lane (lane < 16)
-      const int o = 16 * q4 + lane;
+      // M = 64 accumulators live in lanes 0..15 of every 32-lane quadrant: row o = 16 (warp & 3) + lane (lane < 16)
+      const int o = 16 * (warp & 3) + lane;
       const bool own = lane < 16;
       uint32_t v[32];
       // dW3 [o][0..63], b3[o] = column 64
@@ -695,42 +589,54 @@ mlp_bwd_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* _
 
 using namespace gf;
 
-// launched by gf_mlp_forward (mlp.cu)
+// Shared-memory request per mode.  It also caps residency so that the CTAs of one SM never ask for more than its
+// 512 TMEM columns (a CTA beyond that would sit in tcgen05.alloc until another one exits):
+// 128-column modes: 52 KB -> at most 4 CTAs per SM; full backward: ~102 KB (its tiles) -> 2 CTAs per SM.
+static constexpr int kSmemSmall = 52 * 1024;
+static_assert(tc::kSmemBase <= kSmemSmall, "forward smem");
+
+static int set_attrs() {
+  static bool done = false;
+  if (!done) {
+    GF_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<tc::kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSmall));
+    GF_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<tc::kBwdFrozen>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemSmall));
+    GF_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<tc::kBwdFull>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)tc::kSmemFull));
+    done = true;
+  }
+  return GF_OK;
+}
+
+// launched by gf_mlp_forward / gf_mlp_backward (mlp.cu)
 int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
                          const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, cudaStream_t st) {
+  int rc = set_attrs();
+  if (rc) return rc;
   const int64_t tiles = div_up(n, tc::kTile);
-  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 4);
-  // 46 KB of dynamic shared memory (19 KB used) caps residency at four CTAs per SM = 4 x 128 TMEM columns, so a
-  // fifth CTA can never sit in tcgen05.alloc waiting for columns
-  static_assert(tc::kFwdSmem <= 46 * 1024, "forward smem");
-  tc::mlp_fwd_tc_kernel<<<grid, tc::kThreads, 46 * 1024, st>>>(n, d_n_ptr, params, (const __half*)feat_f16, ray_id,
-                                                                 ray_bias, sigma, rgb);
-  return check_launch("mlp_fwd_tc_kernel");
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 3);
+  tc::mlp_tc_kernel<tc::kFwd><<<grid, tc::kThreads, kSmemSmall, st>>>(
+      n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, sigma, rgb, nullptr, nullptr, nullptr, nullptr,
+      nullptr, 1.f);
+  return check_launch("mlp_tc_kernel<fwd>");
 }
 
 int gf_launch_mlp_bwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
                          const int32_t* ray_id, const float* ray_bias, const float* d_sigma, const float* d_rgb,
                          void* d_feat, float* d_params, float* d_ray_bias, float gscale, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    GF_CUDA(cudaFuncSetAttribute(tc::mlp_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)tc::kBwdSmem));
-    GF_CUDA(cudaFuncSetAttribute(tc::mlp_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024));
-    attr_set = true;
-  }
+  int rc = set_attrs();
+  if (rc) return rc;
   const int64_t tiles = div_up(n, tc::kTile);
   if (d_params) {
-    // 92 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
-    tc::mlp_bwd_tc_kernel<true><<<grid, tc::kBwdThreads, tc::kBwdSmem, st>>>(
-        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, d_sigma, d_rgb, (__half*)d_feat, d_params,
-        d_ray_bias, gscale);
-  } else {
-    // frozen MLP (focal stage): dgrad only, 128 TMEM columns; 60 KB of dynamic smem caps residency at 3 CTAs per SM
-    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 3);
-    tc::mlp_bwd_tc_kernel<false><<<grid, tc::kBwdThreads, 60 * 1024, st>>>(
-        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, d_sigma, d_rgb, (__half*)d_feat, nullptr,
-        nullptr, gscale);
+    tc::mlp_tc_kernel<tc::kBwdFull><<<grid, tc::kThreads, tc::kSmemFull, st>>>(
+        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, nullptr, nullptr, d_sigma, d_rgb,
+        (__half*)d_feat, d_params, d_ray_bias, gscale);
+  } else {  // frozen MLP (focal stage): dgrad only
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
+    tc::mlp_tc_kernel<tc::kBwdFrozen><<<grid, tc::kThreads, kSmemSmall, st>>>(
+        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, nullptr, nullptr, d_sigma, d_rgb,
+        (__half*)d_feat, nullptr, nullptr, gscale);
   }
-  return check_launch("mlp_bwd_tc_kernel");
+  return check_launch("mlp_tc_kernel<bwd>");
 }

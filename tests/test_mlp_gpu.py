@@ -38,6 +38,8 @@ def emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma, d_rgb):
         return out
     Q = lambda x: x.astype(np.float16).astype(np.float32)
     w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = split(params)
+    # b0, b1, b3, b4 enter through a bias MMA (fp16 operand); b2 is part of the fp32 per-ray bias
+    b0, b1, b3, b4 = Q(b0), Q(b1), Q(b3), Q(b4)
     x = feat.astype(np.float32)
     h1 = Q(np.maximum(x @ Q(w0).T + b0, 0))
     h = h1 @ Q(w1).T + b1
