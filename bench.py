@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="global", choices=["global", "focal"],
+                    help="global: BASELINE config 2/3 (the bench line).  focal: config 4 -- frozen global encoder + "
+                         "one private residual sub-encoder per GPU (log2T 21), no gradient exchange")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -209,10 +212,13 @@ def main():
     # (PersSampler.cpp:958-967); the bench measures the fineness-1 regime the other 120 k iterations run in
     sampler.ray_march_fineness_decay_end_iter_ = 0.0
     sampler.ray_march_fineness_ = 1.0
-    eng = GFNeRFEngine(sampler, log2_table_size=LOG2T, num_images=rig["c2w"].shape[0], seed=0, dist_group=group)
+    log2t = 21 if args.workload == "focal" else LOG2T
+    eng = GFNeRFEngine(sampler, log2_table_size=log2t, num_images=rig["c2w"].shape[0], seed=0, dist_group=group)
     if world > 1:    # identical parameters on every rank
         eng.sync.broadcast_([eng.enc.feat_pool_.data, eng.enc.prim_pool_, eng.mlp, eng.emb])
         eng.enc.shadow(force=True)
+    if args.workload == "focal":
+        eng.start_block_stage(seed=100 + rank)
 
     host = make_batches(rig, RAYS_PER_GPU, N_BATCHES, seed=1234 + rank)
     pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
@@ -287,7 +293,7 @@ def main():
         "composite_fwd": ("hbm", (28.0 + 12.0) * v_mean + 20.0 * RAYS_PER_GPU),
         "composite_bwd": ("hbm", 44.0 * v_mean + 20.0 * RAYS_PER_GPU),
         "mlp_fwd": ("tensor", 2.0 * 11392.0 * v_mean), "mlp_bwd": ("tensor", 2.0 * 2.0 * 11392.0 * v_mean),
-        "adam_table": ("hbm", 30.0 * 16 * (1 << LOG2T) * 2),
+        "adam_table": ("hbm", 30.0 * 16 * (1 << log2t) * 2),
     }
     kernels = []
     for name, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
@@ -318,11 +324,15 @@ def main():
 
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.workload == "global" else METRIC.replace("global stage", "focal stage"),
+            "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 tables + f16 tensor-core MLP, f32 accumulate / geometry / optimizer",
             "data": "synthetic",
-            "config": {"workload": workload_name(), "rays_per_gpu": RAYS_PER_GPU, "log2T": LOG2T, "hidden": 64,
+            "config": {"workload": workload_name() if args.workload == "global" else
+                       "GF-NeRF focal stage: frozen global Hash3DAnchored + MLPs, one zero-initialised residual "
+                       f"sub-encoder per GPU (log2T={log2t}), {RAYS_PER_GPU} rays/GPU/step, no gradient exchange",
+                       "rays_per_gpu": RAYS_PER_GPU, "log2T": log2t, "hidden": 64,
                        "samples_per_step_per_gpu": round(v_mean), "slots_per_step_per_gpu": RAYS_PER_GPU * 1024,
                        "l2_policy": "inputs larger than L2 (0.3 GB table+optimizer state, ~1 GB sample buffers, "
                                     f"{N_BATCHES} ray batches cycled)",

@@ -113,7 +113,7 @@ hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
                 const __half2* __restrict__ feat, const int32_t* __restrict__ prim_pool,
                 const float* __restrict__ bias_pool, const float* __restrict__ scales,
                 const float* __restrict__ pts, const AnchorT* __restrict__ anchors,
-                uint4* __restrict__ out16, float4* __restrict__ out32) {
+                uint4* __restrict__ out16, float4* __restrict__ out32, const uint4* __restrict__ base16) {
   if (d_n_ptr) {
     int64_t dn = *d_n_ptr;
     n = dn < n ? dn : n;
@@ -155,6 +155,15 @@ hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
         }
         __half2 o = __floats2half2_rn(t0, t1);
         packed[j] = *reinterpret_cast<uint32_t*>(&o);
+      }
+      if (base16) {  // focal stage: residual on top of the global encoder's features (nerfacto_field.py:477-489)
+        const uint4 b = __ldg(base16 + i * 4 + q);
+        const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          __half2 o = __hadd2(*reinterpret_cast<const __half2*>(&bb[j]), *reinterpret_cast<__half2*>(&packed[j]));
+          packed[j] = *reinterpret_cast<uint32_t*>(&o);
+        }
       }
       if (OUT16) out16[i * 4 + q] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       if (OUT32) {
@@ -331,10 +340,10 @@ int gf_hash_cast_table(const float* feat_f32, void* feat_f16, int64_t n_elems, v
   return GF_OK;
 }
 
-int gf_hash_forward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
-                    const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
-                    const float* level_scales, const float* pts, const void* anchors, int anchor_i64,
-                    void* out_f16, float* out_f32, void* stream) {
+static int hash_forward_impl(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                             const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
+                             const float* level_scales, const float* pts, const void* anchors, int anchor_i64,
+                             void* out_f16, float* out_f32, const void* base_f16, void* stream) {
   GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL,
              "gf_hash_forward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
              (long long)local_size);
@@ -347,7 +356,7 @@ int gf_hash_forward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_
 #define GF_FWD(P2, AT, O16, O32)                                                                              \
   hash_fwd_kernel<P2, AT, O16, O32><<<grid, kHashBlock, 0, st>>>(                                             \
       n, d_n_ptr, n_volumes, (uint32_t)local_size, (const __half2*)feat_f16, prim_pool, bias_pool,            \
-      level_scales, pts, (const AT*)anchors, (uint4*)out_f16, (float4*)out_f32)
+      level_scales, pts, (const AT*)anchors, (uint4*)out_f16, (float4*)out_f32, (const uint4*)base_f16)
 #define GF_FWD_O(P2, AT)                                     \
   do {                                                       \
     if (out_f16 && out_f32) GF_FWD(P2, AT, true, true);      \
@@ -362,6 +371,23 @@ int gf_hash_forward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_
 #undef GF_FWD_O
 #undef GF_FWD
   return check_launch("hash_fwd_kernel");
+}
+
+int gf_hash_forward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                    const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
+                    const float* level_scales, const float* pts, const void* anchors, int anchor_i64,
+                    void* out_f16, float* out_f32, void* stream) {
+  return hash_forward_impl(n, d_n_ptr, n_volumes, local_size, feat_f16, prim_pool, bias_pool, level_scales, pts,
+                           anchors, anchor_i64, out_f16, out_f32, nullptr, stream);
+}
+
+int gf_hash_forward_residual(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                             const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
+                             const float* level_scales, const float* pts, const void* anchors, int anchor_i64,
+                             const void* base_f16, void* out_f16, void* stream) {
+  GF_REQUIRE(base_f16 && out_f16, "gf_hash_forward_residual: null base / output");
+  return hash_forward_impl(n, d_n_ptr, n_volumes, local_size, feat_f16, prim_pool, bias_pool, level_scales, pts,
+                           anchors, anchor_i64, out_f16, nullptr, base_f16, stream);
 }
 
 int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,

@@ -104,6 +104,30 @@ class GFNeRFEngine:
         self._ws = {}
         self.step_count = 0
         self._deferred = None   # lr_scale of an optimizer step whose gradient reduce is still in flight
+        self.stage = "init_stage"
+        self.res = None         # focal stage: this GPU's residual sub-encoder
+        self.opt_res = None
+
+    # ---- focal (block) stage: reference gfnerf/nerfacto_field.py:458-489, gfnerf/nerfacto.py:432-488 ------------
+    def start_block_stage(self, log2_table_size: int = None, lr: float = 5e-3, seed: int = 1):
+        """Freezes the global table, both MLPs and the appearance embedding and adds a zero-initialised residual
+        sub-encoder whose features are summed with the global encoder's before the (frozen) MLP.  One block per GPU:
+        the residual table is private to this rank, so the focal stage has NO gradient exchange at all."""
+        self.flush()
+        log2_table_size = int(np.log2(self.enc.local_size_)) if log2_table_size is None else int(log2_table_size)
+        gen = torch.Generator().manual_seed(seed)
+        self.res = Hash3DAnchoredCore(log2_table_size, self.n_volumes, device=self.device, generator=gen)
+        self.res.feat_pool_.requires_grad_(False)
+        self.res.Zero()
+        self.res.shadow(force=True)
+        self.opt_res = _Adam(self.res.feat_pool_.detach().view(-1), lr)   # sub-encoder lr, gfnerf/nerfacto.py:483
+        self.stage = "block_stage"
+        self.sampler.UpdateMode(1)                                        # nerfacto.py:614-616
+
+    def end_block_stage(self):
+        self.res = self.opt_res = None
+        self.stage = "init_stage"
+        self.sampler.UpdateMode(0)
 
     # ---- per-stage device timing (bench / profiling only) -----------------------------------
     def enable_timers(self, on: bool = True):
@@ -156,6 +180,8 @@ class GFNeRFEngine:
         ray_bias = self._buf("ray_bias", (R, self.hidden), torch.float32)
         with self._stage("hash_fwd"):
             self.enc.launch_forward(cs.pts01, cs.anchor, out_f16=feat, d_n_ptr=cs.total, recast=False)
+            if self.res is not None:
+                self.res.launch_forward_residual(cs.pts01, cs.anchor, feat, d_n_ptr=cs.total, recast=False)
         with self._stage("ray_bias"):
             _lib.check(L.gf_mlp_ray_bias(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
                                          _lib.ptr(ray_emb), _lib.ptr(ray_bias), st), "gf_mlp_ray_bias")
@@ -225,7 +251,7 @@ class GFNeRFEngine:
                                             _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_charbonnier")
             # training feedback (gfnerf/nerfacto.py:598-616).  It only needs the forward's weights, so it is issued
             # here: its (tiny) MAX all-reduce over ranks must not queue behind the gradient all-reduce below
-            if update_octree:
+            if update_octree and self.stage == "init_stage":   # the octree is only updated in the init stage (:605)
                 with self._stage("octree_vote"):
                     self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
                     self.sampler.UpdateRayMarch(step)
@@ -237,27 +263,39 @@ class GFNeRFEngine:
                                                    _lib.ptr(rgb), _lib.ptr(trans), _lib.ptr(g_rgb), None, None,
                                                    _lib.ptr(d_sigma), _lib.ptr(d_rgb), st), "gf_composite_backward")
             d_feat = self._buf("d_feat", (cap, 32), torch.float16)
-            d_ray_bias = self._buf("d_ray_bias", (R, self.hidden), torch.float32, zero=True)
             grad_scale = float(2 ** int(np.ceil(np.log2(max(R, 1)))))
-            with self._stage("mlp_bwd"):
+            block = self.stage == "block_stage"
+            d_ray_bias = None if block else self._buf("d_ray_bias", (R, self.hidden), torch.float32, zero=True)
+            with self._stage("mlp_bwd"):   # block stage: frozen MLP, only d_feat
                 _lib.check(L.gf_mlp_backward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
                                              _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(d_sigma),
-                                             _lib.ptr(d_rgb), _lib.ptr(d_feat), _lib.ptr(self.opt_mlp.grad),
+                                             _lib.ptr(d_rgb), _lib.ptr(d_feat),
+                                             None if block else _lib.ptr(self.opt_mlp.grad),
                                              _lib.ptr(d_ray_bias), grad_scale, st), "gf_mlp_backward")
-            d_ray_emb = self._buf("d_ray_emb", (R, APPEARANCE_DIM), torch.float32, zero=True) if ray_emb is not None else None
-            with self._stage("ray_bias_bwd"):
-                _lib.check(L.gf_mlp_ray_bias_backward(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
-                                                      _lib.ptr(ray_emb), _lib.ptr(d_ray_bias),
-                                                      _lib.ptr(self.opt_mlp.grad), _lib.ptr(d_ray_emb), st),
-                           "gf_mlp_ray_bias_backward")
-                if d_ray_emb is not None:
-                    self.opt_emb.grad.view(-1, APPEARANCE_DIM).index_add_(0, rel_camera_indices.to(torch.int64),
-                                                                          d_ray_emb)
-            with self._stage("hash_bwd"):
-                self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_table.grad.view(-1, 2),
-                                         d_n_ptr=cs.total)
-            if optimizer_step:
-                self._reduce_and_step(lr_scale)
+            if block:
+                with self._stage("hash_bwd"):
+                    self.res.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_res.grad.view(-1, 2),
+                                             d_n_ptr=cs.total)
+                if optimizer_step:
+                    with self._stage("adam_table"):
+                        self.opt_res.step(shadow=self.res._shadow, lr=self.opt_res.lr * lr_scale)
+                    self.res.mark_shadow_fresh()
+            else:
+                d_ray_emb = (self._buf("d_ray_emb", (R, APPEARANCE_DIM), torch.float32, zero=True)
+                             if ray_emb is not None else None)
+                with self._stage("ray_bias_bwd"):
+                    _lib.check(L.gf_mlp_ray_bias_backward(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
+                                                          _lib.ptr(ray_emb), _lib.ptr(d_ray_bias),
+                                                          _lib.ptr(self.opt_mlp.grad), _lib.ptr(d_ray_emb), st),
+                               "gf_mlp_ray_bias_backward")
+                    if d_ray_emb is not None:
+                        self.opt_emb.grad.view(-1, APPEARANCE_DIM).index_add_(0, rel_camera_indices.to(torch.int64),
+                                                                              d_ray_emb)
+                with self._stage("hash_bwd"):
+                    self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_table.grad.view(-1, 2),
+                                             d_n_ptr=cs.total)
+                if optimizer_step:
+                    self._reduce_and_step(lr_scale)
             self.step_count += 1
         return StepOutputs(out_rgb, depth, acc, loss, cs.total)
 

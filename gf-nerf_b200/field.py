@@ -67,9 +67,7 @@ class _FusedFieldFn(torch.autograd.Function):
         feat = torch.empty((V, HASH_DIM), dtype=torch.float16, device=dev)
         enc.launch_forward(pts01, anchors, out_f16=feat)
         if res_enc is not None:   # focal stage: residual at the hash-feature level (nerfacto_field.py:477-489)
-            res = torch.empty((V, HASH_DIM), dtype=torch.float16, device=dev)
-            res_enc.launch_forward(pts01, anchors, out_f16=res)
-            feat = (feat.float() + res.float()).half()
+            res_enc.launch_forward_residual(pts01, anchors, feat)
         blob = mlp_blob.detach().contiguous().float()
         emb = None if ray_emb is None else ray_emb.detach().contiguous().float()
         ray_bias = torch.empty((R, hidden), dtype=torch.float32, device=dev)

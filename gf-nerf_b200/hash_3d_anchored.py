@@ -153,6 +153,16 @@ class Hash3DAnchoredCore:
                 _lib.ptr(points), _lib.ptr(anchors), int(anchors.dtype == torch.int64),
                 _lib.ptr(out_f16), _lib.ptr(out_f32), _lib.cur_stream()), "gf_hash_forward")
 
+    def launch_forward_residual(self, points, anchors, base_f16, out_f16=None, d_n_ptr=None, recast=True):
+        """out_f16 = base_f16 + encode(points) (focal-stage residual, nerfacto_field.py:477-489); in place by default"""
+        out_f16 = base_f16 if out_f16 is None else out_f16
+        with torch.cuda.device(points.device):
+            _lib.check(_lib.lib().gf_hash_forward_residual(
+                points.shape[0], _lib.ptr(d_n_ptr), self.n_volumes_, self.local_size_,
+                _lib.ptr(self.shadow(force=recast)), _lib.ptr(self.prim_pool_), _lib.ptr(self.bias_pool_),
+                _lib.ptr(self.level_scales_), _lib.ptr(points), _lib.ptr(anchors), int(anchors.dtype == torch.int64),
+                _lib.ptr(base_f16), _lib.ptr(out_f16), _lib.cur_stream()), "gf_hash_forward_residual")
+
     def launch_backward(self, points, anchors, grad_in, grad_is_scaled_f16, grad_table, d_n_ptr=None):
         with torch.cuda.device(points.device):
             _lib.check(_lib.lib().gf_hash_backward(

@@ -79,6 +79,14 @@ int gf_hash_forward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_
                     const float* pts, const void* anchors, int anchor_i64,
                     void* out_f16, float* out_f32, void* stream);
 
+/* Focal (block) stage: out_f16 = base_f16 + encode(pts) in fp16, the residual sub-encoder's features added to the
+ * frozen global encoder's at the hash-feature level (gfnerf/nerfacto_field.py:477-489).  base_f16 / out_f16:
+ * __half [n,32]; they may alias. */
+int gf_hash_forward_residual(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                             const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
+                             const float* level_scales, const float* pts, const void* anchors, int anchor_i64,
+                             const void* base_f16, void* out_f16, void* stream);
+
 /* grad_in: fp32 [n,32] dL/dout (unscaled; grad_in_is_scaled_f16=0) -- the kernel
  * applies the reference's x128 -> fp16 quantisation (:209) -- or __half [n,32]
  * already scaled by 128 (grad_in_is_scaled_f16=1, produced by gf_mlp_backward).

@@ -114,6 +114,45 @@ def test_block_stage_trains_only_the_residual_table():
         assert torch.equal(f.base_encoding_3.hash_3d.feat_pool_.detach(), keep)
 
 
+def test_engine_block_stage_equals_operator_api_block_stage():
+    """Focal stage of the fused engine (frozen global table / MLP / embedding, private residual table, no exchange)
+    against the operator-API field in block_stage on the same rays."""
+    rig = load_rig("rig8")
+    eng, model = build(rig)
+    R = 256
+    rb, o, d, cam = bundle(rig, R, seed=21)
+    rb.steps = None
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    eng.start_block_stage(lr=5e-3)
+    f = model.field
+    f.add_table(0)
+    f.set_stage("block_stage", active_block=0)
+    f.base_encoding_0.load_states(eng.res.States(), 0)          # same primes (and zeros)
+    model.train()
+    model.persampler.sampler.UpdateMode(1)
+    table0, mlp0 = eng.enc.feat_pool_.detach().clone(), eng.mlp.clone()
+    out = eng.train_step(o, d, target, cam, optimizer_step=False)
+    res = model.get_outputs(rb)
+    assert torch.allclose(res["rgb"], out.rgb, rtol=1e-4, atol=1e-5)
+    diff = res["rgb"] - target
+    (torch.sqrt(diff * diff + 1e-12).sum() / R).backward()
+    g = f.base_encoding_0.hash_3d.feat_pool_.grad
+    ref = eng.opt_res.grad.view_as(g)
+    assert float(ref.abs().max()) > 0
+    assert float((g - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    assert not eng.opt_table.grad.any() and not eng.opt_mlp.grad.any()      # frozen: nothing accumulated
+    # a few optimizer steps: only the residual table moves, the loss goes down
+    losses = []
+    for it in range(12):
+        losses.append(float(eng.train_step(o, d, target, cam).loss))
+    assert losses[-1] < losses[0]
+    assert torch.equal(eng.enc.feat_pool_.detach(), table0) and torch.equal(eng.mlp, mlp0)
+    assert float(eng.res.feat_pool_.abs().max()) > 0
+    assert torch.equal(eng.res._shadow, eng.res.feat_pool_.detach().half())
+    eng.end_block_stage()
+    assert eng.stage == "init_stage" and eng.res is None
+
+
 def test_state_dict_keys_match_reference_names():
     rig = load_rig("rig8")
     _, model = build(rig)
