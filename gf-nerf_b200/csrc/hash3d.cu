@@ -246,15 +246,17 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
         const int64_t pvol = __shfl_up_sync(0xffffffffu, vol, 1);
         const bool head = lane == 0 || ppx != c.px || ppy != c.py || ppz != c.pz || pvol != vol;
         const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        if (__popc(heads) <= 24) {  // warp-uniform: worth reducing
-          const uint32_t above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
-          const int end = above ? (__ffs(above) - 1) : 32;
+        const uint32_t above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
+        const int end = above ? (__ffs(above) - 1) : 32;
+        // longest run in the warp: the segmented reduction needs ceil(log2) of it steps -- 5 on the coarse levels
+        // (the whole warp in one cell), 0..2 on the fine ones, where most of the samples are
+        const int maxrun = (int)__reduce_max_sync(0xffffffffu, head ? (unsigned)(end - lane) : 0u);
+        if (maxrun > 1) {  // warp-uniform
           if (!valid) {
 #pragma unroll
             for (int d = 0; d < 8; d++) c0[d] = c1[d] = 0.f;
           }
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
+          for (int off = 1; off < maxrun; off <<= 1) {
             const bool take = lane + off < end;
 #pragma unroll
             for (int d = 0; d < 8; d++) {
