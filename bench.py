@@ -309,9 +309,19 @@ def main():
                 ent.update({"bound": "tensor", "achieved": round(a, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": round(a / peaks["bf16_tflops"], 4)})
         kernels.append(ent)
-    top = next(k for k in kernels if "bound" in k)
+    # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01c_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = {k: v["dram_bytes_per_launch"] for k, v in json.load(f)["kernels"].items()}
+    for k in kernels:
+        if k["kernel"] in traffic:
+            k["traffic"] = traffic[k["kernel"]]
+    top = next(k for k in kernels if "bound" in k)          # the dominant kernel of the step
     roofline = {k: top[k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-    roofline.update({"kernel": top["kernel"], "traffic": None, "peak_source": peaks["src"], "ms": top["ms"]})
+    roofline.update({"kernel": top["kernel"], "traffic": top.get("traffic"), "peak_source": peaks["src"],
+                     "ms": top["ms"]})
     if rank == 0 and args.breakdown:
         for k in kernels:
             print(k, file=sys.stderr)
