@@ -153,7 +153,7 @@ def reference_arm(args):
     steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
     value, ms, cores, v = time_oracle(rays, steps, warmup)
     sample = f"{rays} rays/step ({v:.0f} samples), {steps} steps after {warmup} warm-ups, same rig / table / MLP shapes"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -168,23 +168,91 @@ def workload_name():
             f"{RAYS_PER_GPU} rays/GPU/step, up to 1024 samples/ray, H=64 MLPs, fwd+bwd+Adam")
 
 
+def render_arm(args):
+    """BASELINE config 5: forward-only render of 1920x1080 frames along a synthetic fly-over, log2T = 23 tables."""
+    import torch
+    from gfnerf_b200 import _lib
+    from gfnerf_b200.engine import GFNeRFEngine
+    from gfnerf_b200.persoctree import frame_rays
+    from tests.helpers import make_sampler
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    rig = load_rig()
+    sampler = make_sampler(rig, mode=1, device=dev)
+    eng = GFNeRFEngine(sampler, log2_table_size=23, num_images=rig["c2w"].shape[0], seed=0)
+    eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)      # post-training feature scale: opaque surfaces, realistic ray lengths
+    eng.enc.shadow(force=True)
+    W, H = 1920, 1080
+    n_frames = 4
+    frames = []
+    for k in range(n_frames):                         # straight fly-over between two rig cameras
+        c2w = rig["c2w"][10 + k].copy()
+        o, d = frame_rays(c2w, rig["intri"][0], W, H)
+        frames.append((torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)))
+    steps, warmup = max(1, min(args.steps, 8)), 3
+    for i in range(warmup):
+        eng.render_image(*frames[i % n_frames])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    e0.record()
+    for i in range(steps):
+        rgb, depth, acc = eng.render_image(*frames[i % n_frames])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    emit(({
+        "metric": "render rays/sec (forward only), 1920x1080 frames, log2T=23", "value": W * H / (ms * 1e-3),
+        "unit": "rays/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 tables + f16 tensor-core MLP, f32 geometry", "data": "synthetic",
+        "config": {"workload": "forward-only render of 1920x1080 synthetic frames, Hash3DAnchored log2T=23, eval sampling, "
+                               "32768-ray chunks", "frame_ms": ms, "fps": 1e3 / ms},
+        "gpu_launches": int(_lib.launch_count() - l0),
+        "check": {"rgb_mean": float(rgb.mean()), "acc_mean": float(acc.mean()), "finite": bool(torch.isfinite(rgb).all())},
+    }))
+
+
 # --------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries (NCCL prints its version banner there) must not add to
+    it: route file descriptor 1 to stderr for the whole run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="global", choices=["global", "focal"],
+    ap.add_argument("--workload", default="global", choices=["global", "focal", "render"],
                     help="global: BASELINE config 2/3 (the bench line).  focal: config 4 -- frozen global encoder + "
-                         "one private residual sub-encoder per GPU (log2T 21), no gradient exchange")
+                         "one private residual sub-encoder per GPU (log2T 21), no gradient exchange.  render: config 5 "
+                         "-- forward-only 1920x1080 frames, log2T 23, eval sampling; a step = one frame")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload == "render":
+        render_arm(args)
+        return
 
     import torch
     import torch.distributed as dist
@@ -333,7 +401,7 @@ def main():
                         "sample": f"256 rays/step ({cvs:.0f} samples), 3 steps after 1 warm-up, same rig / table / MLP shapes"}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC if args.workload == "global" else METRIC.replace("global stage", "focal stage"),
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -230,6 +230,24 @@ class GFNeRFEngine:
         return StepOutputs(out_rgb, depth, acc, None, cs.total)
 
     @torch.no_grad()
+    def render_image(self, rays_o, rays_d, rel_camera_index: int = 0, chunk: int = 32768):
+        """Full-image render in chunks: Model.get_outputs_for_camera_ray_bundle (nerfstudio/models/base_model.py:
+        166-190, eval_num_rays_per_chunk = 2048 in the reference, gfnerf/config.py:109; here the chunk is as large
+        as the workspace allows and there is no host sync inside it).  Returns rgb [N,3], depth [N], acc [N]."""
+        N = rays_o.shape[0]
+        rgb = torch.empty((N, 3), dtype=torch.float32, device=self.device)
+        depth = torch.empty(N, dtype=torch.float32, device=self.device)
+        acc = torch.empty(N, dtype=torch.float32, device=self.device)
+        cam = None
+        if self.emb is not None:
+            cam = torch.full((chunk,), int(rel_camera_index), dtype=torch.int64, device=self.device)
+        for a in range(0, N, chunk):
+            b = min(a + chunk, N)
+            out = self.render(rays_o[a:b], rays_d[a:b], None if cam is None else cam[:b - a])
+            rgb[a:b], depth[a:b], acc[a:b] = out.rgb, out.depth, out.accumulation
+        return rgb, depth, acc
+
+    @torch.no_grad()
     def train_step(self, rays_o, rays_d, target_rgb, rel_camera_indices=None, noise=None, lr_scale: float = 1.0,
                    update_octree: bool = True, optimizer_step: bool = True) -> StepOutputs:
         L = _lib.lib()

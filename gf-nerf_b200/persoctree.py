@@ -456,3 +456,15 @@ def rig_rays(c2w: np.ndarray, intri: np.ndarray, n_rays: int, seed: int = 0):
     d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
     o = c2w[cam][:, :, 3].astype(np.float32)
     return np.ascontiguousarray(o), np.ascontiguousarray(d), cam.astype(np.int64)
+
+
+def frame_rays(c2w_cam: np.ndarray, intri_cam: np.ndarray, width: int, height: int):
+    """All pixel-centre rays of one camera, row-major [H*W]: origins, unit directions (same pinhole / OpenGL
+    convention as rig_rays; the caller of the reference is Cameras.generate_rays, out of scope)."""
+    px, py = np.meshgrid(np.arange(width, dtype=np.float32) + 0.5, np.arange(height, dtype=np.float32) + 0.5)
+    fx, fy, cx, cy = intri_cam[0, 0], intri_cam[1, 1], intri_cam[0, 2], intri_cam[1, 2]
+    d_cam = np.stack([(px - cx) / fx, -(py - cy) / fy, -np.ones_like(px)], -1).reshape(-1, 3).astype(np.float32)
+    d = d_cam @ c2w_cam[:, :3].T.astype(np.float32)
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+    o = np.broadcast_to(c2w_cam[:, 3].astype(np.float32), d.shape)
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)

@@ -101,3 +101,20 @@ def test_training_reduces_loss_and_prunes():
     r = eng.render(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(cam).cuda())
     assert r.rgb.shape == (R, 3) and float(r.rgb.min()) >= 0 and float(r.rgb.max()) <= 1
     assert torch.isfinite(r.depth).all()
+
+
+def test_render_image_chunking_is_invisible():
+    """Config 5 path: a frame rendered in chunks equals the same rays rendered in one call (eval sampling, no state
+    is carried between chunks), and padding / ray misses give finite zeros."""
+    from gfnerf_b200.persoctree import frame_rays
+    rig = load_rig("rig8")
+    eng = make_engine(rig, log2T=15)
+    eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
+    eng.enc.shadow(force=True)
+    o, d = frame_rays(rig["c2w"][3], rig["intri"][0], 96, 54)
+    to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    rgb, depth, acc = eng.render_image(to, td, rel_camera_index=3, chunk=1000)
+    cam = torch.full((to.shape[0],), 3, dtype=torch.int64, device="cuda")
+    one = eng.render(to, td, cam)
+    assert torch.equal(rgb, one.rgb) and torch.equal(acc, one.accumulation) and torch.equal(depth, one.depth)
+    assert torch.isfinite(rgb).all() and float(rgb.min()) >= 0 and float(rgb.max()) <= 1
