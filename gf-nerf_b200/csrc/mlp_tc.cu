@@ -197,7 +197,7 @@ __device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const uint3
   tc_fence_after();
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, MODE == kFwd ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, MODE == kFwd ? 4 : 2)
 mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __restrict__ params,
               const __half* __restrict__ feat, const int32_t* __restrict__ ray_id,
               const float* __restrict__ ray_bias, float* __restrict__ sigma, float* __restrict__ rgb,
@@ -614,7 +614,7 @@ int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params,
   int rc = set_attrs();
   if (rc) return rc;
   const int64_t tiles = div_up(n, tc::kTile);
-  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 3);
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 4);
   tc::mlp_tc_kernel<tc::kFwd><<<grid, tc::kThreads, kSmemSmall, st>>>(
       n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, sigma, rgb, nullptr, nullptr, nullptr, nullptr,
       nullptr, 1.f);

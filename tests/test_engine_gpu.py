@@ -118,3 +118,46 @@ def test_render_image_chunking_is_invisible():
     one = eng.render(to, td, cam)
     assert torch.equal(rgb, one.rgb) and torch.equal(acc, one.accumulation) and torch.equal(depth, one.depth)
     assert torch.isfinite(rgb).all() and float(rgb.min()) >= 0 and float(rgb.max()) <= 1
+
+
+def test_full_size_step_properties():
+    """BASELINE config 2 sizes (8192 rays, up to 1024 samples per ray, log2T = 19, 400-camera rig): size-independent
+    properties of one training step -- the oracle is too slow here, so invariants instead of values."""
+    from gfnerf_b200.persoctree import rig_rays
+    rig = load_rig("rig20")
+    eng = make_engine(rig, log2T=19, mode=0)
+    eng.enc.feat_pool_.data.uniform_(-0.3, 0.3)
+    eng.enc.shadow(force=True)
+    R = 8192
+    o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=77)
+    to, td, tc = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(cam).cuda()
+    noise = torch.rand(1024 + R + 10, generator=torch.Generator().manual_seed(5)).cuda() + 0.5
+    cs = eng.sampler.sample_compact(to, td, noise=noise)
+    counts, offsets = cs.counts.cpu().numpy(), cs.offsets.cpu().numpy()
+    V = int(cs.total.item())
+    assert counts.min() >= 0 and counts.max() <= 1024 and (counts == 1024).any()      # the per-ray cap is reached
+    assert V == counts.sum() and np.array_equal(offsets, np.concatenate([[0], np.cumsum(counts)]))
+    t = cs.t[:V].cpu().numpy()
+    ray = cs.ray_id[:V].cpu().numpy()
+    assert np.array_equal(ray, np.repeat(np.arange(R), counts))
+    same = ray[1:] == ray[:-1]
+    assert np.all(t[1:][same] > t[:-1][same])                                         # t strictly increases along a ray
+    assert float(cs.delta[:V].min()) > 0 and 0.0 < float(cs.pts01[:V].min()) and float(cs.pts01[:V].max()) < 1.0
+    assert int(cs.anchor[:V].min()) >= 0 and int(cs.anchor[:V].max()) < eng.n_volumes
+    # determinism of the forward (no atomics on its path) and the compositing invariants
+    r1 = eng.render(to, td, tc, noise=noise)
+    r2 = eng.render(to, td, tc, noise=noise)
+    assert torch.equal(r1.rgb, r2.rgb) and torch.equal(r1.depth, r2.depth)
+    acc = r1.accumulation
+    assert float(acc.min()) >= 0 and float(acc.max()) <= 1 + 1e-5
+    assert float(r1.rgb.min()) >= 0 and float(r1.rgb.max()) <= 1
+    assert bool((acc[torch.from_numpy(counts == 0).cuda()] == 0).all())                # rays that miss render nothing
+    # one optimizer step: finite loss, gradients only where samples fell, shadow == fp16(table)
+    before = eng.enc.feat_pool_.detach().clone()
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(6)).cuda()
+    out = eng.train_step(to, td, target, tc, noise=noise)
+    assert np.isfinite(float(out.loss))
+    moved = (eng.enc.feat_pool_.detach() != before).any(-1)
+    assert 0 < int(moved.sum()) < moved.numel()
+    assert torch.equal(eng.enc._shadow, eng.enc.feat_pool_.detach().half())
+    assert not eng.opt_table.grad.any()
