@@ -298,9 +298,9 @@ def main():
         return eng.train_step(o, d, tgt, cam)
 
     def step_e2e(i):
-        o, d, cam, tgt = (a.to(dev, non_blocking=True) for a in pinned[i % N_BATCHES])
-        out = eng.train_step(o, d, tgt, cam)
-        return float(out.loss.cpu())          # device -> host read of the step's result
+        # the public host-buffer entry point: pinned host batch in (H2D inside the step), the step's loss out (D2H)
+        o, d, cam, tgt = pinned[i % N_BATCHES]
+        return eng.train_step_host(o, d, tgt, cam)
 
     def barrier():
         if world > 1:
@@ -334,7 +334,9 @@ def main():
     clocks.stop_flag = True
     ms_step = ms_total / args.steps
     value = RAYS_PER_GPU * world * args.steps / (ms_total * 1e-3)
-    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    ms_e2e, _ = timed(step_e2e, args.steps, 3)       # the loss copies are stream-ordered: inside the timed region
+    e2e_losses = eng.read_losses()
+    assert len(e2e_losses) == args.steps + 3 and all(np.isfinite(e2e_losses)), e2e_losses
     e2e_value = RAYS_PER_GPU * world * args.steps / (ms_e2e * 1e-3)
 
     # per-kernel device times (same steps, events around every launch), for the roofline of the dominant kernel

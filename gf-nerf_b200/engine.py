@@ -317,6 +317,61 @@ class GFNeRFEngine:
             self.step_count += 1
         return StepOutputs(out_rgb, depth, acc, loss, cs.total)
 
+    # ---- host-buffer entry point ------------------------------------------------------------------------------
+    @torch.no_grad()
+    def train_step_host(self, rays_o, rays_d, target_rgb, rel_camera_indices=None, **kw) -> StepOutputs:
+        """`train_step` for HOST tensors (pinned for true asynchrony), the call a data loader makes: the batch goes
+        host -> device on a copy stream into one of two staging slots, so the copy of batch k + 1 overlaps the
+        compute of batch k; the step's loss comes back device -> host asynchronously into a pinned ring
+        (`read_losses()`), so the host never blocks inside the training loop (the reference blocks five times per
+        step on .item())."""
+        dev = self.device
+        if not hasattr(self, "_h2d"):
+            self._h2d = dict(stream=torch.cuda.Stream(device=dev), slot=0, free=[None, None], bufs=[{}, {}],
+                             losses=[], pinned=[])
+        h = self._h2d
+        slot = h["slot"]
+        h["slot"] ^= 1
+        cur = torch.cuda.current_stream(dev)
+        names = ("o", "d", "t", "c")
+        host = (rays_o, rays_d, target_rgb, rel_camera_indices)
+        staged = []
+        with torch.cuda.stream(h["stream"]):
+            if h["free"][slot] is not None:                      # the step that last read this slot has finished
+                h["stream"].wait_event(h["free"][slot])
+            for name, src in zip(names, host):
+                if src is None:
+                    staged.append(None)
+                    continue
+                buf = h["bufs"][slot].get(name)
+                if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+                    buf = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                    h["bufs"][slot][name] = buf
+                buf.copy_(src, non_blocking=True)
+                staged.append(buf)
+            ready = h["stream"].record_event()
+        cur.wait_event(ready)
+        out = self.train_step(staged[0], staged[1], staged[2], staged[3], **kw)
+        h["free"][slot] = cur.record_event()
+        k = len(h["losses"])
+        if k >= len(h["pinned"]):
+            h["pinned"].append(torch.empty(1, dtype=torch.float32).pin_memory())
+        h["pinned"][k].copy_(out.loss, non_blocking=True)
+        h["losses"].append(cur.record_event())
+        return out
+
+    def read_losses(self):
+        """Losses of the `train_step_host` calls since the last read (waits for their device -> host copies)."""
+        h = getattr(self, "_h2d", None)
+        if h is None:
+            return []
+        vals = []
+        for k, ev in enumerate(h["losses"]):
+            ev.synchronize()
+            vals.append(float(h["pinned"][k][0]))
+        h["losses"] = []
+        return vals
+
     def _reduce_and_step(self, lr_scale: float):
         """DDP semantics (mean over ranks) for ALL parameters -- including the hash table, which the reference's
         DDP wrapper silently skips because feat_pool is not a registered nn.Parameter.
