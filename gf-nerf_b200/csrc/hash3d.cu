@@ -67,15 +67,15 @@ hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
-    const int64_t vol = (int64_t)anchors[i];
+    const int vol = (int)anchors[i];
 #pragma unroll 1
     for (int q = 0; q < GF_N_LEVELS / 4; q++) {
       uint32_t packed[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int l = 4 * q + j;
-        const int64_t tr = ((int64_t)l * n_volumes + vol) * 3;
-        const Cell c = cell_of(x, y, z, s_scale[l], bias_pool + tr);
+        const int tr = (l * n_volumes + vol) * 3;
+        const Cell c = cell_of(x, y, z, s_scale[l], bias_pool ? bias_pool + tr : nullptr);
         const uint32_t pa = (uint32_t)__ldg(prim_pool + tr), pb = (uint32_t)__ldg(prim_pool + tr + 1),
                        pc = (uint32_t)__ldg(prim_pool + tr + 2);
         uint32_t pos[8];
@@ -142,12 +142,12 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
     const int64_t i = base + lane;
     const bool valid = i < n;
     float x = 0.f, y = 0.f, z = 0.f;
-    int64_t vol = 0;
+    int vol = 0;
     if (valid) {
       x = __ldg(pts + 3 * i);
       y = __ldg(pts + 3 * i + 1);
       z = __ldg(pts + 3 * i + 2);
-      vol = (int64_t)anchors[i];
+      vol = (int)anchors[i];
     }
 #pragma unroll 2
     for (int l = 0; l < GF_N_LEVELS; l++) {
@@ -179,10 +179,10 @@ hash_rows_kernel(int64_t n, int32_t n_volumes, uint32_t local_size, const int32_
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
-    const int64_t vol = (int64_t)anchors[i];
+    const int vol = (int)anchors[i];
     for (int l = 0; l < GF_N_LEVELS; l++) {
-      const int64_t tr = ((int64_t)l * n_volumes + vol) * 3;
-      const Cell c = cell_of(x, y, z, __ldg(scales + l), bias_pool + tr);
+      const int tr = (l * n_volumes + vol) * 3;
+      const Cell c = cell_of(x, y, z, __ldg(scales + l), bias_pool ? bias_pool + tr : nullptr);
       uint32_t pos[8];
       corners<POW2>(c, (uint32_t)__ldg(prim_pool + tr), (uint32_t)__ldg(prim_pool + tr + 1),
                     (uint32_t)__ldg(prim_pool + tr + 2), local_size, pos);
@@ -236,9 +236,10 @@ static int hash_forward_impl(int64_t n, const int32_t* d_n_ptr, int32_t n_volume
   GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL,
              "gf_hash_forward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
              (long long)local_size);
+  GF_REQUIRE((int64_t)n_volumes * GF_N_LEVELS * 3 <= 0x7fffffffLL, "gf_hash_forward: n_volumes too large");
   GF_REQUIRE(out_f16 || out_f32, "gf_hash_forward: no output buffer");
   if (n == 0) return GF_OK;
-  GF_REQUIRE(feat_f16 && prim_pool && bias_pool && level_scales && pts && anchors, "gf_hash_forward: null pointer");
+  GF_REQUIRE(feat_f16 && prim_pool && level_scales && pts && anchors, "gf_hash_forward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stride_grid(n, kHashBlock, 8, 4);
   const bool p2 = is_pow2(local_size);
@@ -287,8 +288,7 @@ int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64
              "gf_hash_backward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
              (long long)local_size);
   if (n == 0) return GF_OK;
-  GF_REQUIRE(prim_pool && bias_pool && level_scales && pts && anchors && grad_in && grad_table,
-             "gf_hash_backward: null pointer");
+  GF_REQUIRE(prim_pool && level_scales && pts && anchors && grad_in && grad_table, "gf_hash_backward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stride_grid(n, kHashBlock, 4, 4);
   const bool p2 = is_pow2(local_size);
@@ -319,7 +319,7 @@ int gf_hash_corner_rows(int64_t n, int32_t n_volumes, int64_t local_size, const 
   GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size * GF_N_LEVELS <= 0x7fffffffLL,
              "gf_hash_corner_rows: bad sizes");
   if (n == 0) return GF_OK;
-  GF_REQUIRE(prim_pool && bias_pool && level_scales && pts && anchors && rows, "gf_hash_corner_rows: null pointer");
+  GF_REQUIRE(prim_pool && level_scales && pts && anchors && rows, "gf_hash_corner_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stride_grid(n, kHashBlock, 8, 4);
   const bool p2 = is_pow2(local_size);

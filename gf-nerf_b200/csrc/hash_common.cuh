@@ -17,11 +17,12 @@ struct Cell {
   float a, b, c;
 };
 
-// :26-46  pt*mul + bias, floor, fractional part.
+// :26-46  pt*mul + bias, floor, fractional part.  bias == nullptr: an all-zero bias pool (what the reference always
+// has, Hash3DAnchored.cpp:57-62), same arithmetic without the three loads.
 __device__ __forceinline__ Cell cell_of(float x, float y, float z, float mul, const float* __restrict__ bias) {
-  float p0 = __fmaf_rn(x, mul, __ldg(bias + 0));
-  float p1 = __fmaf_rn(y, mul, __ldg(bias + 1));
-  float p2 = __fmaf_rn(z, mul, __ldg(bias + 2));
+  float p0 = __fmaf_rn(x, mul, bias ? __ldg(bias + 0) : 0.f);
+  float p1 = __fmaf_rn(y, mul, bias ? __ldg(bias + 1) : 0.f);
+  float p2 = __fmaf_rn(z, mul, bias ? __ldg(bias + 2) : 0.f);
   float f0 = floorf(p0), f1 = floorf(p1), f2 = floorf(p2);
   Cell c;
   c.px = __float2uint_rz(f0);  // saturating, negative/NaN -> 0
@@ -73,13 +74,13 @@ __device__ __forceinline__ float q16(float v) { return __half2float(__float2half
 // depth adapts to the longest run, and let the run's first lane issue the 8 vectorised fp32 reductions.
 // g0 / g1: this sample's two gradients of the level, already fp16(g * 128) values.  Must be called by all 32 lanes.
 template <bool POW2>
-__device__ __forceinline__ void hash_scatter_level(int l, float x, float y, float z, int64_t vol, bool valid, float g0,
+__device__ __forceinline__ void hash_scatter_level(int l, float x, float y, float z, int vol, bool valid, float g0,
                                                    float g1, int lane, int32_t n_volumes, uint32_t local_size,
                                                    const int32_t* __restrict__ prim_pool,
                                                    const float* __restrict__ bias_pool, float scale,
                                                    float* __restrict__ grad_table, bool aggregate) {
-  const int64_t tr = ((int64_t)l * n_volumes + vol) * 3;
-  const Cell c = cell_of(x, y, z, scale, bias_pool + tr);
+  const int tr = (l * n_volumes + vol) * 3;
+  const Cell c = cell_of(x, y, z, scale, bias_pool ? bias_pool + tr : nullptr);
   const uint32_t pa = (uint32_t)__ldg(prim_pool + tr), pb = (uint32_t)__ldg(prim_pool + tr + 1),
                  pc = (uint32_t)__ldg(prim_pool + tr + 2);
   uint32_t pos[8];
@@ -97,7 +98,7 @@ __device__ __forceinline__ void hash_scatter_level(int l, float x, float y, floa
     // runs of lanes in the same cell of the same volume -> one reduction per run
     const uint32_t ppx = __shfl_up_sync(0xffffffffu, c.px, 1), ppy = __shfl_up_sync(0xffffffffu, c.py, 1),
                    ppz = __shfl_up_sync(0xffffffffu, c.pz, 1);
-    const int64_t pvol = __shfl_up_sync(0xffffffffu, vol, 1);
+    const int pvol = __shfl_up_sync(0xffffffffu, vol, 1);
     const bool head = lane == 0 || ppx != c.px || ppy != c.py || ppz != c.pz || pvol != vol;
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
     const uint32_t above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));

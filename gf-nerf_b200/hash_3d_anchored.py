@@ -142,6 +142,15 @@ class Hash3DAnchoredCore:
         """Called by the fused Adam step, which writes the shadow itself."""
         self._shadow_key = (self.feat_pool_.data_ptr(), self.feat_pool_._version)
 
+    def _bias(self):
+        """bias_pool for the kernels: None (= zeros, no loads) while the pool is all zero, which it always is in the
+        reference; checked once per pool (a host sync) and again after LoadStates"""
+        key = (self.bias_pool_.data_ptr(), self.bias_pool_._version)
+        if getattr(self, "_bias_key", None) != key:
+            self._bias_zero = not bool(self.bias_pool_.any())
+            self._bias_key = key
+        return None if self._bias_zero else self.bias_pool_
+
     def launch_forward(self, points, anchors, out_f16=None, out_f32=None, d_n_ptr=None, recast=True):
         assert points.dtype == torch.float32 and points.is_contiguous()
         assert anchors.dtype in (torch.int64, torch.int32) and anchors.is_contiguous()
@@ -149,7 +158,7 @@ class Hash3DAnchoredCore:
             _lib.check(_lib.lib().gf_hash_forward(
                 points.shape[0], _lib.ptr(d_n_ptr), self.n_volumes_, self.local_size_,
                 _lib.ptr(self.shadow(force=recast)),
-                _lib.ptr(self.prim_pool_), _lib.ptr(self.bias_pool_), _lib.ptr(self.level_scales_),
+                _lib.ptr(self.prim_pool_), _lib.ptr(self._bias()), _lib.ptr(self.level_scales_),
                 _lib.ptr(points), _lib.ptr(anchors), int(anchors.dtype == torch.int64),
                 _lib.ptr(out_f16), _lib.ptr(out_f32), _lib.cur_stream()), "gf_hash_forward")
 
@@ -159,7 +168,7 @@ class Hash3DAnchoredCore:
         with torch.cuda.device(points.device):
             _lib.check(_lib.lib().gf_hash_forward_residual(
                 points.shape[0], _lib.ptr(d_n_ptr), self.n_volumes_, self.local_size_,
-                _lib.ptr(self.shadow(force=recast)), _lib.ptr(self.prim_pool_), _lib.ptr(self.bias_pool_),
+                _lib.ptr(self.shadow(force=recast)), _lib.ptr(self.prim_pool_), _lib.ptr(self._bias()),
                 _lib.ptr(self.level_scales_), _lib.ptr(points), _lib.ptr(anchors), int(anchors.dtype == torch.int64),
                 _lib.ptr(base_f16), _lib.ptr(out_f16), _lib.cur_stream()), "gf_hash_forward_residual")
 
@@ -167,7 +176,7 @@ class Hash3DAnchoredCore:
         with torch.cuda.device(points.device):
             _lib.check(_lib.lib().gf_hash_backward(
                 points.shape[0], _lib.ptr(d_n_ptr), self.n_volumes_, self.local_size_, _lib.ptr(self.prim_pool_),
-                _lib.ptr(self.bias_pool_), _lib.ptr(self.level_scales_), _lib.ptr(points), _lib.ptr(anchors),
+                _lib.ptr(self._bias()), _lib.ptr(self.level_scales_), _lib.ptr(points), _lib.ptr(anchors),
                 int(anchors.dtype == torch.int64), _lib.ptr(grad_in), int(bool(grad_is_scaled_f16)),
                 _lib.ptr(grad_table), _lib.cur_stream()), "gf_hash_backward")
 

@@ -54,7 +54,8 @@ int64_t gf_launch_count(void);
  * Layouts (all row-major, contiguous):
  *   feat_f16   __half [n_levels*local_size, 2]   fp16 shadow of feat_pool
  *   prim_pool  int32  [16, n_volumes, 3]
- *   bias_pool  float  [16*n_volumes, 3]
+ *   bias_pool  float  [16*n_volumes, 3], or NULL = all zeros (what the reference always has,
+ *              Hash3DAnchored.cpp:57-62: rand_bias is never set) -- same arithmetic, three loads fewer per level
  *   pts        float  [n, 3]   (already (warp+1.5)/3, nerfacto_field.py:431)
  *   anchors    int64 [n] (anchor_i64=1, the reference dtype) or int32 [n]
  *   level_scales float[16] device table, see gf_hash_level_scales

@@ -148,3 +148,29 @@ def test_full_size_properties():
     y2 = core.AnchoredQuery(pts, anc)
     # (exact except where the fp16 result is subnormal: allow one subnormal step)
     assert float((y2.detach() - y.detach() * 2).abs().max()) <= 2.0 ** -23
+
+
+def test_bias_pool_paths():
+    """A non-zero bias pool (the reference allocates one but never fills it, Hash3DAnchored.cpp:57-62) against the
+    oracle, and NULL == an all-zero pool bit for bit."""
+    n, n_vol, log2T = 3000, 4, 11
+    feat, prim, bias, pts, anchors = hash_inputs(n, n_vol, log2T, seed=21)
+    rng = np.random.RandomState(1)
+    bias_nz = rng.uniform(0, 1, size=bias.shape).astype(np.float32)
+    for b in (bias_nz, bias):
+        core = make_core(feat, prim, b, log2T)
+        tp, ta = torch.from_numpy(pts).cuda(), torch.from_numpy(anchors).cuda()
+        out = torch.empty((n, 32), device="cuda")
+        core.launch_forward(tp, ta, out_f32=out)
+        ref = orc.hash_forward(feat, prim, b, pts, anchors, core.level_scales_host)
+        assert np.array_equal(out.cpu().numpy(), ref)
+        assert (core._bias() is None) == (not b.any())
+    # explicit zero pool pointer vs NULL through the C-ABI
+    from gfnerf_b200 import _lib
+    core = make_core(feat, prim, bias, log2T)
+    o1, o2 = torch.empty((n, 32), device="cuda"), torch.empty((n, 32), device="cuda")
+    for o, bp in ((o1, core.bias_pool_), (o2, None)):
+        _lib.check(_lib.lib().gf_hash_forward(n, None, n_vol, core.local_size_, _lib.ptr(core.shadow()),
+                                              _lib.ptr(core.prim_pool_), _lib.ptr(bp), _lib.ptr(core.level_scales_),
+                                              _lib.ptr(tp), _lib.ptr(ta), 1, None, _lib.ptr(o), _lib.cur_stream()))
+    assert torch.equal(o1, o2)
