@@ -14,8 +14,14 @@ template <bool SHADOW>
 __global__ void __launch_bounds__(256)
 adam_kernel(int64_t n4, float4* __restrict__ param, float4* __restrict__ grad, float4* __restrict__ m,
             float4* __restrict__ v, uint2* __restrict__ shadow, float step_size, float beta1, float beta2,
-            float inv_bc2_sqrt, float eps, float inv_div, int zero_grad) {
+            float inv_bc2_sqrt, float eps, float inv_div, int zero_grad, const int* __restrict__ skip_flag) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (skip_flag && *skip_flag) {  // a NaN gradient was found: no update (trainer.py:416-426), only the zero-fill
+    if (zero_grad)
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+        grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 p = param[i], g = grad[i], mm = m[i], vv = v[i];
     float* pp = &p.x; float* gp = &g.x; float* mp = &mm.x; float* vp = &vv.x;
@@ -41,9 +47,13 @@ adam_kernel(int64_t n4, float4* __restrict__ param, float4* __restrict__ grad, f
 
 __global__ void adam_tail_kernel(int64_t from, int64_t n, float* param, float* grad, float* m, float* v,
                                  __half* shadow, float step_size, float beta1, float beta2, float inv_bc2_sqrt,
-                                 float eps, float inv_div, int zero_grad) {
+                                 float eps, float inv_div, int zero_grad, const int* skip_flag) {
   const int64_t i = from + threadIdx.x;
   if (i >= n) return;
+  if (skip_flag && *skip_flag) {
+    if (zero_grad) grad[i] = 0.f;
+    return;
+  }
   const float gk = grad[i] * inv_div;
   const float mk = m[i] + (gk - m[i]) * (1.f - beta1);
   const float vk = v[i] * beta2 + (1.f - beta2) * gk * gk;
@@ -54,13 +64,54 @@ __global__ void adam_tail_kernel(int64_t from, int64_t n, float* param, float* g
   if (shadow) shadow[i] = __float2half_rn(pk);
 }
 
+// flag |= any(isnan(x)): the trainer's NaN-gradient scan (nerfstudio/engine/trainer.py:416-423) without its host sync
+__global__ void __launch_bounds__(256) nan_scan_kernel(int64_t n, const float* __restrict__ x, int* __restrict__ flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  const int64_t n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(x4 + i);
+    bad |= isnan(v.x) || isnan(v.y) || isnan(v.z) || isnan(v.w);
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= isnan(x[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 }  // namespace gf
 
 using namespace gf;
 
+extern "C" int gf_grad_nan_scan(int64_t n, const float* grad, int32_t* flag, void* stream) {
+  GF_REQUIRE(n >= 0 && flag, "gf_grad_nan_scan: bad arguments");
+  if (n == 0) return GF_OK;
+  GF_REQUIRE(grad != nullptr, "gf_grad_nan_scan: null pointer");
+  GF_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "gf_grad_nan_scan: grad must be 16-byte aligned");
+  nan_scan_kernel<<<stride_grid(n / 4 + 1, 256, 8, 2), 256, 0, (cudaStream_t)stream>>>(n, grad, flag);
+  return check_launch("nan_scan_kernel");
+}
+
+static int adam_impl(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_f16, float lr,
+                     float beta1, float beta2, float eps, int64_t step, float grad_div, int zero_grad,
+                     const int32_t* skip_flag, void* stream);
+
 extern "C" int gf_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                             void* shadow_f16, float lr, float beta1, float beta2, float eps, int64_t step,
                             float grad_div, int zero_grad, void* stream) {
+  return adam_impl(n, param, grad, exp_avg, exp_avg_sq, shadow_f16, lr, beta1, beta2, eps, step, grad_div, zero_grad,
+                   nullptr, stream);
+}
+
+extern "C" int gf_adam_step_guarded(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                                    void* shadow_f16, float lr, float beta1, float beta2, float eps, int64_t step,
+                                    float grad_div, int zero_grad, const int32_t* skip_flag, void* stream) {
+  return adam_impl(n, param, grad, exp_avg, exp_avg_sq, shadow_f16, lr, beta1, beta2, eps, step, grad_div, zero_grad,
+                   skip_flag, stream);
+}
+
+static int adam_impl(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_f16, float lr,
+                     float beta1, float beta2, float eps, int64_t step, float grad_div, int zero_grad,
+                     const int32_t* skip_flag, void* stream) {
   GF_REQUIRE(n >= 0 && step >= 1 && grad_div != 0.f, "gf_adam_step: bad arguments");
   if (n == 0) return GF_OK;
   GF_REQUIRE(param && grad && exp_avg && exp_avg_sq, "gf_adam_step: null pointer");
@@ -75,17 +126,17 @@ extern "C" int gf_adam_step(int64_t n, float* param, float* grad, float* exp_avg
     if (shadow_f16)
       adam_kernel<true><<<grid, 256, 0, st>>>(n4, (float4*)param, (float4*)grad, (float4*)exp_avg,
                                               (float4*)exp_avg_sq, (uint2*)shadow_f16, step_size, beta1, beta2,
-                                              inv_bc2_sqrt, eps, 1.f / grad_div, zero_grad);
+                                              inv_bc2_sqrt, eps, 1.f / grad_div, zero_grad, skip_flag);
     else
       adam_kernel<false><<<grid, 256, 0, st>>>(n4, (float4*)param, (float4*)grad, (float4*)exp_avg,
                                                (float4*)exp_avg_sq, nullptr, step_size, beta1, beta2, inv_bc2_sqrt,
-                                               eps, 1.f / grad_div, zero_grad);
+                                               eps, 1.f / grad_div, zero_grad, skip_flag);
     int rc = check_launch("adam_kernel");
     if (rc) return rc;
   }
   if (n4 * 4 < n) {
     adam_tail_kernel<<<1, 32, 0, st>>>(n4 * 4, n, param, grad, exp_avg, exp_avg_sq, (__half*)shadow_f16, step_size,
-                                       beta1, beta2, inv_bc2_sqrt, eps, 1.f / grad_div, zero_grad);
+                                       beta1, beta2, inv_bc2_sqrt, eps, 1.f / grad_div, zero_grad, skip_flag);
     return check_launch("adam_tail_kernel");
   }
   return GF_OK;

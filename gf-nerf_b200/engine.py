@@ -54,12 +54,14 @@ class _Adam:
         self.v = torch.zeros_like(param)
         self.t = 0
 
-    def step(self, shadow=None, grad_div=1.0, lr=None):
+    def step(self, shadow=None, grad_div=1.0, lr=None, skip_flag=None):
+        """skip_flag: device int32 set by gf_grad_nan_scan -- non-zero leaves the parameters untouched (the trainer's
+        NaN guard, trainer.py:416-426; the host-side step counter is not rewound)"""
         self.t += 1
-        _lib.check(_lib.lib().gf_adam_step(
+        _lib.check(_lib.lib().gf_adam_step_guarded(
             self.param.numel(), _lib.ptr(self.param), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
             _lib.ptr(shadow), float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.t,
-            float(grad_div), 1, _lib.cur_stream()), "gf_adam_step")
+            float(grad_div), 1, _lib.ptr(skip_flag), _lib.cur_stream()), "gf_adam_step_guarded")
 
 
 @dataclass
@@ -76,10 +78,12 @@ class GFNeRFEngine:
 
     def __init__(self, sampler: PersSamplerCore, log2_table_size: int = 19, num_images: int = 1, hidden: int = HIDDEN,
                  use_appearance_embedding: bool = True, lr_table: float = 1e-2, lr_mlp: float = 1e-2,
-                 seed: int = 0, dist_group=None):
+                 seed: int = 0, dist_group=None, nan_guard: bool = True):
         self.sampler = sampler
         self.device = sampler.device
         self.hidden = hidden
+        self.nan_guard = bool(nan_guard)    # skip the optimizer step on a NaN gradient (trainer.py:416-426)
+        self.last_nan_flag = None
         gen = torch.Generator().manual_seed(seed)
         # n_volumes: the reference sizes the prime pool by the number of tree nodes (gfnerf/nerfacto.py:267)
         # while indexing it with trans_idx (< number of transforms); any bound >= n_trans is equivalent.
@@ -296,7 +300,8 @@ class GFNeRFEngine:
                                              d_n_ptr=cs.total)
                 if optimizer_step:
                     with self._stage("adam_table"):
-                        self.opt_res.step(shadow=self.res._shadow, lr=self.opt_res.lr * lr_scale)
+                        self.opt_res.step(shadow=self.res._shadow, lr=self.opt_res.lr * lr_scale,
+                                          skip_flag=self._nan_flag([self.opt_res.grad]))
                     self.res.mark_shadow_fresh()
             else:
                 d_ray_emb = (self._buf("d_ray_emb", (R, APPEARANCE_DIM), torch.float32, zero=True)
@@ -391,12 +396,24 @@ class GFNeRFEngine:
             self._apply_adam(self._deferred)
             self._deferred = None
 
+    def _nan_flag(self, grads):
+        """device flag = any NaN in the (already all-reduced) gradients; None when the guard is off"""
+        if not self.nan_guard:
+            return None
+        flag = self._buf("nan_flag", (1,), torch.int32, zero=True)
+        L, st = _lib.lib(), _lib.cur_stream()
+        for g in grads:
+            _lib.check(L.gf_grad_nan_scan(g.numel(), _lib.ptr(g), _lib.ptr(flag), st), "gf_grad_nan_scan")
+        self.last_nan_flag = flag
+        return flag
+
     def _apply_adam(self, lr_scale: float):
         div = float(self.world)
         with self._stage("adam_small"):
-            self.opt_mlp.step(grad_div=div, lr=self.opt_mlp.lr * lr_scale)
+            flag = self._nan_flag([self._small_grads, self.opt_table.grad])
+            self.opt_mlp.step(grad_div=div, lr=self.opt_mlp.lr * lr_scale, skip_flag=flag)
             if self.opt_emb is not None:
-                self.opt_emb.step(grad_div=div, lr=self.opt_emb.lr * lr_scale)
+                self.opt_emb.step(grad_div=div, lr=self.opt_emb.lr * lr_scale, skip_flag=flag)
         with self._stage("adam_table"):
-            self.opt_table.step(shadow=self.enc._shadow, grad_div=div, lr=self.opt_table.lr * lr_scale)
+            self.opt_table.step(shadow=self.enc._shadow, grad_div=div, lr=self.opt_table.lr * lr_scale, skip_flag=flag)
         self.enc.mark_shadow_fresh()

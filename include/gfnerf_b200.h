@@ -273,6 +273,15 @@ int gf_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* ex
                  void* shadow_f16, float lr, float beta1, float beta2, float eps,
                  int64_t step, float grad_div, int zero_grad, void* stream);
 
+/* The trainer's NaN-gradient guard (nerfstudio/engine/trainer.py:416-426: scan every parameter's gradient, skip the
+ * optimizer step if any is NaN) without its per-parameter host syncs: gf_grad_nan_scan ORs 1 into *flag (device
+ * int32, caller zeroes) if grad holds a NaN; gf_adam_step_guarded is gf_adam_step that leaves param / moments
+ * untouched (and only zero-fills the gradient) when *skip_flag != 0. */
+int gf_grad_nan_scan(int64_t n, const float* grad, int32_t* flag, void* stream);
+int gf_adam_step_guarded(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                         void* shadow_f16, float lr, float beta1, float beta2, float eps,
+                         int64_t step, float grad_div, int zero_grad, const int32_t* skip_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

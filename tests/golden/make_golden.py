@@ -167,6 +167,52 @@ def loss_adam_case(CharbonnierLoss, R=200, n=4096, seed=7):
                 adam_grads=grads, adam_traj=np.stack(traj))
 
 
+def scheduler_case():
+    """GFNerfExponentialDecayScheduler.get_scheduler (nerfstudio/engine/schedulers.py:138-184) through torch's
+    LambdaLR, for the gf-nerf init stage and a block-stage configuration."""
+    # nerfstudio/configs/base_config.py does not import under Python 3.12 (a mutable dataclass default at :118); the
+    # scheduler only needs its InstantiateConfig base, so that one class is stood in and schedulers.py itself is the
+    # reference's file, unmodified
+    import dataclasses
+    import importlib.util
+    stub = types.ModuleType("nerfstudio.configs.base_config")
+
+    @dataclasses.dataclass
+    class InstantiateConfig:
+        _target: type
+
+        def setup(self, **kwargs):
+            return self._target(self, **kwargs)
+
+    stub.InstantiateConfig = InstantiateConfig
+    sys.modules["nerfstudio.configs.base_config"] = stub
+    spec = importlib.util.spec_from_file_location("gf_ref_schedulers",
+                                                  os.path.join(REF, "nerfstudio", "engine", "schedulers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["gf_ref_schedulers"] = mod
+    spec.loader.exec_module(mod)
+    GFNerfExponentialDecayScheduler = mod.GFNerfExponentialDecayScheduler
+    GFNerfExponentialDecaySchedulerConfig = mod.GFNerfExponentialDecaySchedulerConfig
+    out = {}
+    cfgs = {
+        "init": dict(lr_final=1e-4, max_steps=30000, warmup_steps=0, steps_perssampler_init=30000,
+                     steps_per_split_dataset=10000, n_split_dataset=10),
+        "block": dict(lr_final=5e-4, max_steps=10000, warmup_steps=100, ramp="linear", lr_pre_warmup=1e-6,
+                      steps_perssampler_init=300, steps_per_split_dataset=200, n_split_dataset=3),
+    }
+    steps = np.array([0, 1, 50, 99, 100, 299, 300, 301, 499, 500, 899, 900, 901, 1500, 5000, 29999, 30000, 45000])
+    for name, kw in cfgs.items():
+        cfg = GFNerfExponentialDecaySchedulerConfig(**kw)
+        w = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([w], lr=1e-2)
+        sched = GFNerfExponentialDecayScheduler(cfg).get_scheduler(opt, 1e-2)
+        mult = np.array([sched.lr_lambdas[0](int(s)) for s in steps], np.float64)
+        out[name + "_mult"] = mult
+        out[name + "_cfg"] = np.array(repr(kw))
+    out["steps"] = steps
+    return out
+
+
 def main():
     MLPNetwork, Frustums, RaySamples, trunc_exp, renderers, CharbonnierLoss = _import_reference()
     torch.set_num_threads(1)
@@ -174,6 +220,7 @@ def main():
         "ref_composite": composite_case(Frustums, RaySamples, renderers),
         "ref_mlp": mlp_case(MLPNetwork, trunc_exp),
         "ref_loss_adam": loss_adam_case(CharbonnierLoss),
+        "ref_scheduler": scheduler_case(),
     }
     for name, d in out.items():
         path = os.path.join(HERE, name + ".npz")

@@ -188,3 +188,29 @@ def test_train_step_host_equals_device_path():
     print("rows that agree:", float(close.float().mean()))
     assert float(close.float().mean()) > 0.98
     assert b.read_losses() == []
+
+
+def test_nan_gradient_skips_the_optimizer_step():
+    """The trainer's NaN guard (nerfstudio/engine/trainer.py:416-426) on the device: a NaN anywhere in the gradients
+    leaves every parameter and Adam moment untouched, the gradients are still zeroed, and training continues."""
+    from gfnerf_b200.persoctree import rig_rays
+    rig = load_rig("rig8")
+    eng = make_engine(rig)
+    o, d, cam = rig_rays(rig["c2w"], rig["intri"], 256, seed=1)
+    T = lambda a: torch.from_numpy(a).cuda()
+    good = torch.rand(256, 3).cuda()
+    eng.train_step(T(o), T(d), good, T(cam))
+    assert int(eng.last_nan_flag.item()) == 0
+    table, mlp, emb = eng.enc.feat_pool_.detach().clone(), eng.mlp.clone(), eng.emb.clone()
+    m_table = eng.opt_table.m.clone()
+    bad = good.clone()
+    bad[7, 1] = float("nan")                      # -> NaN loss gradient -> NaN in every gradient buffer
+    eng.train_step(T(o), T(d), bad, T(cam))
+    assert int(eng.last_nan_flag.item()) == 1
+    assert torch.equal(eng.enc.feat_pool_.detach(), table) and torch.equal(eng.mlp, mlp) and torch.equal(eng.emb, emb)
+    assert torch.equal(eng.opt_table.m, m_table)
+    assert not eng.opt_table.grad.any() and not eng.opt_mlp.grad.any() and not torch.isnan(eng.opt_emb.grad).any()
+    eng.train_step(T(o), T(d), good, T(cam))
+    assert int(eng.last_nan_flag.item()) == 0
+    assert not torch.equal(eng.enc.feat_pool_.detach(), table)
+    assert torch.isfinite(eng.enc.feat_pool_).all() and torch.isfinite(eng.mlp).all()
