@@ -43,6 +43,7 @@ _SIGS = {
     "gf_mlp_forward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_mlp_backward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp],
     "gf_mlp_ray_bias_backward": [_i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gf_s3im": [_i64, _i64, _vp, _vp, _vp, _int, _int, _int, _f32, _vp, _vp, _vp],
     "gf_charbonnier": [_i64, _vp, _vp, _f32, _vp, _vp, _vp],
     "gf_grad_nan_scan": [_i64, _vp, _vp, _vp],
     "gf_adam_step_guarded": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _int, _vp, _vp],

@@ -174,6 +174,61 @@ __global__ void charbonnier_kernel(int64_t n3, float inv_rays, const float* __re
   if ((threadIdx.x & 31) == 0 && d_loss) atomicAdd(d_loss, acc * inv_rays);
 }
 
+// S3IM (nerfstudio/model_components/losses.py:713-794): SSIM between two virtual images built from the ray batch
+// laid out `repeat` times (index = arange ++ randperm x (repeat-1)), Gaussian window ksize x ksize (sigma 1.5), stride,
+// zero padding (ksize-1)/2.  One thread per window (channel, oy, ox): gathers its ksize^2 (src, tar) pairs through the
+// index list, adds  -mult/n_map * d ssim/d src  to g_src and  mult * (1 - ssim)/n_map  to the loss.
+struct S3imWindow {
+  float w[64];
+};
+
+__global__ void __launch_bounds__(128)
+s3im_kernel(int64_t n_map, int64_t W, int64_t oh, int64_t ow, int patch_h, int ksize, int stride, int pad,
+            const long long* __restrict__ index, const float* __restrict__ src, const float* __restrict__ tar,
+            S3imWindow win, float mult, float* __restrict__ g_src, float* __restrict__ d_loss) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float part = 0.f;
+  if (i < n_map) {
+    const int64_t ox = i % ow, oy = (i / ow) % oh;
+    const int c = (int)(i / (ow * oh));
+    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    for (int ky = 0; ky < ksize; ky++)
+      for (int kx = 0; kx < ksize; kx++) {
+        const int64_t h = oy * stride - pad + ky, w = ox * stride - pad + kx;
+        if (h < 0 || h >= patch_h || w < 0 || w >= W) continue;
+        const long long r = __ldg(index + h * W + w);
+        const float x = __ldg(src + 3 * r + c), y = __ldg(tar + 3 * r + c), wt = win.w[ky * ksize + kx];
+        mu1 = fmaf(wt, x, mu1);
+        mu2 = fmaf(wt, y, mu2);
+        e11 = fmaf(wt * x, x, e11);
+        e22 = fmaf(wt * y, y, e22);
+        e12 = fmaf(wt * x, y, e12);
+      }
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    const float s11 = e11 - mu1 * mu1, s22 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
+    const float A1 = 2.f * mu1 * mu2 + C1, A2 = 2.f * s12 + C2, B1 = mu1 * mu1 + mu2 * mu2 + C1, B2 = s11 + s22 + C2;
+    const float inv = 1.f / (B1 * B2);
+    const float ssim = A1 * A2 * inv;
+    const float inv_n = 1.f / (float)n_map;
+    part = mult * (1.f - ssim) * inv_n;
+    if (g_src) {
+      const float k = -mult * inv_n;
+      for (int ky = 0; ky < ksize; ky++)
+        for (int kx = 0; kx < ksize; kx++) {
+          const int64_t h = oy * stride - pad + ky, w = ox * stride - pad + kx;
+          if (h < 0 || h >= patch_h || w < 0 || w >= W) continue;
+          const long long r = __ldg(index + h * W + w);
+          const float x = __ldg(src + 3 * r + c), y = __ldg(tar + 3 * r + c), wt = win.w[ky * ksize + kx];
+          const float dA1 = 2.f * mu2 * wt, dA2 = 2.f * wt * (y - mu2), dB1 = 2.f * mu1 * wt, dB2 = 2.f * wt * (x - mu1);
+          const float d = (dA1 * A2 + A1 * dA2) * inv - ssim * (dB1 * B2 + B1 * dB2) * inv;
+          atomicAdd(g_src + 3 * r + c, k * d);
+        }
+    }
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0 && d_loss && part != 0.f) atomicAdd(d_loss, part);
+}
+
 }  // namespace gf
 
 using namespace gf;
@@ -217,6 +272,33 @@ int gf_charbonnier(int64_t n_rays, const float* rgb, const float* target, float 
   charbonnier_kernel<<<stride_grid(n3, 256, 4), 256, 0, (cudaStream_t)stream>>>(n3, 1.f / (float)n_rays, rgb, target,
                                                                                 eps * eps, g_rgb, d_loss);
   return check_launch("charbonnier_kernel");
+}
+
+int gf_s3im(int64_t n_rays, int64_t n_virtual, const int64_t* index, const float* src, const float* target,
+            int patch_h, int ksize, int stride, float mult, float* g_src, float* d_loss, void* stream) {
+  GF_REQUIRE(n_rays >= 0 && n_virtual >= 0 && patch_h > 0 && stride > 0 && ksize >= 1 && ksize <= 8,
+             "gf_s3im: bad sizes");
+  GF_REQUIRE(n_virtual % patch_h == 0, "gf_s3im: n_virtual must be a multiple of the patch height");
+  if (n_rays == 0 || n_virtual == 0) return GF_OK;
+  GF_REQUIRE(index && src && target, "gf_s3im: null pointer");
+  const int64_t W = n_virtual / patch_h;
+  const int pad = (ksize - 1) / 2;
+  const int64_t oh = (patch_h + 2 * pad - ksize) / stride + 1, ow = (W + 2 * pad - ksize) / stride + 1;
+  GF_REQUIRE(oh > 0 && ow > 0, "gf_s3im: the window does not fit the virtual image");
+  // the reference's window: fp32 Gaussian, sigma 1.5, normalised, outer product (losses.py:726-734)
+  S3imWindow win;
+  float g1[8], gs = 0.f;
+  for (int x = 0; x < ksize; x++) {
+    g1[x] = (float)exp(-(double)((x - ksize / 2) * (x - ksize / 2)) / (2.0 * 1.5 * 1.5));
+    gs += g1[x];
+  }
+  for (int x = 0; x < ksize; x++) g1[x] /= gs;
+  for (int y = 0; y < ksize; y++)
+    for (int x = 0; x < ksize; x++) win.w[y * ksize + x] = g1[y] * g1[x];
+  const int64_t n_map = 3 * oh * ow;
+  s3im_kernel<<<(int)div_up(n_map, 128), 128, 0, (cudaStream_t)stream>>>(
+      n_map, W, oh, ow, patch_h, ksize, stride, pad, (const long long*)index, src, target, win, mult, g_src, d_loss);
+  return check_launch("s3im_kernel");
 }
 
 }  // extern "C"

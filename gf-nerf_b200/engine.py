@@ -78,11 +78,16 @@ class GFNeRFEngine:
 
     def __init__(self, sampler: PersSamplerCore, log2_table_size: int = 19, num_images: int = 1, hidden: int = HIDDEN,
                  use_appearance_embedding: bool = True, lr_table: float = 1e-2, lr_mlp: float = 1e-2,
-                 seed: int = 0, dist_group=None, nan_guard: bool = True):
+                 seed: int = 0, dist_group=None, nan_guard: bool = True, s3im_loss_mult: float = 0.0,
+                 s3im_kernel_size: int = 4, s3im_stride: int = 4, s3im_repeat_time: int = 10,
+                 s3im_patch_height: int = 32):
         self.sampler = sampler
         self.device = sampler.device
         self.hidden = hidden
         self.nan_guard = bool(nan_guard)    # skip the optimizer step on a NaN gradient (trainer.py:416-426)
+        # S3IM on top of the Charbonnier loss (gfnerf/nerfacto.py:186-197, 686-688); 0 = off
+        self.s3im = (float(s3im_loss_mult), int(s3im_kernel_size), int(s3im_stride), int(s3im_repeat_time),
+                     int(s3im_patch_height))
         self.last_nan_flag = None
         gen = torch.Generator().manual_seed(seed)
         # n_volumes: the reference sizes the prime pool by the number of tree nodes (gfnerf/nerfacto.py:267)
@@ -271,6 +276,14 @@ class GFNeRFEngine:
             with self._stage("loss"):
                 _lib.check(L.gf_charbonnier(R, _lib.ptr(out_rgb), _lib.ptr(target), 1e-6,
                                             _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_charbonnier")
+            mult, ks, stride, repeat, patch_h = self.s3im
+            if mult > 0.0 and (R * repeat) % patch_h == 0:
+                # S3IM.forward (losses.py:779-794): the batch once in order, then repeat-1 random permutations
+                perms = torch.rand((repeat - 1, R), device=self.device).argsort(dim=1)
+                index = torch.cat([torch.arange(R, device=self.device).view(1, R), perms]).reshape(-1).contiguous()
+                with self._stage("loss"):
+                    _lib.check(L.gf_s3im(R, index.numel(), _lib.ptr(index), _lib.ptr(out_rgb), _lib.ptr(target),
+                                         patch_h, ks, stride, mult, _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_s3im")
             # training feedback (gfnerf/nerfacto.py:598-616).  It only needs the forward's weights, so it is issued
             # here: its (tiny) MAX all-reduce over ranks must not queue behind the gradient all-reduce below
             if update_octree and self.stage == "init_stage":   # the octree is only updated in the init stage (:605)

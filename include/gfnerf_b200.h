@@ -264,6 +264,14 @@ int gf_mlp_ray_bias_backward(int64_t n_rays, int hidden, const float* params, co
 int gf_charbonnier(int64_t n_rays, const float* rgb, const float* target, float eps,
                    float* g_rgb, float* d_loss, void* stream);
 
+/* S3IM (nerfstudio/model_components/losses.py:713-794; gf-nerf: ksize 4, stride 4, repeat 10, patch_h 32,
+ * gfnerf/nerfacto.py:186-197): 1 - SSIM between the rendered and target colours laid out as a virtual image
+ * [3, patch_h, n_virtual / patch_h] through index (int64 [n_virtual] = arange(R) followed by repeat-1 random
+ * permutations of the rays).  ACCUMULATES mult * loss into d_loss[0] and mult * dloss/dsrc into g_src [R,3]
+ * (either may be NULL), so it composes with gf_charbonnier on the same buffers. */
+int gf_s3im(int64_t n_rays, int64_t n_virtual, const int64_t* index, const float* src, const float* target,
+            int patch_h, int ksize, int stride, float mult, float* g_src, float* d_loss, void* stream);
+
 /* torch.optim.Adam (no amsgrad, no weight decay) as configured at
  * gfnerf/config.py:132-135 / Hash3DAnchored.cpp:146-150.  step >= 1.
  * If shadow_f16 != NULL it is refreshed with the updated parameters.

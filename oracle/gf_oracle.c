@@ -895,6 +895,63 @@ double orc_charbonnier(int64_t n_rays, const float* rgb, const float* target, fl
   return loss / (double)n_rays;
 }
 
+/*
+ * S3IM (nerfstudio/model_components/losses.py:713-794): the R rays are laid out `repeat` times (once in order, then
+ * randomly permuted: index[n_virtual] is that concatenation) as a virtual image [3, patch_h, n_virtual / patch_h];
+ * SSIM with a ksize x ksize Gaussian window (sigma 1.5, :726-734), stride `stride`, zero padding (ksize-1)/2
+ * (:737-753); loss = 1 - mean(ssim_map).  g_src (optional, [R,3], ACCUMULATED) = mult * dloss/dsrc.
+ * Returns mult * loss.  fp64 accumulation.
+ */
+double orc_s3im(int64_t n_rays, int64_t n_virtual, const int64_t* index, const float* src, const float* tar,
+                int patch_h, int ksize, int stride, double mult, float* g_src) {
+  const int64_t W = n_virtual / patch_h;
+  const int pad = (ksize - 1) / 2;
+  const int64_t oh = (patch_h + 2 * pad - ksize) / stride + 1, ow = (W + 2 * pad - ksize) / stride + 1;
+  double g1[16], win[16][16];
+  double gs = 0;
+  for (int x = 0; x < ksize; x++) {
+    /* the reference builds the window in fp32 (torch.Tensor, :727-734) */
+    g1[x] = (double)(float)exp(-(double)((x - ksize / 2) * (x - ksize / 2)) / (2.0 * 1.5 * 1.5));
+    gs += g1[x];
+  }
+  float g1f[16];
+  for (int x = 0; x < ksize; x++) g1f[x] = (float)(g1[x]) / (float)gs;
+  for (int y = 0; y < ksize; y++)
+    for (int x = 0; x < ksize; x++) win[y][x] = (double)(float)(g1f[y] * g1f[x]);
+  const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
+  const double n_map = (double)(3 * oh * ow);
+  double total = 0;
+  for (int c = 0; c < 3; c++)
+    for (int64_t oy = 0; oy < oh; oy++)
+      for (int64_t ox = 0; ox < ow; ox++) {
+        double mu1 = 0, mu2 = 0, e11 = 0, e22 = 0, e12 = 0;
+        for (int ky = 0; ky < ksize; ky++)
+          for (int kx = 0; kx < ksize; kx++) {
+            int64_t h = oy * stride - pad + ky, w = ox * stride - pad + kx;
+            if (h < 0 || h >= patch_h || w < 0 || w >= W) continue;
+            int64_t r = index[h * W + w];
+            double x = src[3 * r + c], y = tar[3 * r + c], wt = win[ky][kx];
+            mu1 += wt * x; mu2 += wt * y; e11 += wt * x * x; e22 += wt * y * y; e12 += wt * x * y;
+          }
+        double s11 = e11 - mu1 * mu1, s22 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
+        double A1 = 2 * mu1 * mu2 + C1, A2 = 2 * s12 + C2, B1 = mu1 * mu1 + mu2 * mu2 + C1, B2 = s11 + s22 + C2;
+        total += A1 * A2 / (B1 * B2);
+        if (g_src)
+          for (int ky = 0; ky < ksize; ky++)
+            for (int kx = 0; kx < ksize; kx++) {
+              int64_t h = oy * stride - pad + ky, w = ox * stride - pad + kx;
+              if (h < 0 || h >= patch_h || w < 0 || w >= W) continue;
+              int64_t r = index[h * W + w];
+              double x = src[3 * r + c], y = tar[3 * r + c], wt = win[ky][kx];
+              double dA1 = 2 * mu2 * wt, dA2 = 2 * (wt * y - mu2 * wt), dB1 = 2 * mu1 * wt,
+                     dB2 = 2 * wt * x - 2 * mu1 * wt;
+              double d = (dA1 * A2 + A1 * dA2) / (B1 * B2) - A1 * A2 * (dB1 * B2 + B1 * dB2) / (B1 * B2 * B1 * B2);
+              g_src[3 * r + c] += (float)(-mult * d / n_map);
+            }
+      }
+  return mult * (1.0 - total / n_map);
+}
+
 /* torch.optim.Adam single-tensor step (no amsgrad / weight decay / maximize):
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
  * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)       (torch/optim/adam.py) */

@@ -210,6 +210,17 @@ def charbonnier(rgb, target, eps=1e-6):
     return float(loss), g
 
 
+def s3im(src, tar, index, patch_h=32, ksize=4, stride=4, mult=1.0, want_grad=True):
+    """-> (mult * loss, mult * dloss/dsrc [R,3])"""
+    src, tar = _f32(src), _f32(tar)
+    index = np.ascontiguousarray(index, np.int64)
+    g = np.zeros_like(src) if want_grad else None
+    lib().orc_s3im.restype = C.c_double
+    loss = lib().orc_s3im(C.c_int64(src.shape[0]), C.c_int64(index.size), _p(index), _p(src), _p(tar),
+                          C.c_int(patch_h), C.c_int(ksize), C.c_int(stride), C.c_double(mult), _p(g))
+    return float(loss), g
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
     """In place on param / exp_avg / exp_avg_sq (float32, contiguous)."""
     lib().orc_adam_step(C.c_int64(param.size), _p(param), _p(_f32(grad)), _p(exp_avg), _p(exp_avg_sq),

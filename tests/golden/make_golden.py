@@ -167,6 +167,24 @@ def loss_adam_case(CharbonnierLoss, R=200, n=4096, seed=7):
                 adam_grads=grads, adam_traj=np.stack(traj))
 
 
+def s3im_case(R=512, seed=9):
+    """S3IM (nerfstudio/model_components/losses.py:713-794) as gf-nerf configures it (kernel 4, stride 4, repeat 10,
+    patch height 32, gfnerf/nerfacto.py:186-197).  Its random re-patching draws torch.randperm from the global CPU
+    generator; the same seed replayed gives the index list stored in the fixture."""
+    from nerfstudio.model_components.losses import S3IM
+    rng = np.random.RandomState(seed)
+    src = rng.uniform(0, 1, size=(R, 3)).astype(np.float32)
+    tar = np.clip(src + rng.normal(0, 0.1, size=(R, 3)), 0, 1).astype(np.float32)
+    loss_fn = S3IM(s3im_kernel_size=4, s3im_stride=4, s3im_repeat_time=10, s3im_patch_height=32)
+    x = torch.tensor(src, requires_grad=True)
+    torch.manual_seed(1234)
+    loss = loss_fn(x, torch.tensor(tar))
+    loss.backward()
+    torch.manual_seed(1234)
+    index = torch.cat([torch.arange(R)] + [torch.randperm(R) for _ in range(9)]).numpy().astype(np.int64)
+    return dict(src=src, tar=tar, index=index, loss=np.float64(loss.item()), g_src=x.grad.numpy())
+
+
 def scheduler_case():
     """GFNerfExponentialDecayScheduler.get_scheduler (nerfstudio/engine/schedulers.py:138-184) through torch's
     LambdaLR, for the gf-nerf init stage and a block-stage configuration."""
@@ -221,6 +239,7 @@ def main():
         "ref_mlp": mlp_case(MLPNetwork, trunc_exp),
         "ref_loss_adam": loss_adam_case(CharbonnierLoss),
         "ref_scheduler": scheduler_case(),
+        "ref_s3im": s3im_case(),
     }
     for name, d in out.items():
         path = os.path.join(HERE, name + ".npz")

@@ -214,3 +214,28 @@ def test_nan_gradient_skips_the_optimizer_step():
     assert int(eng.last_nan_flag.item()) == 0
     assert not torch.equal(eng.enc.feat_pool_.detach(), table)
     assert torch.isfinite(eng.enc.feat_pool_).all() and torch.isfinite(eng.mlp).all()
+
+
+def test_s3im_term_in_the_fused_step():
+    """Charbonnier + s3im_loss_mult * S3IM (gfnerf/nerfacto.py:686-688) in the fused step: the loss is the sum of the
+    two terms (S3IM evaluated by the oracle on the same index-free quantity: its first repeat is the identity layout,
+    so with repeat_time = 1 the index list is deterministic)."""
+    from gfnerf_b200.engine import GFNeRFEngine
+    from gfnerf_b200.persoctree import rig_rays
+    rig = load_rig("rig8")
+    mk = lambda mult: GFNeRFEngine(make_sampler(rig, mode=1), log2_table_size=14, num_images=rig["c2w"].shape[0], seed=0,
+                                   s3im_loss_mult=mult, s3im_repeat_time=1)
+    a, b = mk(0.0), mk(2.0)
+    b.enc.feat_pool_.data.copy_(a.enc.feat_pool_.data)
+    b.enc.shadow(force=True)
+    R = 512
+    o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=3)
+    tgt = np.random.RandomState(0).rand(R, 3).astype(np.float32)
+    args = [torch.from_numpy(x).cuda() for x in (o, d, tgt, cam)]
+    oa = a.train_step(*args, optimizer_step=False, update_octree=False)
+    ob = b.train_step(*args, optimizer_step=False, update_octree=False)
+    assert torch.equal(oa.rgb, ob.rgb)
+    s3, _ = orc.s3im(oa.rgb.cpu().numpy(), tgt, np.arange(R), patch_h=32, ksize=4, stride=4, mult=2.0)
+    assert abs(float(ob.loss) - (float(oa.loss) + s3)) < 1e-5 * float(ob.loss)
+    assert not torch.equal(a.opt_mlp.grad, b.opt_mlp.grad)          # the extra term reaches the parameters
+    assert torch.isfinite(b.opt_table.grad).all()

@@ -108,3 +108,25 @@ def test_charbonnier_and_adam_match_reference():
         close(w, g["adam_traj"][k], 2e-6, f"adam step {k + 1}")
         assert float(grad.abs().max()) == 0.0                       # zero_grad
         assert torch.equal(shadow, w.half())                        # fp16 shadow refreshed
+
+
+def test_s3im_matches_reference():
+    from gfnerf_b200 import _lib
+    L, st = _lib.lib(), _lib.cur_stream()
+    g = load("ref_s3im")
+    R = g["src"].shape[0]
+    src, tar, idx = T(g["src"]), T(g["tar"]), T(g["index"])
+    g_src, loss = torch.zeros((R, 3), device="cuda"), torch.zeros(1, device="cuda")
+    _lib.check(L.gf_s3im(R, idx.numel(), _lib.ptr(idx), _lib.ptr(src), _lib.ptr(tar), 32, 4, 4, 1.0, _lib.ptr(g_src),
+                         _lib.ptr(loss), st))
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    close(g_src, g["g_src"], 1e-4, "dL/dsrc")        # fp32 variance terms cancel: 1e-4 of the largest gradient
+    # accumulates on top of the Charbonnier gradient / loss, with the multiplier applied
+    pred, target = T(g["src"]), T(g["tar"])
+    g2, l2 = torch.empty((R, 3), device="cuda"), torch.zeros(1, device="cuda")
+    _lib.check(L.gf_charbonnier(R, _lib.ptr(pred), _lib.ptr(target), 1e-6, _lib.ptr(g2), _lib.ptr(l2), st))
+    base_g, base_l = g2.clone(), float(l2)
+    _lib.check(L.gf_s3im(R, idx.numel(), _lib.ptr(idx), _lib.ptr(pred), _lib.ptr(target), 32, 4, 4, 0.5, _lib.ptr(g2),
+                         _lib.ptr(l2), st))
+    assert abs(float(l2) - (base_l + 0.5 * float(g["loss"]))) < 1e-5
+    close(g2 - base_g, 0.5 * g["g_src"], 1e-4, "scaled dL/dsrc")

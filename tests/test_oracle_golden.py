@@ -86,3 +86,14 @@ def test_charbonnier_and_adam_match_reference():
     for k, gr in enumerate(g["adam_grads"]):
         orc.adam_step(w, gr, m1, m2, 1e-2, 0.9, 0.999, 1e-15, k + 1)
         close(w, g["adam_traj"][k], rtol=2e-6, what=f"adam step {k + 1}")
+
+
+def test_s3im_matches_reference():
+    g = load("ref_s3im")
+    loss, grad = orc.s3im(g["src"], g["tar"], g["index"], patch_h=32, ksize=4, stride=4, mult=1.0)
+    assert abs(loss - float(g["loss"])) <= 1e-6 * float(g["loss"])
+    close(grad, g["g_src"], what="dL/dsrc")
+    # the multiplier scales loss and gradient; no gradient requested -> same loss
+    l2, g2 = orc.s3im(g["src"], g["tar"], g["index"], mult=0.25)
+    assert abs(l2 - 0.25 * loss) < 1e-12 and np.allclose(g2, 0.25 * grad, rtol=1e-6, atol=1e-12)
+    assert orc.s3im(g["src"], g["tar"], g["index"], want_grad=False)[0] == loss
