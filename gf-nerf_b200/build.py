@@ -52,5 +52,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TORCH_LIB = os.path.join(HERE, "f2nerf_bindings_b200.so")
+
+
+def build_torch_bindings(force: bool = False) -> str:
+    """The TorchScript custom classes (torch.classes.my_classes.*) over the C-ABI: csrc/torch_bindings.cpp compiled with
+    g++ against libtorch, linked to libgfnerf_b200.so through an $ORIGIN rpath.  Loaded with
+    torch.classes.load_library(TORCH_LIB), exactly how the reference loads its f2nerf-bindings.so."""
+    import torch
+    from torch.utils import cpp_extension
+    src = os.path.join(CSRC, "torch_bindings.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "gfnerf_b200.h"), LIB]
+    if not (force or _stale(TORCH_LIB, deps)):
+        return TORCH_LIB
+    inc = []
+    for p in cpp_extension.include_paths(device_type="cuda") if "device_type" in cpp_extension.include_paths.__code__.co_varnames \
+            else cpp_extension.include_paths(cuda=True):
+        inc += ["-I", p]
+    lib_dir = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cxx11 = int(torch.compiled_with_cxx11_abi())
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={cxx11}", "-I", "/usr/local/cuda/include"] + inc + [
+        src, "-o", TORCH_LIB, "-L", HERE, "-lgfnerf_b200", "-L", lib_dir, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10",
+        "-lc10_cuda", f"-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{lib_dir}"]
+    subprocess.check_call(cmd)
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--torch" in sys.argv:
+        print(build_torch_bindings(force="--force" in sys.argv))

@@ -1,0 +1,348 @@
+// TorchScript custom classes `torch.classes.my_classes.{Hash3DAnchored, PersSampler}` over the C-ABI.
+//
+// This is the reference's own operator boundary (gfnerf/bindings/hashanchored/bindings.cpp:343-401): the reference's
+// Python does `torch.classes.load_library(".../f2nerf-bindings.so")` and then instantiates these two classes
+// (gfnerf/hash_3d_anchored.py:13-25, gfnerf/perssampler.py:30-31,103-123).  Loading THIS library instead gives the
+// same class names and method signatures, with every method body reduced to pointer extraction + one gf_* call on
+// torch's current stream.  No torch type crosses into libgfnerf_b200.so.
+//
+//  * Hash3DAnchored: the complete surface (ctor, AnchoredQuery with autograd, GetParams, States, LoadStates, Reset,
+//    Zero, SetFeatPoolRequireGrad, to, ReleaseResources), state tensors and their order as in
+//    field/Hash3DAnchored.cpp:17-200.
+//  * PersSampler: the per-step surface (GetSamples, UpdateOctNodes' vote, UpdateRayMarch, UpdateMode, States,
+//    LoadStates, trans_query_frame, the getters).  The octree is built / compacted / subdivided on the host in
+//    gfnerf_b200.persoctree (numpy, as the reference does it on the host in PersSampler.cpp:92-895); it enters here
+//    through LoadStates (the reference's own checkpoint blobs), so InitSampler / ProcOctree are not duplicated in C++.
+#include <torch/custom_class.h>
+#include <torch/script.h>
+#include <torch/cuda.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <cmath>
+#include <random>
+
+#include "../../include/gfnerf_b200.h"
+
+#define GF_CHECK(call) TORCH_CHECK((call) == GF_OK, "gfnerf_b200: ", gf_last_error())
+
+namespace {
+
+using torch::Tensor;
+
+bool is_prime(uint32_t x) {
+  if (x < 4) return x > 1;
+  if (x % 2 == 0) return false;
+  for (uint32_t i = 3; (uint64_t)i * i <= x; i += 2)
+    if (x % i == 0) return false;
+  return true;
+}
+
+struct Hash3DAnchoredImpl : torch::CustomClassHolder {
+  Tensor feat_pool_, prim_pool_, bias_pool_, shadow_, scales_;
+  int64_t pool_size_, local_size_, n_volumes_;
+
+  Hash3DAnchoredImpl(int64_t log2_table_size, int64_t n_volumes, double /*learn_rate*/) {
+    TORCH_CHECK(torch::cuda::is_available(), "Hash3DAnchored needs a CUDA device: the B200 kernels have no CPU fallback");
+    auto f32 = torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA);
+    pool_size_ = (int64_t(1) << log2_table_size) * GF_N_LEVELS;
+    n_volumes_ = n_volumes;
+    // Hash3DAnchored.cpp:26  (rand * .2 - 1) * 1e-4
+    feat_pool_ = (torch::rand({pool_size_, GF_N_CHANNELS}, f32) * .2f - 1.f) * 1e-4f;
+    feat_pool_.requires_grad_(true);
+    // :32-55  3 * 16 * n_volumes random primes in [2^28, 2^30)
+    std::mt19937 rng(1234);
+    std::uniform_int_distribution<uint32_t> dist(1u << 28, (1u << 30) - 1);
+    auto prim = torch::empty({GF_N_LEVELS, n_volumes, 3}, torch::kInt32);
+    int32_t* p = prim.data_ptr<int32_t>();
+    for (int64_t i = 0; i < prim.numel(); i++) {
+      uint32_t x = dist(rng) | 1u;
+      while (!is_prime(x) || x >= (1u << 30)) x = x + 2 >= (1u << 30) ? (dist(rng) | 1u) : x + 2;
+      p[i] = (int32_t)x;
+    }
+    prim_pool_ = prim.to(torch::kCUDA);
+    bias_pool_ = torch::zeros({GF_N_LEVELS * n_volumes, 3}, f32);  // rand_bias is never set (:57-62)
+    local_size_ = ((pool_size_ / GF_N_LEVELS) >> 4) << 4;           // :66-70
+    scales_ = torch::empty({GF_N_LEVELS}, f32);
+    GF_CHECK(gf_hash_level_scales(scales_.data_ptr<float>(), nullptr, stream()));
+    shadow_ = torch::empty({pool_size_, GF_N_CHANNELS}, f32.dtype(torch::kFloat16));
+  }
+
+  static void* stream() { return (void*)c10::cuda::getCurrentCUDAStream().stream(); }
+
+  void cast_table() {  // Hash3DAnchored_cuda.cu:185: the table is cast to fp16 on every forward
+    GF_CHECK(gf_hash_cast_table(feat_pool_.data_ptr<float>(), shadow_.data_ptr(), feat_pool_.numel(), stream()));
+  }
+
+  Tensor forward_raw(const Tensor& points, const Tensor& anchors) {
+    TORCH_CHECK(points.is_cuda() && anchors.is_cuda(), "gfnerf_b200: tensor is not on a CUDA device (there is no CPU path)");
+    TORCH_CHECK(points.dim() == 2 && points.size(1) == 3 && points.scalar_type() == torch::kFloat32, "points: f32 [n,3]");
+    TORCH_CHECK(anchors.dim() == 1 && anchors.scalar_type() == torch::kInt64, "anchors: i64 [n]");
+    c10::cuda::CUDAGuard guard(points.device());
+    auto pts = points.contiguous();
+    auto anc = anchors.contiguous();
+    cast_table();
+    auto out = torch::empty({pts.size(0), GF_HASH_DIM}, pts.options());
+    GF_CHECK(gf_hash_forward(pts.size(0), nullptr, (int32_t)n_volumes_, local_size_, shadow_.data_ptr(),
+                             prim_pool_.data_ptr<int32_t>(), bias_pool_.data_ptr<float>(), scales_.data_ptr<float>(),
+                             pts.data_ptr<float>(), anc.data_ptr<int64_t>(), 1, nullptr, out.data_ptr<float>(),
+                             stream()));
+    return out;
+  }
+
+  Tensor backward_raw(const Tensor& points, const Tensor& anchors, const Tensor& grad_out) {
+    c10::cuda::CUDAGuard guard(points.device());
+    auto g = grad_out.contiguous().to(torch::kFloat32);
+    auto grad_table = torch::zeros_like(feat_pool_);
+    GF_CHECK(gf_hash_backward(points.size(0), nullptr, (int32_t)n_volumes_, local_size_, prim_pool_.data_ptr<int32_t>(),
+                              bias_pool_.data_ptr<float>(), scales_.data_ptr<float>(), points.data_ptr<float>(),
+                              anchors.data_ptr<int64_t>(), 1, g.data_ptr<float>(), 0, grad_table.data_ptr<float>(),
+                              stream()));
+    return grad_table;
+  }
+
+  Tensor AnchoredQuery(const Tensor& points, const Tensor& anchors);
+
+  std::vector<Tensor> GetParams() { return {feat_pool_}; }
+  std::vector<Tensor> States() {
+    return {feat_pool_.detach(), prim_pool_, bias_pool_, torch::full({1}, n_volumes_, torch::kInt32)};
+  }
+  int64_t LoadStates(const std::vector<Tensor>& states, int64_t idx) {
+    {
+      torch::NoGradGuard ng;
+      feat_pool_.copy_(states[idx++]);
+    }
+    prim_pool_ = states[idx++].clone().to(torch::kCUDA).contiguous();
+    bias_pool_ = states[idx++].clone().to(torch::kCUDA).contiguous();
+    n_volumes_ = states[idx++].item<int64_t>();
+    return idx;
+  }
+  void Reset() {
+    torch::NoGradGuard ng;
+    feat_pool_.uniform_(-1e-2, 1e-2);  // :171-174
+  }
+  void Zero() {
+    torch::NoGradGuard ng;
+    feat_pool_.zero_();
+  }
+  void SetFeatPoolRequireGrad(bool require_grad) { feat_pool_.requires_grad_(require_grad); }
+  void to(std::string device) {  // :180-200: "cpu" parks the table on the host, anything else is cuda
+    const bool rg = feat_pool_.requires_grad();
+    feat_pool_ = feat_pool_.detach().to(device == "cpu" ? torch::kCPU : torch::kCUDA).requires_grad_(rg);
+  }
+  void ReleaseResources() {
+    feat_pool_ = Tensor();
+    prim_pool_ = Tensor();
+    bias_pool_ = Tensor();
+    shadow_ = Tensor();
+  }
+};
+
+// Hash3DAnchoredFunction (Hash3DAnchored_cuda.cu:160-239).  Unlike the reference the query points / anchors are saved
+// on the autograd node, not on the encoder object, so two forwards before a backward do not corrupt each other.
+struct AnchoredQueryFn : torch::autograd::Function<AnchoredQueryFn> {
+  static Tensor forward(torch::autograd::AutogradContext* ctx, Tensor feat_pool, Tensor points, Tensor anchors,
+                        c10::intrusive_ptr<Hash3DAnchoredImpl> self) {
+    auto pts = points.contiguous();
+    auto anc = anchors.contiguous();
+    ctx->save_for_backward({pts, anc});
+    ctx->saved_data["self"] = self;
+    return self->forward_raw(pts, anc);
+  }
+  static torch::autograd::tensor_list backward(torch::autograd::AutogradContext* ctx,
+                                                torch::autograd::tensor_list grad_outputs) {
+    auto saved = ctx->get_saved_variables();
+    auto self = ctx->saved_data["self"].toCustomClass<Hash3DAnchoredImpl>();
+    return {self->backward_raw(saved[0], saved[1], grad_outputs[0]), Tensor(), Tensor(), Tensor()};
+  }
+};
+
+Tensor Hash3DAnchoredImpl::AnchoredQuery(const Tensor& points, const Tensor& anchors) {
+  if (feat_pool_.requires_grad() && torch::GradMode::is_enabled())
+    return AnchoredQueryFn::apply(feat_pool_, points, anchors, c10::intrusive_ptr<Hash3DAnchoredImpl>::reclaim_copy(this));
+  return forward_raw(points, anchors);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct PersSamplerImpl : torch::CustomClassHolder {
+  Tensor tree_nodes_, pers_trans_, visit_cnt_, weight_stats_, alpha_stats_, search_order_, milestones_;
+  double global_near_ = 0.01, sample_l_ = 1.0 / 256, fineness_ = 1.0, init_fineness_ = 16.0, decay_end_ = 10000.0;
+  double sampled_oct_per_ray_ = 512.0;
+  int64_t mode_ = 0, max_oct_ = 1024, compact_freq_ = 1000;
+  bool scale_by_dis_ = true;
+
+  PersSamplerImpl() {}
+  static void* stream() { return (void*)c10::cuda::getCurrentCUDAStream().stream(); }
+  int64_t n_nodes() const { return tree_nodes_.numel() / GF_TREE_NODE_BYTES; }
+  int64_t n_trans() const { return pers_trans_.numel() / GF_TRANS_INFO_BYTES; }
+
+  void InitSampler(double, std::vector<int64_t>, int64_t, int64_t, double, bool, int64_t, double, int64_t, Tensor,
+                   Tensor, Tensor, Tensor, int64_t, int64_t, double, double, int64_t) {
+    TORCH_CHECK(false,
+                "gfnerf_b200: the octree is built on the host by gfnerf_b200.persoctree.PersOctree (as the reference "
+                "builds it on the host, PersSampler.cpp:92-895); hand its blobs to this class with Configure + "
+                "LoadStates, or use gfnerf_b200.perssampler.PersSamplerCore.InitSampler");
+  }
+  // the scalar arguments of InitSampler (PersSampler.cpp:899-952) without the cameras
+  void Configure(int64_t compact_freq, int64_t max_oct_intersect_per_ray, double global_near, bool scale_by_dis,
+                 double sample_l, int64_t mode, double ray_march_fineness, double ray_march_init_fineness,
+                 int64_t ray_march_fineness_decay_end_iter) {
+    compact_freq_ = compact_freq;
+    max_oct_ = max_oct_intersect_per_ray;
+    global_near_ = global_near;
+    scale_by_dis_ = scale_by_dis;
+    sample_l_ = sample_l;
+    mode_ = mode;
+    fineness_ = ray_march_fineness;
+    init_fineness_ = ray_march_init_fineness;
+    decay_end_ = (double)ray_march_fineness_decay_end_iter;
+  }
+
+  std::vector<Tensor> States() { return {tree_nodes_, pers_trans_, visit_cnt_, milestones_}; }
+  int64_t LoadStates(const std::vector<Tensor>& states, int64_t idx) {  // PersSampler.cpp:983-1016
+    tree_nodes_ = states[idx++].clone().to(torch::kCUDA).contiguous();
+    pers_trans_ = states[idx++].clone().to(torch::kCUDA).contiguous();
+    visit_cnt_ = states[idx++].clone().to(torch::kCUDA).contiguous();
+    milestones_ = states[idx++].clone();
+    auto i64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA);
+    weight_stats_ = torch::full({n_nodes()}, 1000, i64);  // INIT_NODE_STAT
+    alpha_stats_ = torch::full({n_nodes()}, 1000, i64);
+    // search order of the children per ray octant (PersSampler.cpp:137-151): descending bitrev3(child ^ octant)
+    auto so = torch::empty({64}, torch::kUInt8);
+    uint8_t* o = so.data_ptr<uint8_t>();
+    auto bitrev3 = [](int v) { return ((v & 1) << 2) | (v & 2) | ((v >> 2) & 1); };
+    for (int st = 0; st < 8; st++) {
+      int idx8[8];
+      for (int i = 0; i < 8; i++) idx8[i] = i;
+      std::stable_sort(idx8, idx8 + 8, [&](int a, int b) { return bitrev3(a ^ st) > bitrev3(b ^ st); });
+      for (int i = 0; i < 8; i++) o[st * 8 + i] = (uint8_t)idx8[i];
+    }
+    search_order_ = so.to(torch::kCUDA);
+    return idx;
+  }
+
+  // PersSampler::GetSamples (PersSampler_cuda.cu:321-477): the reference's eight dense tensors, same order
+  std::vector<Tensor> GetSamples(const Tensor& rays_o_raw, const Tensor& rays_d_raw, const Tensor& /*bounds*/) {
+    TORCH_CHECK(rays_o_raw.is_cuda() && rays_d_raw.is_cuda(), "gfnerf_b200: tensor is not on a CUDA device");
+    TORCH_CHECK(tree_nodes_.defined(), "PersSampler: no octree loaded (LoadStates)");
+    c10::cuda::CUDAGuard guard(rays_o_raw.device());
+    auto rays_o = rays_o_raw.contiguous().to(torch::kFloat32);
+    auto rays_d = (rays_d_raw / torch::linalg_norm(rays_d_raw, 2, {-1}, true)).contiguous().to(torch::kFloat32);  // :323
+    const int64_t R = rays_o.size(0), S = GF_MAX_SAMPLE_PER_RAY;
+    auto f32 = rays_o.options();
+    auto i64 = f32.dtype(torch::kInt64);
+    // :380-389  ones in VALIDATE mode, U(0.5, 1.5) in TRAIN mode, times the fineness
+    Tensor noise = mode_ == 1 ? torch::ones({S + R + 10}, f32) : torch::rand({S + R + 10}, f32) + 0.5f;
+    noise = noise * (float)fineness_;
+    auto world = torch::zeros({R, S, 3}, f32), warp = torch::zeros({R, S, 3}, f32), dirs = torch::zeros({R, S, 3}, f32);
+    auto anchors = torch::zeros({R, S, 3}, i64);
+    auto dists = torch::zeros({R, S}, f32), ts = torch::zeros({R, S}, f32);
+    auto start_end = torch::zeros({R, 2}, i64);
+    auto first = torch::zeros({R, 1}, f32);
+    auto counts = torch::zeros({R}, f32.dtype(torch::kInt32));
+    if (R > 0) {
+      gf_sampler_out out = {};
+      out.world_pts = world.data_ptr<float>();
+      out.warp_pts = warp.data_ptr<float>();
+      out.dirs = dirs.data_ptr<float>();
+      out.dists = dists.data_ptr<float>();
+      out.ts = ts.data_ptr<float>();
+      out.anchors_i64 = anchors.data_ptr<int64_t>();
+      out.pts_idx_start_end = start_end.data_ptr<int64_t>();
+      out.counts = counts.data_ptr<int32_t>();
+      out.first_oct_dis = first.data_ptr<float>();
+      GF_CHECK(gf_sampler_get_samples(R, rays_o.data_ptr<float>(), rays_d.data_ptr<float>(), noise.data_ptr<float>(),
+                                      tree_nodes_.data_ptr(), n_nodes(), pers_trans_.data_ptr(), n_trans(),
+                                      search_order_.data_ptr<uint8_t>(), (float)global_near_, (float)sample_l_,
+                                      scale_by_dis_ ? 1 : 0, max_oct_, &out, stream()));
+    }
+    return {world, warp, dirs, dists, ts, anchors, start_end, first};
+  }
+
+  // the per-step part of PersSampler::UpdateOctNodes (PersSampler_cuda.cu:584-655): votes, stat update, pruning.
+  // ProcOctree at the milestones / every compact_freq steps is host work (gfnerf_b200.persoctree.PersOctree.proc_octree).
+  void UpdateOctNodes(const Tensor& sampled_anchors, const Tensor& pts_idx_bounds, const Tensor& sampled_weight,
+                      const Tensor& sampled_alpha, int64_t /*iter_step*/) {
+    c10::cuda::CUDAGuard guard(sampled_weight.device());
+    const int64_t R = sampled_weight.size(0), S = GF_MAX_SAMPLE_PER_RAY;
+    auto se = pts_idx_bounds.select(1, 0);  // [R,2]
+    auto counts = (se.select(1, 1) - se.select(1, 0)).to(torch::kInt32).contiguous();
+    auto offsets = (torch::arange(R + 1, sampled_weight.options().dtype(torch::kInt64)) * S).to(torch::kInt32);
+    auto node = sampled_anchors.reshape({R * S, 3}).select(1, 1).to(torch::kInt32).contiguous();
+    auto w = sampled_weight.reshape({-1}).contiguous().to(torch::kFloat32);
+    auto a = sampled_alpha.reshape({-1}).contiguous().to(torch::kFloat32);
+    auto scratch = torch::empty({3 * n_nodes()}, visit_cnt_.options());
+    GF_CHECK(gf_sampler_update_oct_nodes(R, counts.data_ptr<int32_t>(), offsets.data_ptr<int32_t>(),
+                                         node.data_ptr<int32_t>(), w.data_ptr<float>(), a.data_ptr<float>(),
+                                         tree_nodes_.data_ptr(), n_nodes(), weight_stats_.data_ptr<int64_t>(),
+                                         alpha_stats_.data_ptr<int64_t>(), visit_cnt_.data_ptr<int64_t>(),
+                                         scratch.data_ptr<int64_t>(), stream()));
+  }
+
+  void UpdateRayMarch(int64_t cur_step) {  // PersSampler.cpp:958-967 (fp32 arithmetic)
+    if ((double)cur_step >= decay_end_) {
+      fineness_ = 1.0;
+    } else {
+      const float progress = (float)cur_step / (float)decay_end_;
+      fineness_ = std::exp(std::log(1.f) * progress + std::log((float)init_fineness_) * (1.f - progress));
+    }
+  }
+  void UpdateMode(int64_t mode) { mode_ = mode; }
+
+  Tensor TransQueryFrame(const Tensor& world_positions, const Tensor& anchors) {  // :854-922
+    c10::cuda::CUDAGuard guard(world_positions.device());
+    auto wp = world_positions.contiguous().to(torch::kFloat32);
+    auto an = anchors.contiguous().to(torch::kInt64);
+    auto out = torch::zeros_like(wp);
+    GF_CHECK(gf_sampler_trans_query_frame(wp.size(0), tree_nodes_.data_ptr(), n_nodes(), pers_trans_.data_ptr(),
+                                          an.data_ptr<int64_t>(), wp.data_ptr<float>(), out.data_ptr<float>(), stream()));
+    return out;
+  }
+
+  int64_t get_compact_freq_() { return compact_freq_; }
+  int64_t get_max_oct_intersect_per_ray_() { return max_oct_; }
+  double get_global_near_() { return global_near_; }
+  double get_sample_l_() { return sample_l_; }
+  bool get_scale_by_dis_() { return scale_by_dis_; }
+  int64_t get_mode_() { return mode_; }
+  int64_t get_n_volumes_() { return n_trans(); }
+  double get_sampled_oct_per_ray_() { return sampled_oct_per_ray_; }
+  double get_ray_march_fineness_() { return fineness_; }
+};
+
+}  // namespace
+
+TORCH_LIBRARY(my_classes, m) {  // same names as gfnerf/bindings/hashanchored/bindings.cpp:343-401
+  m.class_<Hash3DAnchoredImpl>("Hash3DAnchored")
+      .def(torch::init<int64_t, int64_t, double>())
+      .def("AnchoredQuery", &Hash3DAnchoredImpl::AnchoredQuery)
+      .def("LoadStates", &Hash3DAnchoredImpl::LoadStates)
+      .def("States", &Hash3DAnchoredImpl::States)
+      .def("Reset", &Hash3DAnchoredImpl::Reset)
+      .def("Zero", &Hash3DAnchoredImpl::Zero)
+      .def("GetParams", &Hash3DAnchoredImpl::GetParams)
+      .def("SetFeatPoolRequireGrad", &Hash3DAnchoredImpl::SetFeatPoolRequireGrad)
+      .def("ReleaseResources", &Hash3DAnchoredImpl::ReleaseResources)
+      .def("to", &Hash3DAnchoredImpl::to);
+
+  m.class_<PersSamplerImpl>("PersSampler")
+      .def(torch::init<>())
+      .def("InitSampler", &PersSamplerImpl::InitSampler)
+      .def("Configure", &PersSamplerImpl::Configure)
+      .def("GetSamples", &PersSamplerImpl::GetSamples)
+      .def("UpdateOctNodes", &PersSamplerImpl::UpdateOctNodes)
+      .def("UpdateRayMarch", &PersSamplerImpl::UpdateRayMarch)
+      .def("UpdateMode", &PersSamplerImpl::UpdateMode)
+      .def("States", &PersSamplerImpl::States)
+      .def("LoadStates", &PersSamplerImpl::LoadStates)
+      .def("get_compact_freq_", &PersSamplerImpl::get_compact_freq_)
+      .def("get_max_oct_intersect_per_ray_", &PersSamplerImpl::get_max_oct_intersect_per_ray_)
+      .def("get_global_near_", &PersSamplerImpl::get_global_near_)
+      .def("get_sample_l_", &PersSamplerImpl::get_sample_l_)
+      .def("get_scale_by_dis_", &PersSamplerImpl::get_scale_by_dis_)
+      .def("get_mode_", &PersSamplerImpl::get_mode_)
+      .def("get_n_volumes_", &PersSamplerImpl::get_n_volumes_)
+      .def("get_sampled_oct_per_ray_", &PersSamplerImpl::get_sampled_oct_per_ray_)
+      .def("get_ray_march_fineness_", &PersSamplerImpl::get_ray_march_fineness_)
+      .def("trans_query_frame", &PersSamplerImpl::TransQueryFrame);
+}

@@ -1,0 +1,100 @@
+"""The TorchScript custom classes `torch.classes.my_classes.{Hash3DAnchored, PersSampler}` (csrc/torch_bindings.cpp,
+the reference's own operator boundary, gfnerf/bindings/hashanchored/bindings.cpp:343-401) loaded the way the
+reference loads its f2nerf-bindings.so, against the Python host layer over the same C-ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "gf-nerf_b200", "f2nerf_bindings_b200.so")
+
+
+def load():
+    if not os.path.exists(SO):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gf_build", os.path.join(ROOT, "gf-nerf_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+        mod.build_torch_bindings()
+    torch.classes.load_library(SO)      # gfnerf/hash_3d_anchored.py:13-14
+    return torch.classes.my_classes
+
+
+def test_library_registers_the_reference_class_names():
+    mc = load()
+    s = mc.PersSampler()
+    for name in ("InitSampler", "GetSamples", "UpdateOctNodes", "UpdateRayMarch", "UpdateMode", "States", "LoadStates",
+                 "trans_query_frame", "get_ray_march_fineness_", "get_n_volumes_"):
+        assert hasattr(s, name), name
+    s.UpdateMode(1)
+    assert s.get_mode_() == 1
+    s.Configure(1000, 1024, 0.01, True, 1.0 / 256, 0, 1.0, 16.0, 10000)
+    s.UpdateRayMarch(0)
+    assert abs(s.get_ray_march_fineness_() - 16.0) < 1e-5
+    s.UpdateRayMarch(10000)
+    assert s.get_ray_march_fineness_() == 1.0
+    with pytest.raises(RuntimeError, match="persoctree"):
+        s.InitSampler(1.5, [2000], 1000, 1024, 0.01, True, 10, 1.0 / 256, 16, torch.zeros(1, 3, 4), torch.zeros(1, 3, 4),
+                      torch.zeros(1, 3, 3), torch.zeros(1, 2), 0, 512, 1.0, 16.0, 10000)
+    assert hasattr(mc, "Hash3DAnchored")
+
+
+@pytest.mark.gpu
+def test_hash3d_class_equals_python_core():
+    from gfnerf_b200.hash_3d_anchored import Hash3DAnchoredCore
+    from tests.helpers import hash_inputs
+    mc = load()
+    n, n_vol, log2T = 5000, 6, 13
+    _, _, _, pts, anchors = hash_inputs(n, n_vol, log2T, seed=4)
+    py = Hash3DAnchoredCore(log2T, n_vol)
+    py.Reset()
+    cc = mc.Hash3DAnchored(log2T, n_vol, 0.1)
+    assert cc.LoadStates(py.States(), 0) == 4
+    for a, b in zip(cc.States(), py.States()):
+        assert torch.equal(a.cpu(), b.cpu())
+    tp, ta = torch.from_numpy(pts).cuda(), torch.from_numpy(anchors).cuda()
+    out_c = cc.AnchoredQuery(tp, ta)
+    out_p = py.AnchoredQuery(tp, ta)
+    assert out_c.shape == (n, 32) and torch.equal(out_c, out_p)                      # bit-exact encodings
+    g = torch.randn(n, 32, generator=torch.Generator().manual_seed(0)).cuda() * 1e-3
+    out_c.backward(g)
+    out_p.backward(g)
+    gc, gp = cc.GetParams()[0].grad, py.GetParams()[0].grad
+    assert float((gc - gp).abs().max()) <= 1e-5 * float(gp.abs().max())            # fp32 atomics: order only
+    cc.Zero()
+    assert float(cc.AnchoredQuery(tp, ta).abs().max()) == 0.0
+    cc.SetFeatPoolRequireGrad(False)
+    assert not cc.AnchoredQuery(tp, ta).requires_grad
+
+
+@pytest.mark.gpu
+def test_perssampler_class_equals_python_core():
+    from gfnerf_b200.persoctree import rig_rays
+    from tests.helpers import load_rig, make_sampler
+    mc = load()
+    rig = load_rig("rig8")
+    py = make_sampler(rig, mode=1)
+    cc = mc.PersSampler()
+    cc.Configure(1000, 1024, 0.01, True, 1.0 / 256, 1, 1.0, 16.0, 10000)
+    assert cc.LoadStates(py.States(), 0) == 4
+    assert cc.get_n_volumes_() == py.get_n_volumes()
+    o, d, _ = rig_rays(rig["c2w"], rig["intri"], 300, seed=8)
+    to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    bounds = torch.zeros(300, 2).cuda()
+    a, b = cc.GetSamples(to, td, bounds), py.GetSamples(to, td, bounds)
+    assert len(a) == 8
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and x.dtype == y.dtype and torch.equal(x, y)     # bit-exact dense tensors
+    w = torch.rand(300, 1024, 1).cuda() * (a[3] > 0).unsqueeze(-1)
+    se = a[6].unsqueeze(1).expand(-1, 1024, -1).contiguous()
+    cc.UpdateOctNodes(a[5], se, w, w, 10)
+    py._vote(300, (a[6][:, 1] - a[6][:, 0]).int().contiguous(),
+             (torch.arange(301, device="cuda") * 1024).int(), a[5].reshape(-1, 3)[:, 1].int().contiguous(),
+             w.reshape(-1).contiguous(), w.reshape(-1).contiguous())
+    assert torch.equal(cc.States()[2], py.States()[2])                               # visit counts
+    wp = torch.rand(50, 3).cuda()
+    nodes = a[5][0, :50, 1].contiguous()
+    assert torch.equal(cc.trans_query_frame(wp, nodes), py.TransQueryFrame(wp, nodes))
