@@ -240,6 +240,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sample-ahead", action="store_true",
+                    help="sample each batch at the start of its own step instead of under the previous backward")
     ap.add_argument("--workload", default="global", choices=["global", "focal", "render"],
                     help="global: BASELINE config 2/3 (the bench line).  focal: config 4 -- frozen global encoder + "
                          "one private residual sub-encoder per GPU (log2T 21), no gradient exchange.  render: config 5 "
@@ -293,14 +295,20 @@ def main():
     resident = [tuple(a.to(dev, non_blocking=True) for a in b) for b in pinned]
     torch.cuda.synchronize()
 
-    def step_resident(i):
+    # the data loader knows the next batch: its rays are handed over one step early, so their sampling (which only
+    # depends on the octree) runs underneath this step's backward pass
+    ahead = not args.no_sample_ahead
+    if os.environ.get("GF_PRESAMPLE_EARLY"):      # A/B: issue the next batch's sampling right after the octree vote
+        eng.presample_after_mlp = False
+
+    def step_resident(i, ahead=ahead):
         o, d, cam, tgt = resident[i % N_BATCHES]
-        return eng.train_step(o, d, tgt, cam)
+        return eng.train_step(o, d, tgt, cam, next_rays=resident[(i + 1) % N_BATCHES][:2] if ahead else None)
 
     def step_e2e(i):
         # the public host-buffer entry point: pinned host batch in (H2D inside the step), the step's loss out (D2H)
         o, d, cam, tgt = pinned[i % N_BATCHES]
-        return eng.train_step_host(o, d, tgt, cam)
+        return eng.train_step_host(o, d, tgt, cam, next_rays=pinned[(i + 1) % N_BATCHES][:2] if ahead else None)
 
     def barrier():
         if world > 1:
@@ -343,8 +351,8 @@ def main():
     eng.enable_timers(True)
     n_prof = min(args.steps, 10)
     samples = 0
-    for i in range(n_prof):
-        out = step_resident(args.warmup + args.steps + i)
+    for i in range(n_prof):   # one kernel at a time (no sampling ahead): the stage events need serial execution
+        out = step_resident(args.warmup + args.steps + i, ahead=False)
         samples += int(out.n_samples.item())
     stages = eng.stage_times()
     eng.enable_timers(False)
@@ -416,6 +424,7 @@ def main():
                        "samples_per_step_per_gpu": round(v_mean), "slots_per_step_per_gpu": RAYS_PER_GPU * 1024,
                        "l2_policy": "inputs larger than L2 (0.3 GB table+optimizer state, ~1 GB sample buffers, "
                                     f"{N_BATCHES} ray batches cycled)",
+                       "sample_ahead": bool(ahead),
                        "parallelism": f"dp{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "rays/s",
                     "h2d_bytes_per_step": int(sum(a.numel() * a.element_size() for a in pinned[0])) * world,

@@ -121,7 +121,7 @@ hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
   }
 }
 
-template <bool POW2, typename AnchorT, bool GRAD_F16>
+template <bool POW2, typename AnchorT, bool GRAD_F16, bool HAS_BIAS, bool UNSCALE>
 __global__ void __launch_bounds__(kHashBlock)
 hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volumes, uint32_t local_size,
                 const int32_t* __restrict__ prim_pool, const float* __restrict__ bias_pool,
@@ -133,6 +133,7 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
     n = dn < n ? dn : n;
   }
   __shared__ float s_scale[GF_N_LEVELS];
+  __shared__ __align__(16) float s_stage[(kHashBlock / 32) * kScatterWarpWords];
   if (threadIdx.x < GF_N_LEVELS) s_scale[threadIdx.x] = __ldg(scales + threadIdx.x);
   __syncthreads();
   const int lane = lane_id();
@@ -149,23 +150,21 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
       z = __ldg(pts + 3 * i + 2);
       vol = (int)anchors[i];
     }
-#pragma unroll 2
+#pragma unroll 1
     for (int l = 0; l < GF_N_LEVELS; l++) {
       // this level's two gradients, quantised like the reference: fp16(g*128)  (:209)
-      float g0 = 0.f, g1 = 0.f;
+      __half2 gh = __float2half2_rn(0.f);
       if (valid) {
-        __half2 gh;
         if (GRAD_F16) {
           gh = __ldg(reinterpret_cast<const __half2*>(grad_in_v) + i * GF_N_LEVELS + l);
         } else {
           const float2 v = __ldg(reinterpret_cast<const float2*>(grad_in_v) + i * GF_N_LEVELS + l);
           gh = __floats2half2_rn(__fmul_rn(v.x, GF_GRAD_SCALE), __fmul_rn(v.y, GF_GRAD_SCALE));
         }
-        g0 = __low2float(gh);
-        g1 = __high2float(gh);
       }
-      hash_scatter_level<POW2>(l, x, y, z, vol, valid, g0, g1, lane, n_volumes, local_size, prim_pool, bias_pool,
-                               s_scale[l], grad_table, aggregate != 0);
+      hash_scatter_level<POW2, HAS_BIAS, UNSCALE>(l, x, y, z, vol, valid, gh, lane, n_volumes, local_size, prim_pool,
+                                                  bias_pool, s_scale[l], grad_table, aggregate != 0,
+                                                  s_stage + (threadIdx.x >> 5) * kScatterWarpWords);
     }
   }
 }
@@ -294,14 +293,25 @@ int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64
   const bool p2 = is_pow2(local_size);
   // GF_HASH_AGG=0 disables the warp-aggregated reduction (profiling A/B only)
   static const int aggregate = [] { const char* e = getenv("GF_HASH_AGG"); return e ? atoi(e) : 1; }();
-#define GF_BWD(P2, AT, G16)                                                                               \
-  hash_bwd_kernel<P2, AT, G16><<<grid, kHashBlock, 0, st>>>(n, d_n_ptr, n_volumes, (uint32_t)local_size,  \
-                                                            prim_pool, bias_pool, level_scales, pts,      \
-                                                            (const AT*)anchors, grad_in, grad_table, aggregate)
-#define GF_BWD_G(P2, AT)                                    \
-  do {                                                      \
-    if (grad_in_is_scaled_f16) GF_BWD(P2, AT, true);        \
-    else GF_BWD(P2, AT, false);                             \
+  const bool g16 = (grad_in_is_scaled_f16 & 1) != 0, unscale = (grad_in_is_scaled_f16 & 2) == 0;
+#define GF_BWD(P2, AT, G16, HB, US)                                                                              \
+  hash_bwd_kernel<P2, AT, G16, HB, US><<<grid, kHashBlock, 0, st>>>(n, d_n_ptr, n_volumes, (uint32_t)local_size, \
+                                                                    prim_pool, bias_pool, level_scales, pts,     \
+                                                                    (const AT*)anchors, grad_in, grad_table, aggregate)
+#define GF_BWD_U(P2, AT, G16, HB)                  \
+  do {                                             \
+    if (unscale) GF_BWD(P2, AT, G16, HB, true);    \
+    else GF_BWD(P2, AT, G16, HB, false);           \
+  } while (0)
+#define GF_BWD_B(P2, AT, G16)                      \
+  do {                                             \
+    if (bias_pool) GF_BWD_U(P2, AT, G16, true);    \
+    else GF_BWD_U(P2, AT, G16, false);             \
+  } while (0)
+#define GF_BWD_G(P2, AT)                           \
+  do {                                             \
+    if (g16) GF_BWD_B(P2, AT, true);               \
+    else GF_BWD_B(P2, AT, false);                  \
   } while (0)
   if (p2) {
     if (anchor_i64) GF_BWD_G(true, int64_t); else GF_BWD_G(true, int32_t);
@@ -309,6 +319,8 @@ int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64
     if (anchor_i64) GF_BWD_G(false, int64_t); else GF_BWD_G(false, int32_t);
   }
 #undef GF_BWD_G
+#undef GF_BWD_B
+#undef GF_BWD_U
 #undef GF_BWD
   return check_launch("hash_bwd_kernel");
 }

@@ -68,72 +68,154 @@ __device__ __forceinline__ void weights(const Cell& c, float (&w)[8]) {
 // fp16 round trip of a product, :148-151  (__half)(w0 * ws[d])
 __device__ __forceinline__ float q16(float v) { return __half2float(__float2half_rn(v)); }
 
+// ---- backward scatter ---------------------------------------------------------------------------------------
+// Shared-memory staging of the run reduction: one row per lane = 8 x (float2 contribution) + 8 x (u32 table row),
+// padded to 26 words so that the four lane quarters of a column read fall into disjoint bank halves.
+constexpr int kScatterRowWords = 26;
+constexpr int kScatterWarpWords = 32 * kScatterRowWords;
+
+// red.global.add.v2.f32 of (s0, s1) * out_scale to tab[row] unless both are zero or `mask` (0 / ~0) is off: one
+// predicated instruction, no branch and no reconvergence bookkeeping around the 8 corner updates of a level
+template <bool UNSCALE>
+__device__ __forceinline__ void red_add_f32x2(const char* tab, uint32_t row, float s0, float s1, uint32_t mask) {
+  constexpr float out_scale = 1.f / GF_GRAD_SCALE;
+  if (!UNSCALE) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        ".reg .b64 a;\n"
+        "or.b32 t, %2, %3;\n"
+        "and.b32 t, t, %4;\n"
+        "and.b32 t, t, 0x7fffffff;\n"
+        "setp.ne.b32 p, t, 0;\n"
+        "mad.wide.u32 a, %1, 8, %0;\n"
+        "@p red.global.add.v2.f32 [a], {%2, %3};\n"
+        "}\n" ::"l"(tab),
+        "r"(row), "f"(s0), "f"(s1), "r"(mask)
+        : "memory");
+    return;
+  }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t;\n"
+      ".reg .b64 a;\n"
+      ".reg .f32 u, v;\n"
+      "or.b32 t, %2, %3;\n"
+      "and.b32 t, t, %4;\n"
+      "and.b32 t, t, 0x7fffffff;\n"
+      "setp.ne.b32 p, t, 0;\n"
+      "mad.wide.u32 a, %1, 8, %0;\n"
+      "mul.rn.f32 u, %2, %5;\n"
+      "mul.rn.f32 v, %3, %5;\n"
+      "@p red.global.add.v2.f32 [a], {u, v};\n"
+      "}\n" ::"l"(tab),
+      "r"(row), "f"(s0), "f"(s1), "r"(mask), "f"(out_scale)
+      : "memory");
+}
+
 // One level of the backward scatter for the 32 consecutive samples held by a warp (:81-155): recompute cell / corner
 // rows / weights, quantise the 8 x 2 contributions like the reference (fp16(g * 128) times w, each product rounded to
-// fp16), sum runs of lanes that fall into the same cell of the same volume with a segmented shuffle reduction whose
-// depth adapts to the longest run, and let the run's first lane issue the 8 vectorised fp32 reductions.
-// g0 / g1: this sample's two gradients of the level, already fp16(g * 128) values.  Must be called by all 32 lanes.
-template <bool POW2>
-__device__ __forceinline__ void hash_scatter_level(int l, float x, float y, float z, int vol, bool valid, float g0,
-                                                   float g1, int lane, int32_t n_volumes, uint32_t local_size,
+// fp16, one F2FP per corner), then add them to the fp32 gradient table.  Lanes that fall into the same cell of the
+// same volume (contiguous runs along the ray) are summed first; three warp-uniform paths by the longest run:
+//   1        every lane issues its own 8 predicated vector reductions;
+//   2..4     segmented shuffle reduction (1-2 steps), the run's first lane issues the reductions;
+//   > 4      the contributions and rows go through shared memory and lane (corner d = lane & 7, quarter q = lane >> 3)
+//            walks the 8 rows of its quarter in lane order, flushing its fp32 partial sum at every run boundary:
+//            8 loads + 16 adds per lane whatever the run structure (a 5-step shuffle tree costs 80 + 80).
+// gh: this sample's two gradients of the level as fp16(g * 128).  Must be called by all 32 lanes.
+// UNSCALE: the sums are divided by GF_GRAD_SCALE (:238); false leaves the table at the x128 scale for a caller that
+// folds the division into its optimizer step (exact either way: a power of two).
+template <bool POW2, bool HAS_BIAS, bool UNSCALE>
+__device__ __forceinline__ void hash_scatter_level(int l, float x, float y, float z, int vol, bool valid, __half2 gh,
+                                                   int lane, int32_t n_volumes, uint32_t local_size,
                                                    const int32_t* __restrict__ prim_pool,
                                                    const float* __restrict__ bias_pool, float scale,
-                                                   float* __restrict__ grad_table, bool aggregate) {
+                                                   float* __restrict__ grad_table, bool aggregate,
+                                                   float* __restrict__ s_warp) {
   const int tr = (l * n_volumes + vol) * 3;
-  const Cell c = cell_of(x, y, z, scale, bias_pool ? bias_pool + tr : nullptr);
+  const Cell c = cell_of(x, y, z, scale, HAS_BIAS ? bias_pool + tr : nullptr);
   const uint32_t pa = (uint32_t)__ldg(prim_pool + tr), pb = (uint32_t)__ldg(prim_pool + tr + 1),
                  pc = (uint32_t)__ldg(prim_pool + tr + 2);
   uint32_t pos[8];
   corners<POW2>(c, pa, pb, pc, local_size, pos);
   float w[8];
   weights(c, w);
-  float c0[8], c1[8];
+  const float g0 = __low2float(gh), g1 = __high2float(gh);
+  // gh is zero for a lane past the end; a zero gradient gives zero products, which are never written (:147)
+  uint32_t cq[8];  // (__half)(g0 * w), (__half)(g1 * w) :148-151
 #pragma unroll
   for (int d = 0; d < 8; d++) {
-    c0[d] = q16(__fmul_rn(g0, w[d]));
-    c1[d] = q16(__fmul_rn(g1, w[d]));
+    const __half2 h = __floats2half2_rn(__fmul_rn(g0, w[d]), __fmul_rn(g1, w[d]));
+    cq[d] = *reinterpret_cast<const uint32_t*>(&h);
   }
-  bool writer = valid && (g0 != 0.f || g1 != 0.f);  // :147 skip when both are zero
+  const char* tab = reinterpret_cast<const char*>(grad_table) + (uint64_t)l * local_size * 8u;
+  int maxrun = 1;
+  uint32_t heads = 0xffffffffu;
+  int end = lane + 1;
   if (aggregate) {
-    // runs of lanes in the same cell of the same volume -> one reduction per run
     const uint32_t ppx = __shfl_up_sync(0xffffffffu, c.px, 1), ppy = __shfl_up_sync(0xffffffffu, c.py, 1),
                    ppz = __shfl_up_sync(0xffffffffu, c.pz, 1);
     const int pvol = __shfl_up_sync(0xffffffffu, vol, 1);
     const bool head = lane == 0 || ppx != c.px || ppy != c.py || ppz != c.pz || pvol != vol;
-    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    heads = __ballot_sync(0xffffffffu, head);
     const uint32_t above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
-    const int end = above ? (__ffs(above) - 1) : 32;
-    // longest run in the warp: the segmented reduction needs ceil(log2) of it steps -- 5 on the coarse levels
-    // (the whole warp in one cell), 0..2 on the fine ones, where most of the samples are
-    const int maxrun = (int)__reduce_max_sync(0xffffffffu, head ? (unsigned)(end - lane) : 0u);
-    if (maxrun > 1) {  // warp-uniform
-      if (!valid) {
-#pragma unroll
-        for (int d = 0; d < 8; d++) c0[d] = c1[d] = 0.f;
-      }
-      for (int off = 1; off < maxrun; off <<= 1) {
-        const bool take = lane + off < end;
-#pragma unroll
-        for (int d = 0; d < 8; d++) {
-          float o0 = __shfl_down_sync(0xffffffffu, c0[d], off);
-          float o1 = __shfl_down_sync(0xffffffffu, c1[d], off);
-          if (take) {
-            c0[d] += o0;
-            c1[d] += o1;
-          }
-        }
-      }
-      writer = head && valid;
-    }
+    end = above ? (__ffs(above) - 1) : 32;
+    maxrun = (int)__reduce_max_sync(0xffffffffu, head ? (unsigned)(end - lane) : 0u);
   }
-  if (writer) {
-    float2* tab = reinterpret_cast<float2*>(grad_table) + (int64_t)l * local_size;
+  if (maxrun > 4) {  // warp-uniform
+    float* row = s_warp + lane * kScatterRowWords;
 #pragma unroll
     for (int d = 0; d < 8; d++) {
-      const float s0 = c0[d] * (1.f / GF_GRAD_SCALE), s1 = c1[d] * (1.f / GF_GRAD_SCALE);
-      if (s0 != 0.f || s1 != 0.f) atomicAdd(tab + pos[d], make_float2(s0, s1));
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&cq[d]));
+      *reinterpret_cast<float2*>(row + 2 * d) = v;
     }
+#pragma unroll
+    for (int d = 0; d < 8; d += 2) *reinterpret_cast<uint2*>(row + 16 + d) = make_uint2(pos[d], pos[d + 1]);
+    __syncwarp();
+    const int d = lane & 7, j0 = lane & 24;
+    const uint32_t stops = (heads >> 1) | 0x80808080u;  // bit j: lane j is the last of its run or of its quarter
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float* rj = s_warp + (j0 + k) * kScatterRowWords;
+      const float2 v = *reinterpret_cast<const float2*>(rj + 2 * d);
+      a0 += v.x;
+      a1 += v.y;
+      if ((stops >> (j0 + k)) & 1u) {
+        red_add_f32x2<UNSCALE>(tab, __float_as_uint(rj[16 + d]), a0, a1, 0xffffffffu);
+        a0 = a1 = 0.f;
+      }
+    }
+    __syncwarp();  // the rows are rewritten by the next level
+    return;
   }
+  float c0[8], c1[8];
+#pragma unroll
+  for (int d = 0; d < 8; d++) {
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&cq[d]));
+    c0[d] = v.x;
+    c1[d] = v.y;
+  }
+  uint32_t writer = 0xffffffffu;  // contributions of dead lanes are already zero
+  if (maxrun > 1) {
+    for (int off = 1; off < maxrun; off <<= 1) {
+      const bool take = lane + off < end;
+#pragma unroll
+      for (int d = 0; d < 8; d++) {
+        const float o0 = __shfl_down_sync(0xffffffffu, c0[d], off);
+        const float o1 = __shfl_down_sync(0xffffffffu, c1[d], off);
+        if (take) {
+          c0[d] += o0;
+          c1[d] += o1;
+        }
+      }
+    }
+    writer = 0u - ((heads >> lane) & 1u);
+  }
+#pragma unroll
+  for (int d = 0; d < 8; d++) red_add_f32x2<UNSCALE>(tab, pos[d], c0[d], c1[d], writer);
 }
 
 }  // namespace gf

@@ -44,6 +44,20 @@ constexpr int kThreads = 256;
 
 enum Mode { kFwd = 0, kBwdFrozen = 1, kBwdFull = 2 };
 
+#ifdef GF_MLP_TRACE
+// profiling build only (tools/mlp_trace.py): clock64() of thread 0 / thread 128 of CTA 0 at the phase boundaries of
+// its third tile
+__device__ unsigned long long g_mlp_trace[2][64];
+#define GF_TR()                                                                              \
+  {                                                                                          \
+    if (blockIdx.x == 0 && tile == 2 * (int64_t)gridDim.x && (tid & 127) == 0 && tr_i < 64)  \
+      g_mlp_trace[tid >> 7][tr_i] = clock64();                                               \
+    tr_i++;                                                                                  \
+  }
+#else
+#define GF_TR()
+#endif
+
 // ---- shared memory ------------------------------------------------------------------------------------
 // B operands: [N rows][K] fp16, K-major, no swizzle: element (n, k) at
 //   (n / 8) * SBO + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2,   SBO = (K / 8) * 128
@@ -60,9 +74,11 @@ constexpr uint32_t kOffBb3 = kOffBb1 + 16 * 16 * 2;
 constexpr uint32_t kOffBb4 = kOffBb3 + 64 * 16 * 2;
 constexpr uint32_t kOffOnes = kOffBb4 + 16 * 16 * 2;  // A tile [128][16]: column 0 = 1
 constexpr uint32_t kOffBar = kOffOnes + 128 * 16 * 2;
-constexpr uint32_t kOffTmem = kOffBar + 8;
+constexpr uint32_t kOffBarW = kOffBar + 8;            // second mbarrier: completion of the weight-gradient MMAs
+constexpr uint32_t kOffTmem = kOffBar + 16;
 constexpr uint32_t kOffRay = kOffTmem + 8;             // int32 ray id of each row (full backward)
-constexpr uint32_t kSmemBase = (kOffRay + 512 + 127) / 128 * 128;
+// + int32 [8]: the ray of each of the tile's (up to) 8 ray slots, + int32: "a row fell outside the 8 slots"
+constexpr uint32_t kSmemBase = (kOffRay + 512 + 64 + 127) / 128 * 128;
 // [sample][feature] tiles of the full backward
 constexpr uint32_t kSboX = 640, kSboH = 1152, kSboG = 1024, kSboS = 256;
 constexpr uint32_t kOffX = kSmemBase;                  // [128][32 + 8]   SBO 640
@@ -71,7 +87,8 @@ constexpr uint32_t kOffH2 = kOffH1 + 16 * kSboH;
 constexpr uint32_t kOffH3 = kOffH2 + 16 * kSboH;
 constexpr uint32_t kOffHh = kOffH3 + 16 * kSboH;       // [128][16]       SBO 256
 constexpr uint32_t kOffGo = kOffHh + 16 * kSboS;       // [128][16]       SBO 256 (Gh reuses it)
-constexpr uint32_t kSmemFull = kOffGo + 16 * kSboS + 1024;  // + slack: the M = 128 reads of H3' run past its tile
+constexpr uint32_t kOffInd = kOffGo + 16 * kSboS;      // [128][8]        SBO 128: ray-slot indicator (one-hot rows)
+constexpr uint32_t kSmemFull = kOffInd + 16 * 128 + 1024;  // + slack: the M = 128 reads of H3' run past its tile
 
 // ---- tensor memory --------------------------------------------------------------------------------------
 constexpr uint32_t kColD = 0, kColA = 64;
@@ -115,31 +132,33 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ p, unsig
 }
 
 // forward layer: D[kColD .. +N) = A[kColA .. +K/2) . B^T (+ bias): K/16 TS-form MMAs + one SS-form bias MMA
+// (sBe = smem_base_enc of the CTA's shared memory; all offsets are compile-time constants)
 template <int N, int K, bool BIAS>
-__device__ __forceinline__ void issue_fwd(uint32_t tmem, uint32_t sB, uint32_t off_w, uint32_t off_bias) {
+__device__ __forceinline__ void issue_fwd(uint32_t tmem, uint32_t sBe, uint32_t off_w, uint32_t off_bias) {
   constexpr uint32_t idesc = instr_desc(kTile, N);
 #pragma unroll
   for (int k = 0; k < K / 16; k++)
-    mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc(sB + off_w + 2 * k * kLbo, kLbo, sbo_of(K)), idesc, k > 0);
+    mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc_at(sBe, off_w + 2 * k * kLbo, kLbo, sbo_of(K)), idesc, k > 0);
   if (BIAS)
-    mma_ss(tmem + kColD, smem_desc(sB + kOffOnes, kLbo, sbo_of(16)), smem_desc(sB + off_bias, kLbo, sbo_of(16)), idesc, 1u);
+    mma_ss(tmem + kColD, smem_desc_at(sBe, kOffOnes, kLbo, sbo_of(16)), smem_desc_at(sBe, off_bias, kLbo, sbo_of(16)),
+           idesc, 1u);
 }
 // dgrad layer: D[128 x N] = G[128 x K] (TMEM) . W[K x N], W = the forward tile [K = out][N = in] read MN-major
 template <int N, int K>
-__device__ __forceinline__ void issue_dgrad(uint32_t tmem, uint32_t w_smem, uint32_t sbo_fwd) {
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem, uint32_t sBe, uint32_t off_w, uint32_t sbo_fwd) {
   constexpr uint32_t idesc = instr_desc(kTile, N, 0, 1);
 #pragma unroll
   for (int k = 0; k < K / 16; k++)
-    mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc(w_smem + 2 * k * sbo_fwd, sbo_fwd, 128), idesc, k > 0);
+    mma_ts(tmem + kColD, tmem + kColA + 8 * k, smem_desc_at(sBe, off_w + 2 * k * sbo_fwd, sbo_fwd, 128), idesc, k > 0);
 }
 // wgrad: D[M x N] (+)= P^T . Q over the tile's 128 samples; P, Q = [sample][feature] tiles (SBO sp / sq), MN-major
 template <int M, int N>
-__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t p_smem, uint32_t sp, uint32_t q_smem, uint32_t sq,
-                                            bool first_tile) {
+__device__ __forceinline__ void issue_wgrad(uint32_t d_tmem, uint32_t sBe, uint32_t off_p, uint32_t sp, uint32_t off_q,
+                                            uint32_t sq, bool first_tile) {
   constexpr uint32_t idesc = instr_desc(M, N, 1, 1);
 #pragma unroll
   for (int k = 0; k < kTile / 16; k++)
-    mma_ss(d_tmem, smem_desc(p_smem + 2 * k * sp, sp, 128), smem_desc(q_smem + 2 * k * sq, sq, 128), idesc,
+    mma_ss(d_tmem, smem_desc_at(sBe, off_p + 2 * k * sp, sp, 128), smem_desc_at(sBe, off_q + 2 * k * sq, sq, 128), idesc,
            (k > 0 || !first_tile) ? 1u : 0u);
 }
 
@@ -182,19 +201,55 @@ __device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const uint3
 
 // publish this thread's TMEM / shared-memory writes, let one thread issue the MMAs, wait for their completion
 #define GF_TC_SYNC_ISSUE(ISSUE) \
+  GF_TR()                       \
   tmem_wait_st();               \
   tc_fence_before();            \
   fence_proxy_async();          \
   __syncthreads();              \
-  if (tid == 0) {               \
-    tc_fence_after();           \
-    ISSUE;                      \
-    mma_commit(bar);            \
-  }
+  GF_TR()                       \
+  if (warp_u == 0) {            \
+    if (elect_one()) {          \
+      tc_fence_after();         \
+      ISSUE;                    \
+      mma_commit(bar);          \
+    }                           \
+    __syncwarp();               \
+  }                             \
+  GF_TR()
 #define GF_TC_WAIT()     \
   mbar_wait(bar, phase); \
   phase ^= 1;            \
-  tc_fence_after();
+  tc_fence_after();      \
+  GF_TR()
+// backward round: the dgrad MMAs (whose result the epilogue needs) and the weight-gradient MMAs (which only have to
+// finish before their shared-memory operands are overwritten) are committed to different barriers, so the
+// weight-gradient MMAs run underneath the epilogue's tcgen05.ld / pack / tcgen05.st
+#define GF_TC_SYNC_ISSUE2(ISSUE_D, ISSUE_W) \
+  GF_TR()                                   \
+  tmem_wait_st();                           \
+  tc_fence_before();                        \
+  fence_proxy_async();                      \
+  __syncthreads();                          \
+  GF_TR()                                   \
+  if (warp_u == 0) {                        \
+    if (elect_one()) {                      \
+      tc_fence_after();                     \
+      ISSUE_D;                              \
+      mma_commit(bar);                      \
+      if (WGRAD) {                          \
+        ISSUE_W;                            \
+        mma_commit(bar_w);                  \
+      }                                     \
+    }                                       \
+    __syncwarp();                           \
+  }                                         \
+  GF_TR()
+#define GF_TC_WAIT_W()         \
+  if (WGRAD) {                 \
+    mbar_wait(bar_w, phase_w); \
+    phase_w ^= 1;              \
+  }                            \
+  GF_TR()
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == kFwd ? 4 : 2)
@@ -212,9 +267,10 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
   const int hf = warp >> 2;              // column half
   const float inv_gscale = BWD ? 1.f / gscale : 1.f;
   stage_weights(params, smem);
-  const uint32_t bar = smem_u32(smem + kOffBar);
+  const uint32_t bar = smem_u32(smem + kOffBar), bar_w = smem_u32(smem + kOffBarW);
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_w, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -227,38 +283,96 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmem);
   const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t sB = smem_u32(smem);
+  const uint32_t sBe = smem_base_enc(smem_u32(smem));
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform: the issue branch stays converged
   int* s_ray = reinterpret_cast<int*>(smem + kOffRay);
   if (d_n_ptr) {
     const int64_t dn = *d_n_ptr;
     n = dn < n ? dn : n;
   }
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase_w = 0;
   bool first_tile = true;
   const int64_t n_tiles = (n + kTile - 1) / kTile;
+  // this thread's inputs of the CTA's NEXT tile are loaded one tile ahead into registers (a DRAM round trip at the
+  // top of a tile would sit on the critical path of all 256 threads)
+  // (backward modes: the forward runs 4 CTAs per SM at 64 registers and uses an L2 prefetch instead)
+  constexpr bool kRegAhead = BWD;
+  uint4 xn0 = make_uint4(0u, 0u, 0u, 0u), xn1 = xn0;
+  int rayn = -1;
+  if (kRegAhead) {
+    const int64_t row0 = (int64_t)blockIdx.x * kTile + r;
+    if (row0 < n) {
+      const uint4* src = reinterpret_cast<const uint4*>(feat + row0 * 32 + 16 * hf);
+      xn0 = __ldg(src);
+      xn1 = __ldg(src + 1);
+      rayn = __ldg(ray_id + row0);
+    }
+  }
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = tile * kTile + r;
     const bool valid = row < n;
-    const int ray = valid ? __ldg(ray_id + row) : -1;
+#ifdef GF_MLP_TRACE
+    int tr_i = 0;
+    GF_TR()
+#endif
+    int ray = rayn;
+    uint4 x0 = xn0, x1 = xn1;
+    if (!kRegAhead) {
+      ray = -1;
+      x0 = x1 = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) {
+        const uint4* src = reinterpret_cast<const uint4*>(feat + row * 32 + 16 * hf);
+        x0 = __ldg(src);
+        x1 = __ldg(src + 1);
+        ray = __ldg(ray_id + row);
+      }
+    }
+    // the ray's bias row (b2 + W2[:, SH] SH(d) + W2[:, emb] emb), read in the epilogue of the head's first layer,
+    // and the upstream gradients read at the turn to the backward half: towards L1 now
+    const float* rb = ray_bias + (int64_t)(valid ? ray : 0) * kH + 32 * hf;
+    if (valid) {
+      prefetch_l1(rb);
+      if (BWD) {
+        if (hf == 0) prefetch_l1(d_rgb + 3 * row);
+        else prefetch_l1(d_sigma + row);
+      }
+    }
+    const int64_t nrow = row + (int64_t)gridDim.x * kTile;
     uint32_t h1p[16], h2p[16], h3p[16];  // post-ReLU activations of this thread's column half (the ReLU masks)
     float pre = 0.f;                      // density logit + 1 (hf == 0)
     // ---- input: features 16 hf .. 16 hf + 15 of this row -> A columns [8 hf, 8 hf + 8) (+ X tile) -------------
     {
-      uint32_t x[8];
-      const uint4* src = reinterpret_cast<const uint4*>(feat + row * 32 + 16 * hf);
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const uint4 u = valid ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
-        x[4 * q] = u.x; x[4 * q + 1] = u.y; x[4 * q + 2] = u.z; x[4 * q + 3] = u.w;
-        if (WGRAD) *tile_chunk(smem + kOffX, kSboX, r, 2 * hf + q) = u;
+      const uint32_t x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      if (WGRAD) {
+        *tile_chunk(smem + kOffX, kSboX, r, 2 * hf) = x0;
+        *tile_chunk(smem + kOffX, kSboX, r, 2 * hf + 1) = x1;
       }
       tmem_st8(lane_addr + kColA + 8 * hf, x);
       if (WGRAD && hf == 0) {
         store_ones(smem + kOffX, kSboX, r, 4);
         s_ray[r] = ray;
       }
+      if (WGRAD && tid >= 128 && tid < 137) s_ray[tid] = tid == 136 ? 0 : -1;  // slot rays := none, bad flag := 0
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 32, true>(tmem, sB, kOffB0, kOffBb0)))
+    // next tile's inputs: in flight during this whole tile
+    xn0 = xn1 = make_uint4(0u, 0u, 0u, 0u);
+    rayn = -1;
+    if (nrow < n) {
+      if (kRegAhead) {
+        const uint4* src = reinterpret_cast<const uint4*>(feat + nrow * 32 + 16 * hf);
+        xn0 = __ldg(src);
+        xn1 = __ldg(src + 1);
+        rayn = __ldg(ray_id + nrow);
+      } else {
+        prefetch_l2(feat + nrow * 32 + 16 * hf);
+        if ((lane & 7) == 0) prefetch_l2(ray_id + nrow);
+      }
+      if (BWD && (lane & 7) == 0) {  // its upstream gradients towards L2
+        if (hf == 0) prefetch_l2(d_rgb + 3 * nrow);
+        else prefetch_l2(d_sigma + nrow);
+      }
+    }
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 32, true>(tmem, sBe, kOffB0, kOffBb0)))
     GF_TC_WAIT()
     // ---- h1 = relu(acc) ----------------------------------------------------------------------------------
     {
@@ -269,10 +383,30 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       tmem_st16(lane_addr + kColA + 16 * hf, h1p);
       if (WGRAD) {
         store_chunks<4>(smem + kOffH1, kSboH, r, 4 * hf, h1p);
-        if (hf == 0) store_ones(smem + kOffH1, kSboH, r, 8);
+        if (hf == 0) {
+          store_ones(smem + kOffH1, kSboH, r, 8);
+        } else {
+          // One-hot "ray slot" row of this sample (slot = ray - the tile's first ray; rays are non-decreasing along
+          // the samples): d ray_bias of the tile's rays is then G2^T . Ind, one more weight-gradient-shaped MMA,
+          // instead of a CUDA-core reduction over the rows.  A tile whose rays do not fit 8 slots (runs of empty or
+          // very short rays) raises the flag and takes the CUDA-core path below.
+          const unsigned slot = (unsigned)(ray - s_ray[0]);
+          uint32_t one = 0u;
+          if (valid) {
+            if (slot < 8u) {
+              one = 0x3C00u << (16 * (slot & 1));  // fp16 1.0 in the slot's half of its 32-bit word
+              if (r == 0 || s_ray[r - 1] != ray) s_ray[128 + slot] = ray;
+            } else {
+              s_ray[136] = 1;
+            }
+          }
+          const unsigned wd = slot >> 1;
+          *tile_chunk(smem + kOffInd, 128, r, 0) =
+              make_uint4(wd == 0u ? one : 0u, wd == 1u ? one : 0u, wd == 2u ? one : 0u, wd == 3u ? one : 0u);
+        }
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sB, kOffB1, kOffBb1)))
+    GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sBe, kOffB1, kOffBb1)))
     GF_TC_WAIT()
     // ---- h = acc; density = exp(h0 + 1); geo features -> A (16 fp16) ------------------------------------------
     if (hf == 0) {
@@ -287,9 +421,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       tmem_st8(lane_addr + kColA, a);
       if (WGRAD) store_chunks<2>(smem + kOffHh, kSboS, r, 0, a);
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 16, false>(tmem, sB, kOffB2, 0u)))
-    // the ray's bias row (b2 + W2[:, SH] SH(d) + W2[:, emb] emb)
-    const float* rb = ray_bias + (int64_t)(valid ? ray : 0) * kH + 32 * hf;
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 16, false>(tmem, sBe, kOffB2, 0u)))
     GF_TC_WAIT()
     // ---- h2 = relu(acc + ray_bias[ray]) ----------------------------------------------------------------------
     {
@@ -303,7 +435,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
         if (hf == 0) store_ones(smem + kOffH2, kSboH, r, 8);
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 64, true>(tmem, sB, kOffB3, kOffBb3)))
+    GF_TC_SYNC_ISSUE((issue_fwd<64, 64, true>(tmem, sBe, kOffB3, kOffBb3)))
     GF_TC_WAIT()
     // ---- h3 = relu(acc) ----------------------------------------------------------------------------------
     {
@@ -317,7 +449,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
         if (hf == 0) store_ones(smem + kOffH3, kSboH, r, 8);
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sB, kOffB4, kOffBb4)))
+    GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sBe, kOffB4, kOffBb4)))
     GF_TC_WAIT()
     if (MODE == kFwd) {
       // ---- rgb = sigmoid(acc) --------------------------------------------------------------------------------
@@ -355,9 +487,8 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       if (WGRAD) store_chunks<2>(smem + kOffGo, kSboS, r, 0, a);
     }
     // g h3 = g o . W4 ; dW4^T (+ b4 row) += H3'^T . Go
-    GF_TC_SYNC_ISSUE((issue_dgrad<64, 16>(tmem, sB + kOffB4, sbo_of(64)),
-                      WGRAD ? issue_wgrad<128, 16>(tmem + kColW4, sB + kOffH3, kSboH, sB + kOffGo, kSboS, first_tile)
-                            : (void)0))
+    GF_TC_SYNC_ISSUE2((issue_dgrad<64, 16>(tmem, sBe, kOffB4, sbo_of(64))),
+                      (issue_wgrad<128, 16>(tmem + kColW4, sBe, kOffH3, kSboH, kOffGo, kSboS, first_tile)))
     GF_TC_WAIT()
     {
       uint32_t v[32], g[16];
@@ -365,12 +496,12 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       tmem_wait_ld();
       mask_pack32(v, h3p, g);
       tmem_st16(lane_addr + kColA + 16 * hf, g);
+      GF_TC_WAIT_W()
       if (WGRAD) store_chunks<4>(smem + kOffH3, kSboG, r, 4 * hf, g);  // G3 over H3 (its readers have completed)
     }
     // g h2 = g h3 . W3 ; dW3 (+ b3 column) += G3^T . H2'
-    GF_TC_SYNC_ISSUE((issue_dgrad<64, 64>(tmem, sB + kOffB3, sbo_of(64)),
-                      WGRAD ? issue_wgrad<64, 72>(tmem + kColW3, sB + kOffH3, kSboG, sB + kOffH2, kSboH, first_tile)
-                            : (void)0))
+    GF_TC_SYNC_ISSUE2((issue_dgrad<64, 64>(tmem, sBe, kOffB3, sbo_of(64))),
+                      (issue_wgrad<64, 72>(tmem + kColW3, sBe, kOffH3, kSboG, kOffH2, kSboH, first_tile)))
     GF_TC_WAIT()
     {
       uint32_t v[32], g[16];
@@ -378,13 +509,16 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       tmem_wait_ld();
       mask_pack32(v, h2p, g);
       tmem_st16(lane_addr + kColA + 16 * hf, g);
+      GF_TC_WAIT_W()
       if (WGRAD) store_chunks<4>(smem + kOffH2, kSboG, r, 4 * hf, g);  // G2 over H2
     }
     // g h[1:16] = g h2 . W2[:, geo] ; dW2[:, geo] += G2^T . Hh
-    GF_TC_SYNC_ISSUE((issue_dgrad<16, 64>(tmem, sB + kOffB2, sbo_of(16)),
-                      WGRAD ? issue_wgrad<64, 16>(tmem + kColW2, sB + kOffH2, kSboG, sB + kOffHh, kSboS, first_tile)
-                            : (void)0))
-    if (WGRAD) {
+    // (+ per-slot column sums of g h2 into the free accumulator columns 16..23: S[64 x 8] = G2^T . Ind)
+    GF_TC_SYNC_ISSUE2((issue_dgrad<16, 64>(tmem, sBe, kOffB2, sbo_of(16)),
+                       WGRAD ? issue_wgrad<64, 8>(tmem + kColD + 16, sBe, kOffH2, kSboG, kOffInd, 128, true) : (void)0),
+                      (issue_wgrad<64, 16>(tmem + kColW2, sBe, kOffH2, kSboG, kOffHh, kSboS, first_tile)))
+    const bool slots_ok = WGRAD && s_ray[136] == 0;
+    if (WGRAD && !slots_ok) {
       // d ray_bias[ray] += column sums of g h2 over the rows of that ray (rows of a ray are contiguous), from the
       // G2 tile the MMAs are reading too.  Warp w sums rows 16 w .. 16 w + 15: lane = (row group of 4, chunk of 8
       // columns); 4 rows in fp16 pairs, then across the row groups with shuffles, fp32 from there.
@@ -451,6 +585,21 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       }
     }
     GF_TC_WAIT()
+    if (slots_ok && hf == 1) {
+      // d ray_bias[ray of slot s][o] += S[o][s]; M = 64 accumulator: row o = 16 (warp & 3) + lane, lane < 16
+      uint32_t sv[8];
+      tmem_ld8(lane_addr + kColD + 16, sv);
+      tmem_wait_ld();
+      if (lane < 16) {
+        const int o = 16 * (warp & 3) + lane;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int rr = s_ray[128 + q];
+          const float f = __uint_as_float(sv[q]);
+          if (rr >= 0 && f != 0.f) atomicAdd(d_ray_bias + (int64_t)rr * kH + o, f * inv_gscale);
+        }
+      }
+    }
     // ---- g h = [ d sigma * exp(clamp(h0 + 1)) | acc[1:16] ] ---------------------------------------------------
     if (hf == 0) {
       uint32_t v[16], a[8];
@@ -462,12 +611,12 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
 #pragma unroll
       for (int j = 1; j < 8; j++) a[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
       tmem_st8(lane_addr + kColA, a);
-      if (WGRAD) store_chunks<2>(smem + kOffGo, kSboS, r, 0, a);  // Gh over Go
+      if (WGRAD) store_chunks<2>(smem + kOffGo, kSboS, r, 0, a);  // Gh over Go (read by round 1's dW4 only)
     }
+    GF_TC_WAIT_W()   // dW2's MMAs; every thread waits every phase of bar_w (the parity is tracked per thread)
     // g h1 = g h . W1 ; dW1^T (+ b1 row) += H1'^T . Gh
-    GF_TC_SYNC_ISSUE((issue_dgrad<64, 16>(tmem, sB + kOffB1, sbo_of(64)),
-                      WGRAD ? issue_wgrad<128, 16>(tmem + kColW1, sB + kOffH1, kSboH, sB + kOffGo, kSboS, first_tile)
-                            : (void)0))
+    GF_TC_SYNC_ISSUE2((issue_dgrad<64, 16>(tmem, sBe, kOffB1, sbo_of(64))),
+                      (issue_wgrad<128, 16>(tmem + kColW1, sBe, kOffH1, kSboH, kOffGo, kSboS, first_tile)))
     GF_TC_WAIT()
     {
       uint32_t v[32], g[16];
@@ -475,12 +624,12 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       tmem_wait_ld();
       mask_pack32(v, h1p, g);
       tmem_st16(lane_addr + kColA + 16 * hf, g);
+      GF_TC_WAIT_W()
       if (WGRAD) store_chunks<4>(smem + kOffH1, kSboG, r, 4 * hf, g);  // G1 over H1
     }
     // g x = g h1 . W0 ; dW0 (+ b0 column) += G1^T . X'
-    GF_TC_SYNC_ISSUE((issue_dgrad<32, 64>(tmem, sB + kOffB0, sbo_of(32)),
-                      WGRAD ? issue_wgrad<64, 40>(tmem + kColW0, sB + kOffH1, kSboG, sB + kOffX, kSboX, first_tile)
-                            : (void)0))
+    GF_TC_SYNC_ISSUE2((issue_dgrad<32, 64>(tmem, sBe, kOffB0, sbo_of(32))),
+                      (issue_wgrad<64, 40>(tmem + kColW0, sBe, kOffH1, kSboG, kOffX, kSboX, first_tile)))
     GF_TC_WAIT()
     // ---- d feat, handed to the hash backward as fp16(g * 128) (Hash3DAnchored_cuda.cu:209) ---------------------
     {
@@ -498,6 +647,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
                               pack_h2(__uint_as_float(v[8 * q + 6]) * sc, __uint_as_float(v[8 * q + 7]) * sc));
       }
     }
+    GF_TC_WAIT_W()   // dW0's MMAs read the X and G1 tiles the next tile overwrites (and the flush reads the sums)
     tc_fence_before();
     first_tile = false;
   }
@@ -582,10 +732,18 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
   if (warp == 0) tmem_dealloc(tmem, kCols);
 }
 #undef GF_TC_SYNC_ISSUE
+#undef GF_TC_SYNC_ISSUE2
 #undef GF_TC_WAIT
+#undef GF_TC_WAIT_W
 
 }  // namespace tc
 }  // namespace gf
+
+#ifdef GF_MLP_TRACE
+extern "C" int gf_debug_mlp_trace(unsigned long long* host128) {
+  return cudaMemcpyFromSymbol(host128, gf::tc::g_mlp_trace, sizeof(unsigned long long) * 128) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 using namespace gf;
 

@@ -28,6 +28,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 // ---- fences ------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -52,6 +55,30 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
+// The same descriptor from the pre-encoded 16-byte-unit base of the CTA's shared memory window plus a byte offset:
+// for compile-time offsets the low word is ONE add on the issuing thread (the MMA issue sequence is serial in a
+// single thread, so every instruction in it is on the critical path of the layer)
+__device__ __forceinline__ uint32_t smem_base_enc(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
+__device__ __forceinline__ uint64_t smem_desc_at(uint32_t base_enc, uint32_t byte_off, uint32_t lbo_bytes,
+                                                 uint32_t sbo_bytes) {
+  const uint32_t lo = base_enc + ((byte_off >> 4) | ((lbo_bytes >> 4) << 16));
+  const uint32_t hi = (sbo_bytes >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
+// one lane of a fully converged warp (cute::elect_one_sync): lets ptxas emit the tcgen05 instructions without the
+// per-lane serialisation loop it wraps around them under a thread-id test
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Instruction descriptor for kind::f16, fp16 A/B, fp32 accumulate (cute::UMMA::InstrDescriptor):
 // c_format F32 = 1 @4, a/b_format F16 = 0 @7/@10, a/b major @15/@16 (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t instr_desc(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {

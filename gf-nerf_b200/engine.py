@@ -26,6 +26,7 @@ from .hash_3d_anchored import Hash3DAnchoredCore
 from .perssampler import CompactSamples, PersSamplerCore
 
 HIDDEN = 64
+GRAD_SCALE = 128.0   # GF_GRAD_SCALE, field/Hash3DAnchored_cuda.cu:209
 APPEARANCE_DIM = 32
 
 
@@ -47,12 +48,20 @@ def init_mlp_params(hidden: int = HIDDEN, generator: torch.Generator = None, dev
 class _Adam:
     """State of gf_adam_step for one flat fp32 tensor."""
 
-    def __init__(self, param: torch.Tensor, lr: float, eps: float = 1e-15, betas=(0.9, 0.999), grad=None):
+    def __init__(self, param: torch.Tensor, lr: float, eps: float = 1e-15, betas=(0.9, 0.999), grad=None,
+                 grad_scale: float = 1.0):
         self.param, self.lr, self.eps, self.betas = param, lr, eps, betas
+        # `grad` holds grad_scale x the gradient (a power of two: the hash tables stay at the reference's x128 scale,
+        # Hash3DAnchored_cuda.cu:209, and the division rides along with the optimizer's 1 / world)
+        self.grad_scale = float(grad_scale)
         self.grad = torch.zeros_like(param) if grad is None else grad
         self.m = torch.zeros_like(param)
         self.v = torch.zeros_like(param)
         self.t = 0
+
+    def unscaled_grad(self) -> torch.Tensor:
+        """The gradient in units of dL/dparam (a copy when grad_scale != 1; exact, the scale is a power of two)."""
+        return self.grad if self.grad_scale == 1.0 else self.grad / self.grad_scale
 
     def step(self, shadow=None, grad_div=1.0, lr=None, skip_flag=None):
         """skip_flag: device int32 set by gf_grad_nan_scan -- non-zero leaves the parameters untouched (the trainer's
@@ -61,7 +70,7 @@ class _Adam:
         _lib.check(_lib.lib().gf_adam_step_guarded(
             self.param.numel(), _lib.ptr(self.param), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
             _lib.ptr(shadow), float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.t,
-            float(grad_div), 1, _lib.ptr(skip_flag), _lib.cur_stream()), "gf_adam_step_guarded")
+            float(grad_div) * self.grad_scale, 1, _lib.ptr(skip_flag), _lib.cur_stream()), "gf_adam_step_guarded")
 
 
 @dataclass
@@ -99,7 +108,7 @@ class GFNeRFEngine:
         self.mlp = init_mlp_params(hidden, gen, self.device)
         self.emb = (torch.randn(num_images, APPEARANCE_DIM, generator=gen).to(self.device)
                     if use_appearance_embedding else None)
-        self.opt_table = _Adam(self.enc.feat_pool_.detach().view(-1), lr_table)
+        self.opt_table = _Adam(self.enc.feat_pool_.detach().view(-1), lr_table, grad_scale=GRAD_SCALE)
         # MLP + embedding gradients live in one flat bucket: one collective for both
         small = FlatBucket([self.mlp.shape] + ([self.emb.shape] if self.emb is not None else []), device=self.device)
         self.opt_mlp = _Adam(self.mlp, lr_mlp, grad=small.views[0])
@@ -129,7 +138,7 @@ class GFNeRFEngine:
         self.res.feat_pool_.requires_grad_(False)
         self.res.Zero()
         self.res.shadow(force=True)
-        self.opt_res = _Adam(self.res.feat_pool_.detach().view(-1), lr)   # sub-encoder lr, gfnerf/nerfacto.py:483
+        self.opt_res = _Adam(self.res.feat_pool_.detach().view(-1), lr, grad_scale=GRAD_SCALE)   # sub-encoder lr, gfnerf/nerfacto.py:483
         self.stage = "block_stage"
         self.sampler.UpdateMode(1)                                        # nerfacto.py:614-616
 
@@ -256,14 +265,48 @@ class GFNeRFEngine:
             rgb[a:b], depth[a:b], acc[a:b] = out.rgb, out.depth, out.accumulation
         return rgb, depth, acc
 
+    # ---- sampling one batch ahead ----------------------------------------------------------------------------
+    def _presample(self, rays_o, rays_d):
+        """Launches the ray sampling of the NEXT batch on a side stream, ordered after everything issued so far on the
+        current stream (in particular this step's octree vote, the only thing the sampler depends on).  The sampler
+        is a latency-bound kernel that leaves most issue slots of an SM idle; the backward kernels of the current
+        batch run underneath it.  Results are identical to sampling at the start of the next step."""
+        if not hasattr(self, "_pre_stream"):
+            self._pre_stream = torch.cuda.Stream(device=self.device)
+            self._pre = None
+            self._cs_slot = 0
+        cur = torch.cuda.current_stream(self.device)
+        slot = self._cs_slot ^ 1
+        self._pre_stream.wait_stream(cur)
+        hook, self.sampler.stage_hook = getattr(self.sampler, "stage_hook", None), None   # events are per stream
+        with torch.cuda.stream(self._pre_stream):
+            cs = self.sampler.sample_compact(rays_o, rays_d, slot=slot)
+            done = self._pre_stream.record_event()
+        self.sampler.stage_hook = hook
+        self._pre = (rays_o.data_ptr(), rays_d.data_ptr(), tuple(rays_o.shape), cs, done, slot)
+
+    def _take_presampled(self, rays_o, rays_d):
+        pre, self._pre = getattr(self, "_pre", None), None
+        if pre is None:
+            return None
+        torch.cuda.current_stream(self.device).wait_event(pre[4])    # also orders the workspace reuse
+        if pre[:3] != (rays_o.data_ptr(), rays_d.data_ptr(), tuple(rays_o.shape)):
+            return None                                              # another batch came: sample it now
+        self._cs_slot = pre[5]
+        return pre[3]
+
     @torch.no_grad()
     def train_step(self, rays_o, rays_d, target_rgb, rel_camera_indices=None, noise=None, lr_scale: float = 1.0,
-                   update_octree: bool = True, optimizer_step: bool = True) -> StepOutputs:
+                   update_octree: bool = True, optimizer_step: bool = True, next_rays=None) -> StepOutputs:
+        """next_rays = (rays_o, rays_d) of the batch the NEXT call will be given: their sampling is started as soon
+        as this step's octree vote has been issued and overlaps this step's backward pass (`_presample`)."""
         L = _lib.lib()
         with torch.cuda.device(self.device):
             st = _lib.cur_stream()
             step = self.step_count
-            cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise)
+            cs = self._take_presampled(rays_o, rays_d) if noise is None else None
+            if cs is None:
+                cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise, slot=getattr(self, "_cs_slot", 0))
             self.flush()   # a deferred optimizer step of the previous iteration lands here
             cap, R = cs.pts01.shape[0], cs.n_rays
             ray_emb = self._ray_emb(rel_camera_indices)
@@ -290,6 +333,9 @@ class GFNeRFEngine:
                 with self._stage("octree_vote"):
                     self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
                     self.sampler.UpdateRayMarch(step)
+            presample_late = next_rays is not None and getattr(self, "presample_after_mlp", True)
+            if next_rays is not None and not presample_late:
+                self._presample(next_rays[0], next_rays[1])
             # backward
             d_sigma = self._buf("d_sigma", (cap,), torch.float32)
             d_rgb = self._buf("d_rgb", (cap, 3), torch.float32)
@@ -307,10 +353,14 @@ class GFNeRFEngine:
                                              _lib.ptr(d_rgb), _lib.ptr(d_feat),
                                              None if block else _lib.ptr(self.opt_mlp.grad),
                                              _lib.ptr(d_ray_bias), grad_scale, st), "gf_mlp_backward")
+            if presample_late:
+                # issued behind the MLP backward: that kernel is resident first (2 CTAs / SM, tensor pipe + epilogue,
+                # ~25 % of the issue slots) and the sampler's CTAs fill the registers it leaves free
+                self._presample(next_rays[0], next_rays[1])
             if block:
                 with self._stage("hash_bwd"):
                     self.res.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_res.grad.view(-1, 2),
-                                             d_n_ptr=cs.total)
+                                             d_n_ptr=cs.total, keep_x128=True)
                 if optimizer_step:
                     with self._stage("adam_table"):
                         self.opt_res.step(shadow=self.res._shadow, lr=self.opt_res.lr * lr_scale,
@@ -329,7 +379,7 @@ class GFNeRFEngine:
                                                                               d_ray_emb)
                 with self._stage("hash_bwd"):
                     self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_table.grad.view(-1, 2),
-                                             d_n_ptr=cs.total)
+                                             d_n_ptr=cs.total, keep_x128=True)
                 if optimizer_step:
                     self._reduce_and_step(lr_scale)
             self.step_count += 1
@@ -337,39 +387,57 @@ class GFNeRFEngine:
 
     # ---- host-buffer entry point ------------------------------------------------------------------------------
     @torch.no_grad()
-    def train_step_host(self, rays_o, rays_d, target_rgb, rel_camera_indices=None, **kw) -> StepOutputs:
+    def train_step_host(self, rays_o, rays_d, target_rgb, rel_camera_indices=None, next_rays=None, **kw) -> StepOutputs:
         """`train_step` for HOST tensors (pinned for true asynchrony), the call a data loader makes: the batch goes
         host -> device on a copy stream into one of two staging slots, so the copy of batch k + 1 overlaps the
         compute of batch k; the step's loss comes back device -> host asynchronously into a pinned ring
         (`read_losses()`), so the host never blocks inside the training loop (the reference blocks five times per
-        step on .item())."""
+        step on .item()).  next_rays = the NEXT call's (rays_o, rays_d) host tensors: they are
+        staged now and sampled underneath this step's backward pass (`train_step(next_rays=...)`)."""
         dev = self.device
         if not hasattr(self, "_h2d"):
             self._h2d = dict(stream=torch.cuda.Stream(device=dev), slot=0, free=[None, None], bufs=[{}, {}],
-                             losses=[], pinned=[])
+                             losses=[], pinned=[], staged_rays=[None, None])
         h = self._h2d
         slot = h["slot"]
         h["slot"] ^= 1
         cur = torch.cuda.current_stream(dev)
+
+        def stage(slot_, name, src):
+            buf = h["bufs"][slot_].get(name)
+            if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+                buf = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                h["bufs"][slot_][name] = buf
+            buf.copy_(src, non_blocking=True)
+            return buf
+
         names = ("o", "d", "t", "c")
         host = (rays_o, rays_d, target_rgb, rel_camera_indices)
+        # rays already staged by the previous call's next_rays?
+        pre = h["staged_rays"][slot]
+        have_rays = pre is not None and pre == (rays_o.data_ptr(), rays_d.data_ptr(), tuple(rays_o.shape))
+        h["staged_rays"][slot] = None
         staged = []
         with torch.cuda.stream(h["stream"]):
-            if h["free"][slot] is not None:                      # the step that last read this slot has finished
+            if h["free"][slot] is not None and not have_rays:    # the step that last read this slot has finished
                 h["stream"].wait_event(h["free"][slot])
             for name, src in zip(names, host):
                 if src is None:
                     staged.append(None)
-                    continue
-                buf = h["bufs"][slot].get(name)
-                if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
-                    buf = torch.empty(src.shape, dtype=src.dtype, device=dev)
-                    h["bufs"][slot][name] = buf
-                buf.copy_(src, non_blocking=True)
-                staged.append(buf)
+                elif have_rays and name in ("o", "d"):
+                    staged.append(h["bufs"][slot][name])
+                else:
+                    staged.append(stage(slot, name, src))
+            nxt = None
+            if next_rays is not None:
+                nslot = slot ^ 1
+                if h["free"][nslot] is not None:
+                    h["stream"].wait_event(h["free"][nslot])
+                nxt = (stage(nslot, "o", next_rays[0]), stage(nslot, "d", next_rays[1]))
+                h["staged_rays"][nslot] = (next_rays[0].data_ptr(), next_rays[1].data_ptr(), tuple(next_rays[0].shape))
             ready = h["stream"].record_event()
         cur.wait_event(ready)
-        out = self.train_step(staged[0], staged[1], staged[2], staged[3], **kw)
+        out = self.train_step(staged[0], staged[1], staged[2], staged[3], next_rays=nxt, **kw)
         h["free"][slot] = cur.record_event()
         k = len(h["losses"])
         if k >= len(h["pinned"]):

@@ -172,12 +172,15 @@ class Hash3DAnchoredCore:
                 _lib.ptr(self.level_scales_), _lib.ptr(points), _lib.ptr(anchors), int(anchors.dtype == torch.int64),
                 _lib.ptr(base_f16), _lib.ptr(out_f16), _lib.cur_stream()), "gf_hash_forward_residual")
 
-    def launch_backward(self, points, anchors, grad_in, grad_is_scaled_f16, grad_table, d_n_ptr=None):
+    def launch_backward(self, points, anchors, grad_in, grad_is_scaled_f16, grad_table, d_n_ptr=None,
+                        keep_x128=False):
+        """keep_x128: leave grad_table at the reference's x128 gradient scale (Hash3DAnchored_cuda.cu:209) for a
+        caller that divides in its optimizer step (the fused engine: `_Adam.grad_scale`)."""
         with torch.cuda.device(points.device):
             _lib.check(_lib.lib().gf_hash_backward(
                 points.shape[0], _lib.ptr(d_n_ptr), self.n_volumes_, self.local_size_, _lib.ptr(self.prim_pool_),
                 _lib.ptr(self._bias()), _lib.ptr(self.level_scales_), _lib.ptr(points), _lib.ptr(anchors),
-                int(anchors.dtype == torch.int64), _lib.ptr(grad_in), int(bool(grad_is_scaled_f16)),
+                int(anchors.dtype == torch.int64), _lib.ptr(grad_in), int(bool(grad_is_scaled_f16)) | (2 if keep_x128 else 0),
                 _lib.ptr(grad_table), _lib.cur_stream()), "gf_hash_backward")
 
     # ---- reference method surface (bindings.cpp:300-357) ----------------

@@ -166,24 +166,30 @@ class PersSamplerCore:
             self._pending_n_oct = None
 
     # ---- compact API (fused engine) -------------------------------------------------------
-    def sample_compact(self, rays_o_raw, rays_d_raw, noise: torch.Tensor = None, want_n_oct=False) -> CompactSamples:
+    def sample_compact(self, rays_o_raw, rays_d_raw, noise: torch.Tensor = None, want_n_oct=False,
+                       slot: int = 0) -> CompactSamples:
+        """`slot` selects one of several independent output workspaces, so that the samples of batch k + 1 can be
+        produced (on another stream) while batch k's are still being read by its backward pass."""
         _lib.require_cuda(rays_o_raw, rays_d_raw)
         rays_o, rays_d = self._normalise(rays_o_raw, rays_d_raw)
         R, S = rays_o.shape[0], MAX_SAMPLE_PER_RAY
         cap = max(R * S, 1)
         if noise is None:
             noise = self._noise(R)
-        packed = self._buf("packed", (cap, 8), torch.float32)
-        counts = self._buf("counts", (R,), torch.int32)
-        offsets = self._buf("offsets", (R + 1,), torch.int32)
-        total = self._buf("total", (1,), torch.int32)
-        first = self._buf("first", (R,), torch.float32)
-        n_oct = self._buf("n_oct", (R,), torch.int32) if want_n_oct else None
+        sfx = "@%d" % slot if slot else ""
+        packed = self._buf("packed", (cap, 8), torch.float32)      # consumed by gf_sampler_compact right below
+        counts = self._buf("counts" + sfx, (R,), torch.int32)
+        offsets = self._buf("offsets" + sfx, (R + 1,), torch.int32)
+        total = self._buf("total" + sfx, (1,), torch.int32)
+        first = self._buf("first" + sfx, (R,), torch.float32)
+        n_oct = self._buf("n_oct" + sfx, (R,), torch.int32) if want_n_oct else None
         cs = CompactSamples(
             n_rays=R, counts=counts, offsets=offsets, total=total,
-            pts01=self._buf("pts01", (cap, 3), torch.float32), anchor=self._buf("anchor", (cap,), torch.int32),
-            node=self._buf("node", (cap,), torch.int32), t=self._buf("t", (cap,), torch.float32),
-            delta=self._buf("delta", (cap,), torch.float32), ray_id=self._buf("ray_id", (cap,), torch.int32),
+            pts01=self._buf("pts01" + sfx, (cap, 3), torch.float32),
+            anchor=self._buf("anchor" + sfx, (cap,), torch.int32),
+            node=self._buf("node" + sfx, (cap,), torch.int32), t=self._buf("t" + sfx, (cap,), torch.float32),
+            delta=self._buf("delta" + sfx, (cap,), torch.float32),
+            ray_id=self._buf("ray_id" + sfx, (cap,), torch.int32),
             first_oct_dis=first, rays_d_unit=rays_d)
         if R == 0:
             offsets.zero_()
@@ -254,13 +260,25 @@ class PersSamplerCore:
 
     def ProcOctree(self, compact: bool, subdivide: bool, brute_force: bool):
         """PersOctree::ProcOctree (PersSampler.cpp:154-417): D2H of the node blob + stats, host compaction /
-        subdivision, H2D -- same round trip as the reference."""
+        subdivision in C++ (gf_octree_proc, csrc/octree_host.cu), H2D -- the same round trip as the reference."""
+        import ctypes as C
+        nodes = self.tree_nodes_gpu_.cpu().contiguous()
+        w = self.tree_weight_stats_.cpu().contiguous()
+        a = self.tree_alpha_stats_.cpu().contiguous()
+        v = self.tree_visit_cnt_.cpu().contiguous()
+        n_in, n_out, L = nodes.numel() // 128, C.c_int64(0), _lib.lib()
+        args = (_lib.ptr(nodes), n_in, _lib.ptr(w), _lib.ptr(a), _lib.ptr(v), int(compact), int(subdivide),
+                int(brute_force))
+        _lib.check(L.gf_octree_proc(*args, None, None, None, 0, C.byref(n_out)), "gf_octree_proc")
+        n = int(n_out.value)
+        nodes_o = torch.empty(n * 128, dtype=torch.uint8)
+        w_o, a_o = torch.empty(n, dtype=torch.int64), torch.empty(n, dtype=torch.int64)
+        _lib.check(L.gf_octree_proc(*args, _lib.ptr(nodes_o), _lib.ptr(w_o), _lib.ptr(a_o), n, C.byref(n_out)),
+                   "gf_octree_proc")
         oc = self.octree
-        oc.load_blobs(self.tree_nodes_gpu_.cpu().numpy(), self.pers_trans_gpu_.cpu().numpy())
-        oc.weight_stats = self.tree_weight_stats_.cpu().numpy()
-        oc.alpha_stats = self.tree_alpha_stats_.cpu().numpy()
-        oc.visit_cnt = self.tree_visit_cnt_.cpu().numpy()
-        oc.proc_octree(compact, subdivide, brute_force)
+        oc.load_blobs(nodes_o.numpy(), self.pers_trans_gpu_.cpu().numpy())
+        oc.weight_stats, oc.alpha_stats = w_o.numpy(), a_o.numpy()
+        oc.visit_cnt = np.zeros(n, np.int64)
         self._upload_octree(stats=True)
 
     def MarkInvisibleNodes(self):

@@ -92,7 +92,10 @@ int gf_hash_forward_residual(int64_t n, const int32_t* d_n_ptr, int32_t n_volume
  * applies the reference's x128 -> fp16 quantisation (:209) -- or __half [n,32]
  * already scaled by 128 (grad_in_is_scaled_f16=1, produced by gf_mlp_backward).
  * grad_table: float [n_levels*local_size, 2]; ACCUMULATED into (caller zeroes it),
- * in units of dL/dfeat (the /128 of :238 is applied per contribution). */
+ * in units of dL/dfeat (the /128 of :238 is applied per contribution).
+ * grad_in_is_scaled_f16 is a bit set: bit 0 as above; bit 1 (value 2) leaves the table at
+ * the x128 scale -- a caller that folds the division into its optimizer step
+ * (gf_adam_step's grad_div) saves two multiplies per corner; exact, 128 is a power of two. */
 int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
                      const int32_t* prim_pool, const float* bias_pool, const float* level_scales,
                      const float* pts, const void* anchors, int anchor_i64,
@@ -176,6 +179,19 @@ int gf_sampler_vote(int64_t n_rays, const int32_t* counts, const int32_t* offset
                     int64_t* scratch, void* stream);
 int gf_sampler_apply_votes(void* tree_nodes, int64_t n_nodes, int64_t* weight_stats, int64_t* alpha_stats,
                            const int64_t* scratch, void* stream);
+
+/* PersOctree::ProcOctree (PtsSampler/PersSampler.cpp:154-417) -- HOST code, like the reference's (which copies the
+ * node blob to the CPU, rebuilds it and uploads it again): all pointers are host pointers, no stream.
+ * compact: drop leaves with trans_idx < 0 from their parents, turn childless interior nodes into leaves (repeat),
+ * splice out single-child chains, keep interior nodes and valid leaves in their old order.  subdivide: depth-first
+ * renumbering in which every leaf with visit_cnt > 4 (or every leaf, brute_force) becomes an interior node followed
+ * by its eight new leaf children (same trans_idx, statistics inherited, the parent's reset to 1000).
+ * nodes_in: n_in TreeNode blobs (128 B each, PersSampler.h:31-40); *_stats_in / visit_cnt_in: int64 [n_in].
+ * nodes_out == NULL: size query, only *n_out is written.  Otherwise `capacity` nodes of room in nodes_out /
+ * weight_stats_out / alpha_stats_out (int64); visit counts restart at 0 in the reference, so none are returned. */
+int gf_octree_proc(const void* nodes_in, int64_t n_in, const int64_t* weight_stats_in, const int64_t* alpha_stats_in,
+                   const int64_t* visit_cnt_in, int compact, int subdivide, int brute_force, void* nodes_out,
+                   int64_t* weight_stats_out, int64_t* alpha_stats_out, int64_t capacity, int64_t* n_out);
 
 /* QueryFrameTransform for arbitrary points (TransQueryFrameKernel, :854-922) */
 int gf_sampler_trans_query_frame(int64_t n_pts, const void* tree_nodes, int64_t n_nodes,

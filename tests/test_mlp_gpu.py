@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 H = 64
 
 
-def make_case(n, R, seed, with_emb=True):
+def make_case(n, R, seed, with_emb=True, ray_stride=1):
+    """ray_stride > 1 leaves ray ids without samples in between (rays that missed the octree)"""
     rng = np.random.RandomState(seed)
     g = torch.Generator().manual_seed(seed)
     from gfnerf_b200.engine import init_mlp_params
@@ -20,7 +21,8 @@ def make_case(n, R, seed, with_emb=True):
     # exercised in a non-trivial range (post-training features are O(0.1 - 1))
     feat = (rng.normal(0, 0.5, size=(n, 32))).astype(np.float16)
     cuts = np.sort(rng.choice(np.arange(1, n), size=R - 1, replace=False)) if R > 1 else np.array([], int)
-    ray_id = np.searchsorted(cuts, np.arange(n), side="right").astype(np.int32)
+    ray_id = (np.searchsorted(cuts, np.arange(n), side="right") * ray_stride).astype(np.int32)
+    R = (R - 1) * ray_stride + 1
     dirs = rng.normal(size=(R, 3))
     dirs = (dirs / np.linalg.norm(dirs, axis=-1, keepdims=True)).astype(np.float32)
     emb = rng.normal(size=(R, 32)).astype(np.float32) if with_emb else None
@@ -122,11 +124,17 @@ def test_device_side_count_limits_work():
     assert torch.equal(c2[:613], rgb[:613]) and not c2[613:].any()
 
 
-@pytest.mark.parametrize("n,R,seed,with_emb", [(6000, 41, 5, True), (130, 3, 6, False), (129, 1, 7, True)])
-def test_backward_matches_oracle(n, R, seed, with_emb):
+# the per-ray gradient of the head's first-layer bias leaves a 128-sample tile through 8 "ray slots" (an MMA against a
+# one-hot matrix) when the tile's ray ids span < 8, else through a CUDA-core reduction: long rays, rays with gaps in
+# their ids (stride 2: slots 0, 2, 4, 6; stride 3: mixed), many short rays (every tile overflows the slots)
+@pytest.mark.parametrize("n,R,seed,with_emb,stride", [(6000, 41, 5, True, 1), (130, 3, 6, False, 1), (129, 1, 7, True, 1),
+                                                      (6000, 41, 5, True, 2), (6000, 60, 5, True, 3),
+                                                      (6000, 800, 5, True, 1)])
+def test_backward_matches_oracle(n, R, seed, with_emb, stride):
     from gfnerf_b200 import _lib
     L, st = _lib.lib(), _lib.cur_stream()
-    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb)
+    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb, stride)
+    R = dirs.shape[0]
     (tp, tf, tr, td, te, rb), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb)
     rng = np.random.RandomState(seed + 100)
     d_sigma = (rng.normal(size=n) * 1e-4).astype(np.float32)

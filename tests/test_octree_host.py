@@ -1,0 +1,82 @@
+"""gf_octree_proc (C++, csrc/octree_host.cu = PersOctree::ProcOctree, PtsSampler/PersSampler.cpp:154-417) against the
+numpy restatement `PersOctree.proc_octree` on the same blobs: byte-identical node blobs and statistics.  Host code,
+runs without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.helpers import load_rig
+
+
+def _octree(rig):
+    from gfnerf_b200.persoctree import PersOctree
+    oc = PersOctree.__new__(PersOctree)
+    oc.load_blobs(rig["tree_nodes"], rig["pers_trans"])
+    n = oc.nodes.shape[0]
+    oc.weight_stats = np.full(n, 1000, np.int64)
+    oc.alpha_stats = np.full(n, 1000, np.int64)
+    oc.visit_cnt = np.zeros(n, np.int64)
+    return oc
+
+
+def _cxx(oc, compact, subdivide, brute_force):
+    from gfnerf_b200 import _lib
+    L = _lib.lib()
+    nodes = np.ascontiguousarray(oc.nodes).view(np.uint8).reshape(-1).copy()
+    w, a, v = (np.ascontiguousarray(x, np.int64) for x in (oc.weight_stats, oc.alpha_stats, oc.visit_cnt))
+    n_out = C.c_int64(0)
+    args = (nodes.ctypes.data, nodes.size // 128, w.ctypes.data, a.ctypes.data, v.ctypes.data, int(compact),
+            int(subdivide), int(brute_force))
+    _lib.check(L.gf_octree_proc(*args, None, None, None, 0, C.byref(n_out)))
+    n = n_out.value
+    o_nodes, o_w, o_a = np.empty(n * 128, np.uint8), np.empty(n, np.int64), np.empty(n, np.int64)
+    _lib.check(L.gf_octree_proc(*args, o_nodes.ctypes.data, o_w.ctypes.data, o_a.ctypes.data, n, C.byref(n_out)))
+    return o_nodes, o_w, o_a
+
+
+@pytest.mark.parametrize("compact,subdivide,brute", [(True, False, False), (True, True, False), (True, True, True),
+                                                      (False, True, False), (False, False, False)])
+def test_matches_numpy_restatement(compact, subdivide, brute):
+    rig = load_rig("rig8")
+    rng = np.random.RandomState(5)
+    for trial in range(3):
+        oc = _octree(rig)
+        n = oc.nodes.shape[0]
+        # a training history: some leaves voted empty (pruned by MarkInvalidNodes), random statistics, visit counts
+        leaves = np.nonzero(oc.nodes["trans_idx"] >= 0)[0]
+        dead = rng.choice(leaves, size=int(len(leaves) * (0.2 + 0.3 * trial)), replace=False)
+        oc.nodes["trans_idx"][dead] = -1
+        oc.weight_stats = rng.randint(-100, 5000, size=n).astype(np.int64)
+        oc.alpha_stats = rng.randint(-100, 5000, size=n).astype(np.int64)
+        oc.visit_cnt = rng.randint(0, 12, size=n).astype(np.int64)
+        got_nodes, got_w, got_a = _cxx(oc, compact, subdivide, brute)
+        oc.proc_octree(compact, subdivide, brute)
+        ref_nodes = np.ascontiguousarray(oc.nodes).view(np.uint8).reshape(-1)
+        assert got_nodes.size == ref_nodes.size
+        assert np.array_equal(got_nodes, ref_nodes)
+        assert np.array_equal(got_w, oc.weight_stats) and np.array_equal(got_a, oc.alpha_stats)
+        # structure: parent / child links are mutual, every leaf that survived is valid after a compaction
+        nodes = got_nodes.view(oc.nodes.dtype)
+        for u in range(nodes.shape[0]):
+            for c in nodes["childs"][u]:
+                if c >= 0:
+                    assert nodes["parent"][c] == u
+        if compact and not subdivide:
+            assert ((nodes["is_leaf_node"] == 0) | (nodes["trans_idx"] >= 0)).all()
+
+
+def test_errors():
+    from gfnerf_b200 import _lib
+    L = _lib.lib()
+    n_out = C.c_int64(0)
+    assert L.gf_octree_proc(None, 0, None, None, None, 1, 0, 0, None, None, None, 0, C.byref(n_out)) != 0
+    assert b"gf_octree_proc" in L.gf_last_error()
+    rig = load_rig("rig8")
+    oc = _octree(rig)
+    nodes = np.ascontiguousarray(oc.nodes).view(np.uint8).reshape(-1).copy()
+    w = np.full(oc.nodes.shape[0], 1000, np.int64)
+    out = np.empty(128, np.uint8)
+    rc = L.gf_octree_proc(nodes.ctypes.data, nodes.size // 128, w.ctypes.data, w.ctypes.data, w.ctypes.data, 1, 1, 1,
+                          out.ctypes.data, w.ctypes.data, w.ctypes.data, 1, C.byref(n_out))
+    assert rc != 0 and b"capacity" in L.gf_last_error()

@@ -69,7 +69,7 @@ def test_operator_path_equals_fused_engine():
     assert abs(float(loss) - float(out.loss)) < 1e-4 * float(out.loss)
     f = model.field
     g_table = f.base_encoding_init.hash_3d.feat_pool_.grad
-    ref = eng.opt_table.grad.view_as(g_table)
+    ref = eng.opt_table.unscaled_grad().view_as(g_table)
     assert float((g_table - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
     got = torch.cat([torch.cat([l.weight.grad.reshape(-1), l.bias.grad.reshape(-1)])
                      for l in f.base_network.linears() + f.mlp_head.linears()])
@@ -137,7 +137,7 @@ def test_engine_block_stage_equals_operator_api_block_stage():
     diff = res["rgb"] - target
     (torch.sqrt(diff * diff + 1e-12).sum() / R).backward()
     g = f.base_encoding_0.hash_3d.feat_pool_.grad
-    ref = eng.opt_res.grad.view_as(g)
+    ref = eng.opt_res.unscaled_grad().view_as(g)
     assert float(ref.abs().max()) > 0
     assert float((g - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
     assert not eng.opt_table.grad.any() and not eng.opt_mlp.grad.any()      # frozen: nothing accumulated
