@@ -16,6 +16,7 @@ buffers ~1 GB) is several times the 126 MB L2, and a pool of distinct ray batche
 is needed between iterations ("inputs larger than L2").
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -389,8 +390,9 @@ def main():
         kernels.append(ent)
     # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01c_traffic.json")
-    if os.path.exists(tp):
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))     # the latest round's capture
+    tp = tps[-1] if tps else ""
+    if tp:
         with open(tp) as f:
             traffic = {k: v["dram_bytes_per_launch"] for k, v in json.load(f)["kernels"].items()}
     for k in kernels:

@@ -36,6 +36,9 @@ _SIGS = {
     "gf_sampler_update_oct_nodes": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "gf_sampler_vote": [_i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "gf_sampler_apply_votes": [_vp, _i64, _vp, _vp, _vp, _vp],
+    "gf_octree_build": [_i64, _f32, _f32, _vp, _vp, _vp, _i64, C.c_uint32, _i64, _i64, _vp, _vp, _vp],
+    "gf_octree_build_fetch": [_vp, _vp, _vp],
+    "gf_octree_search_order": [_vp],
     "gf_octree_proc": [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _i64, _vp],
     "gf_sampler_trans_query_frame": [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "gf_composite_forward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

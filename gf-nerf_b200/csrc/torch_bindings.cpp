@@ -9,10 +9,10 @@
 //  * Hash3DAnchored: the complete surface (ctor, AnchoredQuery with autograd, GetParams, States, LoadStates, Reset,
 //    Zero, SetFeatPoolRequireGrad, to, ReleaseResources), state tensors and their order as in
 //    field/Hash3DAnchored.cpp:17-200.
-//  * PersSampler: the per-step surface (GetSamples, UpdateOctNodes' vote, UpdateRayMarch, UpdateMode, States,
-//    LoadStates, trans_query_frame, the getters).  The octree is built / compacted / subdivided on the host in
-//    gfnerf_b200.persoctree (numpy, as the reference does it on the host in PersSampler.cpp:92-895); it enters here
-//    through LoadStates (the reference's own checkpoint blobs), so InitSampler / ProcOctree are not duplicated in C++.
+//  * PersSampler: InitSampler (octree + leaf transforms built on the host by gf_octree_build, as the reference builds
+//    them on the host in PersSampler.cpp:92-152, 516-831), GetSamples, UpdateOctNodes (vote, statistics, pruning and
+//    the milestone / compact_freq ProcOctree through gf_octree_proc), UpdateRayMarch, UpdateMode, States, LoadStates,
+//    trans_query_frame, the getters.
 #include <torch/custom_class.h>
 #include <torch/script.h>
 #include <torch/cuda.h>
@@ -165,7 +165,9 @@ Tensor Hash3DAnchoredImpl::AnchoredQuery(const Tensor& points, const Tensor& anc
 
 // ---------------------------------------------------------------------------------------------------------------
 struct PersSamplerImpl : torch::CustomClassHolder {
-  Tensor tree_nodes_, pers_trans_, visit_cnt_, weight_stats_, alpha_stats_, search_order_, milestones_;
+  Tensor tree_nodes_, pers_trans_, visit_cnt_, weight_stats_, alpha_stats_, search_order_;
+  Tensor w2c_, intri_, bound_;               // cameras, for MarkInvisibleNodes at the subdivision milestones
+  std::vector<int64_t> sub_div_milestones_;  // reversed: the next milestone is at the back
   double global_near_ = 0.01, sample_l_ = 1.0 / 256, fineness_ = 1.0, init_fineness_ = 16.0, decay_end_ = 10000.0;
   double sampled_oct_per_ray_ = 512.0;
   int64_t mode_ = 0, max_oct_ = 1024, compact_freq_ = 1000;
@@ -176,12 +178,36 @@ struct PersSamplerImpl : torch::CustomClassHolder {
   int64_t n_nodes() const { return tree_nodes_.numel() / GF_TREE_NODE_BYTES; }
   int64_t n_trans() const { return pers_trans_.numel() / GF_TRANS_INFO_BYTES; }
 
-  void InitSampler(double, std::vector<int64_t>, int64_t, int64_t, double, bool, int64_t, double, int64_t, Tensor,
-                   Tensor, Tensor, Tensor, int64_t, int64_t, double, double, int64_t) {
-    TORCH_CHECK(false,
-                "gfnerf_b200: the octree is built on the host by gfnerf_b200.persoctree.PersOctree (as the reference "
-                "builds it on the host, PersSampler.cpp:92-895); hand its blobs to this class with Configure + "
-                "LoadStates, or use gfnerf_b200.perssampler.PersSamplerCore.InitSampler");
+  // PersSampler::PersSampler + PersOctree::PersOctree (PersSampler.cpp:899-952, 92-152): the octree and the leaf
+  // transforms are built on the host by gf_octree_build (csrc/octree_build.cu), as the reference builds them on the host
+  void InitSampler(double split_dist_thres, std::vector<int64_t> sub_div_milestones, int64_t compact_freq,
+                   int64_t max_oct_intersect_per_ray, double global_near, bool scale_by_dis, int64_t bbox_levels,
+                   double sample_l, int64_t max_level, Tensor c2w, Tensor w2c, Tensor intri, Tensor bounds, int64_t mode,
+                   int64_t sampled_oct_per_ray, double ray_march_fineness, double ray_march_init_fineness,
+                   int64_t ray_march_fineness_decay_end_iter) {
+    TORCH_CHECK(torch::cuda::is_available(), "PersSampler needs a CUDA device: the B200 kernels have no CPU fallback");
+    Configure(compact_freq, max_oct_intersect_per_ray, global_near, scale_by_dis, sample_l, mode, ray_march_fineness,
+              ray_march_init_fineness, ray_march_fineness_decay_end_iter);
+    sampled_oct_per_ray_ = (double)sampled_oct_per_ray;
+    sub_div_milestones_.assign(sub_div_milestones.rbegin(), sub_div_milestones.rend());  // popped from the back
+    auto f32c = torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCPU);
+    auto c2w_h = c2w.detach().to(f32c).contiguous(), intri_h = intri.detach().to(f32c).contiguous(),
+         bounds_h = bounds.detach().to(f32c).contiguous();
+    TORCH_CHECK(c2w_h.dim() == 3 && c2w_h.size(1) == 3 && c2w_h.size(2) == 4, "c2w: f32 [n,3,4]");
+    TORCH_CHECK(intri_h.dim() == 3 && intri_h.size(0) == c2w_h.size(0) && bounds_h.size(0) == c2w_h.size(0),
+                "intri: f32 [n,3,3], bounds: f32 [n,2]");
+    w2c_ = w2c.detach().to(torch::kFloat32).to(torch::kCUDA).contiguous();
+    intri_ = intri_h.to(torch::kCUDA);
+    bound_ = bounds_h.to(torch::kCUDA);
+    void* handle = nullptr;
+    int64_t n_nodes = 0, n_trans = 0;
+    GF_CHECK(gf_octree_build(max_level, (float)(int64_t(1) << (bbox_levels - 1)), (float)split_dist_thres,
+                             c2w_h.data_ptr<float>(), intri_h.data_ptr<float>(), bounds_h.data_ptr<float>(),
+                             c2w_h.size(0), /*seed=*/0u, 32 * 32 * 32, 128, &handle, &n_nodes, &n_trans));
+    auto nodes = torch::empty({n_nodes * GF_TREE_NODE_BYTES}, torch::kUInt8);
+    auto trans = torch::empty({n_trans * GF_TRANS_INFO_BYTES}, torch::kUInt8);
+    GF_CHECK(gf_octree_build_fetch(handle, nodes.data_ptr(), trans.data_ptr()));
+    LoadStates({nodes, trans, torch::zeros({n_nodes}, torch::kInt64), torch::tensor(sub_div_milestones_, torch::kInt64)}, 0);
   }
   // the scalar arguments of InitSampler (PersSampler.cpp:899-952) without the cameras
   void Configure(int64_t compact_freq, int64_t max_oct_intersect_per_ray, double global_near, bool scale_by_dis,
@@ -198,25 +224,20 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     decay_end_ = (double)ray_march_fineness_decay_end_iter;
   }
 
-  std::vector<Tensor> States() { return {tree_nodes_, pers_trans_, visit_cnt_, milestones_}; }
+  std::vector<Tensor> States() {  // PersSampler.cpp:969-979: the milestones still ahead, next one last
+    return {tree_nodes_, pers_trans_, visit_cnt_, torch::tensor(sub_div_milestones_, torch::kInt64).to(torch::kCUDA)};
+  }
   int64_t LoadStates(const std::vector<Tensor>& states, int64_t idx) {  // PersSampler.cpp:983-1016
     tree_nodes_ = states[idx++].clone().to(torch::kCUDA).contiguous();
     pers_trans_ = states[idx++].clone().to(torch::kCUDA).contiguous();
     visit_cnt_ = states[idx++].clone().to(torch::kCUDA).contiguous();
-    milestones_ = states[idx++].clone();
+    auto ms = states[idx++].to(torch::kCPU).to(torch::kInt64).contiguous();
+    sub_div_milestones_.assign(ms.data_ptr<int64_t>(), ms.data_ptr<int64_t>() + ms.numel());
     auto i64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA);
     weight_stats_ = torch::full({n_nodes()}, 1000, i64);  // INIT_NODE_STAT
     alpha_stats_ = torch::full({n_nodes()}, 1000, i64);
-    // search order of the children per ray octant (PersSampler.cpp:137-151): descending bitrev3(child ^ octant)
-    auto so = torch::empty({64}, torch::kUInt8);
-    uint8_t* o = so.data_ptr<uint8_t>();
-    auto bitrev3 = [](int v) { return ((v & 1) << 2) | (v & 2) | ((v >> 2) & 1); };
-    for (int st = 0; st < 8; st++) {
-      int idx8[8];
-      for (int i = 0; i < 8; i++) idx8[i] = i;
-      std::stable_sort(idx8, idx8 + 8, [&](int a, int b) { return bitrev3(a ^ st) > bitrev3(b ^ st); });
-      for (int i = 0; i < 8; i++) o[st * 8 + i] = (uint8_t)idx8[i];
-    }
+    auto so = torch::empty({64}, torch::kUInt8);  // children front to back per ray octant (PersSampler.cpp:137-151)
+    GF_CHECK(gf_octree_search_order(so.data_ptr<uint8_t>()));
     search_order_ = so.to(torch::kCUDA);
     return idx;
   }
@@ -262,7 +283,7 @@ struct PersSamplerImpl : torch::CustomClassHolder {
   // the per-step part of PersSampler::UpdateOctNodes (PersSampler_cuda.cu:584-655): votes, stat update, pruning.
   // ProcOctree at the milestones / every compact_freq steps is host work (gfnerf_b200.persoctree.PersOctree.proc_octree).
   void UpdateOctNodes(const Tensor& sampled_anchors, const Tensor& pts_idx_bounds, const Tensor& sampled_weight,
-                      const Tensor& sampled_alpha, int64_t /*iter_step*/) {
+                      const Tensor& sampled_alpha, int64_t iter_step) {
     c10::cuda::CUDAGuard guard(sampled_weight.device());
     const int64_t R = sampled_weight.size(0), S = GF_MAX_SAMPLE_PER_RAY;
     auto se = pts_idx_bounds.select(1, 0);  // [R,2]
@@ -277,6 +298,56 @@ struct PersSamplerImpl : torch::CustomClassHolder {
                                          tree_nodes_.data_ptr(), n_nodes(), weight_stats_.data_ptr<int64_t>(),
                                          alpha_stats_.data_ptr<int64_t>(), visit_cnt_.data_ptr<int64_t>(),
                                          scratch.data_ptr<int64_t>(), stream()));
+    // :657-677 subdivision at the milestones, compaction every compact_freq steps
+    while (!sub_div_milestones_.empty() && sub_div_milestones_.back() <= iter_step) {
+      ProcOctree(true, true, sub_div_milestones_.back() <= 0);
+      MarkInvisibleNodes();
+      ProcOctree(true, false, false);
+      sub_div_milestones_.pop_back();
+    }
+    if (compact_freq_ > 0 && iter_step % compact_freq_ == 0) ProcOctree(true, false, false);
+  }
+
+  // PersOctree::ProcOctree (PersSampler.cpp:154-417): node blob + statistics to the host, gf_octree_proc, back
+  void ProcOctree(bool compact, bool subdivide, bool brute_force) {
+    auto nodes = tree_nodes_.cpu().contiguous();
+    auto w = weight_stats_.cpu().contiguous(), a = alpha_stats_.cpu().contiguous(), v = visit_cnt_.cpu().contiguous();
+    int64_t n_out = 0;
+    GF_CHECK(gf_octree_proc(nodes.data_ptr(), n_nodes(), w.data_ptr<int64_t>(), a.data_ptr<int64_t>(),
+                            v.data_ptr<int64_t>(), compact, subdivide, brute_force, nullptr, nullptr, nullptr, 0, &n_out));
+    auto nodes_o = torch::empty({n_out * GF_TREE_NODE_BYTES}, torch::kUInt8);
+    auto w_o = torch::empty({n_out}, torch::kInt64), a_o = torch::empty({n_out}, torch::kInt64);
+    GF_CHECK(gf_octree_proc(nodes.data_ptr(), n_nodes(), w.data_ptr<int64_t>(), a.data_ptr<int64_t>(),
+                            v.data_ptr<int64_t>(), compact, subdivide, brute_force, nodes_o.data_ptr(),
+                            w_o.data_ptr<int64_t>(), a_o.data_ptr<int64_t>(), n_out, &n_out));
+    tree_nodes_ = nodes_o.to(torch::kCUDA);
+    weight_stats_ = w_o.to(torch::kCUDA);
+    alpha_stats_ = a_o.to(torch::kCUDA);
+    visit_cnt_ = torch::zeros({n_out}, visit_cnt_.options());
+  }
+
+  // MarkInvisibleNodesKernel + CheckVisible (PersSampler_cuda.cu:680-742): a node no camera can see loses its
+  // transform.  Cold (subdivision milestones only): a handful of torch ops over [n_nodes, n_cams].
+  void MarkInvisibleNodes() {
+    if (!w2c_.defined()) return;  // state loaded without cameras
+    auto nodes = tree_nodes_.view({-1, GF_TREE_NODE_BYTES});
+    auto cs = nodes.slice(1, 0, 16).contiguous().view(torch::kFloat32);  // center xyz, side_len
+    auto center = cs.slice(1, 0, 3), side = cs.select(1, 3);
+    auto cam = torch::einsum("cij,nj->nci", {w2c_.slice(2, 0, 3), center}) + w2c_.select(2, 3).unsqueeze(0);
+    auto radius = (side * 0.707f).unsqueeze(1);
+    auto z = -cam.select(2, 2);
+    auto out_z = (z < bound_.select(1, 0).unsqueeze(0) - radius) | (z > bound_.select(1, 1).unsqueeze(0) + radius);
+    auto inside = torch::linalg_norm(cam, 2, {-1}, false) < radius;
+    auto cx = intri_.select(1, 0).select(1, 2).unsqueeze(0), cy = intri_.select(1, 1).select(1, 2).unsqueeze(0);
+    auto fx = intri_.select(1, 0).select(1, 0).unsqueeze(0), fy = intri_.select(1, 1).select(1, 1).unsqueeze(0);
+    auto bx = radius / z * fx, by = radius / z * fy;
+    auto ix = cam.select(2, 0) / z * fx, iy = cam.select(2, 1) / z * fy;
+    auto out_img = (ix + bx < -cx) | (ix > cx + bx) | (iy + by < -cy) | (iy > cy + by);
+    auto visible = (~out_z) & (inside | ~out_img);
+    auto invisible = visible.sum(-1) < 1;
+    auto tidx = nodes.slice(1, 96, 104).contiguous().view(torch::kInt64).view({-1});
+    tidx.masked_fill_(invisible, -1);
+    nodes.slice(1, 96, 104).copy_(tidx.view({-1, 1}).view(torch::kUInt8));
   }
 
   void UpdateRayMarch(int64_t cur_step) {  // PersSampler.cpp:958-967 (fp32 arithmetic)
@@ -331,6 +402,8 @@ TORCH_LIBRARY(my_classes, m) {  // same names as gfnerf/bindings/hashanchored/bi
       .def("Configure", &PersSamplerImpl::Configure)
       .def("GetSamples", &PersSamplerImpl::GetSamples)
       .def("UpdateOctNodes", &PersSamplerImpl::UpdateOctNodes)
+      .def("ProcOctree", &PersSamplerImpl::ProcOctree)
+      .def("MarkInvisibleNodes", &PersSamplerImpl::MarkInvisibleNodes)
       .def("UpdateRayMarch", &PersSamplerImpl::UpdateRayMarch)
       .def("UpdateMode", &PersSamplerImpl::UpdateMode)
       .def("States", &PersSamplerImpl::States)

@@ -42,6 +42,40 @@ class CompactSamples:
     rays_d_unit: torch.Tensor   # f32 [R,3]
 
 
+def build_octree(max_depth: int, bbox_side_len: float, split_dist_thres: float, c2w, intri, bounds, seed: int = 0,
+                 n_rand_pts: int = 32 * 32 * 32, visi_res_w: int = 128) -> PersOctree:
+    """PersOctree::PersOctree (PersSampler.cpp:92-152) through the C++ host builder gf_octree_build
+    (csrc/octree_build.cu); returns the blobs wrapped in a `PersOctree` (whose numpy constructor is the independent
+    restatement the builder is tested against)."""
+    import ctypes as C
+    c2w = np.ascontiguousarray(c2w, np.float32)
+    intri = np.ascontiguousarray(intri, np.float32)
+    bounds = np.ascontiguousarray(bounds, np.float32)
+    if c2w.ndim != 3 or c2w.shape[1:] != (3, 4) or intri.shape != (c2w.shape[0], 3, 3) or bounds.shape != (c2w.shape[0], 2):
+        raise RuntimeError("build_octree: c2w f32 [n,3,4], intri f32 [n,3,3], bounds f32 [n,2]")
+    L = _lib.lib()
+    handle, n_nodes, n_trans = C.c_void_p(), C.c_int64(), C.c_int64()
+    _lib.check(L.gf_octree_build(int(max_depth), float(bbox_side_len), float(split_dist_thres), c2w.ctypes.data,
+                                 intri.ctypes.data, bounds.ctypes.data, c2w.shape[0], int(seed) & 0xffffffff,
+                                 int(n_rand_pts), int(visi_res_w), C.byref(handle), C.byref(n_nodes), C.byref(n_trans)),
+               "gf_octree_build")
+    nodes = np.empty(n_nodes.value * 128, np.uint8)
+    trans = np.empty(n_trans.value * 576, np.uint8)
+    _lib.check(L.gf_octree_build_fetch(handle, nodes.ctypes.data, trans.ctypes.data), "gf_octree_build_fetch")
+    oc = PersOctree.__new__(PersOctree)
+    oc.max_depth, oc.bbox_side_len, oc.split_dist_thres = int(max_depth), float(bbox_side_len), float(split_dist_thres)
+    oc.c2w, oc.intri, oc.bound = c2w, intri, bounds
+    oc.load_blobs(nodes, trans)
+    n = oc.nodes.shape[0]
+    oc.weight_stats = np.full(n, INIT_NODE_STAT, np.int64)
+    oc.alpha_stats = np.full(n, INIT_NODE_STAT, np.int64)
+    oc.visit_cnt = np.zeros(n, np.int64)
+    so = np.zeros(64, np.uint8)
+    _lib.check(L.gf_octree_search_order(so.ctypes.data), "gf_octree_search_order")
+    oc.search_order = so
+    return oc
+
+
 class PersSamplerCore:
     def __init__(self):
         self.octree: Optional[PersOctree] = None
@@ -70,8 +104,8 @@ class PersSamplerCore:
         self.intri_ = torch.as_tensor(to_np(intri), dtype=torch.float32).to(self.device).contiguous()
         self.bound_ = torch.as_tensor(to_np(bounds), dtype=torch.float32).to(self.device).contiguous()
         if octree is None:
-            octree = PersOctree(int(max_level), float(1 << (int(bbox_levels) - 1)), float(np.float32(split_dist_thres)),
-                                to_np(c2w), to_np(intri), to_np(bounds), seed=seed)
+            octree = build_octree(int(max_level), float(1 << (int(bbox_levels) - 1)), float(np.float32(split_dist_thres)),
+                                  to_np(c2w), to_np(intri), to_np(bounds), seed=seed)
         self.octree = octree
         self.n_volumes_ = int(octree.trans.shape[0])
         self._upload_octree(stats=True)

@@ -180,6 +180,20 @@ int gf_sampler_vote(int64_t n_rays, const int32_t* counts, const int32_t* offset
 int gf_sampler_apply_votes(void* tree_nodes, int64_t n_nodes, int64_t* weight_stats, int64_t* alpha_stats,
                            const int64_t* scratch, void* stream);
 
+/* PersOctree::PersOctree / ConstructTreeNode / GetVisiCams / DistanceSummary / ConstructTrans
+ * (PtsSampler/PersSampler.cpp:12-26, 45-152, 516-831) -- HOST code, as in the reference: builds the octree over the
+ * camera rig (c2w f32 [n,3,4], intri f32 [n,3,3], bound f32 [n,2] = near, far; host pointers) down to max_depth, with
+ * the perspective-warp transform of every valid leaf.  bbox_side_len = 2^(bbox_levels - 1); n_rand_pts sample points
+ * per leaf for the PCA (reference: 32^3); visi_res_w = width of the visibility pixel grid (reference: 128).
+ * The result stays behind *handle; *n_nodes / *n_trans give the blob sizes (128 B / 576 B each, PersSampler.h:31-49).
+ * gf_octree_build_fetch copies the blobs out (either pointer may be NULL) and frees the handle. */
+int gf_octree_build(int64_t max_depth, float bbox_side_len, float split_dist_thres, const float* c2w, const float* intri,
+                    const float* bound, int64_t n_cams, uint32_t seed, int64_t n_rand_pts, int64_t visi_res_w,
+                    void** handle, int64_t* n_nodes, int64_t* n_trans);
+int gf_octree_build_fetch(void* handle, void* tree_nodes_out, void* pers_trans_out);
+/* uint8 [64]: children in front-to-back order for each of the 8 ray octants (PersSampler.cpp:137-151) */
+int gf_octree_search_order(uint8_t* out64);
+
 /* PersOctree::ProcOctree (PtsSampler/PersSampler.cpp:154-417) -- HOST code, like the reference's (which copies the
  * node blob to the CPU, rebuilds it and uploads it again): all pointers are host pointers, no stream.
  * compact: drop leaves with trans_idx < 0 from their parents, turn childless interior nodes into leaves (repeat),

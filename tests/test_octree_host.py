@@ -80,3 +80,30 @@ def test_errors():
     rc = L.gf_octree_proc(nodes.ctypes.data, nodes.size // 128, w.ctypes.data, w.ctypes.data, w.ctypes.data, 1, 1, 1,
                           out.ctypes.data, w.ctypes.data, w.ctypes.data, 1, C.byref(n_out))
     assert rc != 0 and b"capacity" in L.gf_last_error()
+
+
+def test_builder_reproduces_the_fixture():
+    """gf_octree_build (C++, csrc/octree_build.cu = PersOctree::PersOctree + ConstructTreeNode + ConstructTrans,
+    PersSampler.cpp:92-152, 516-831) on the 64-camera rig against the committed fixture, which the numpy restatement
+    `PersOctree(...)` built from the same cameras and the same (replayed) random draws: the node blob byte for byte,
+    the leaf transforms to fp32 rounding -- PCA components up to their sign, which an eigen-decomposition leaves open."""
+    from gfnerf_b200.persoctree import TRANS_INFO_DTYPE, aerial_rig, search_order_table
+    from gfnerf_b200.perssampler import build_octree
+    rig = load_rig("rig8")
+    c2w, intri, bounds = aerial_rig(n_side=int(rig["n_side"]), extent=float(rig["extent"]), seed=1)
+    assert np.array_equal(c2w, rig["c2w"])
+    oc = build_octree(16, 512.0, 1.5, c2w, intri, bounds, seed=0)
+    assert np.array_equal(oc.tree_nodes_blob(), rig["tree_nodes"])
+    assert np.array_equal(oc.search_order, search_order_table())
+    got, ref = oc.trans, rig["pers_trans"].view(TRANS_INFO_DTYPE)
+    assert got.shape == ref.shape
+    assert np.allclose(got["w2xz"], ref["w2xz"], rtol=1e-4, atol=1e-4 * np.abs(ref["w2xz"]).max())
+    assert np.array_equal(got["center"], ref["center"]) and np.array_equal(got["side_len"], ref["side_len"])
+    assert np.allclose(got["dis_summary"], ref["dis_summary"], rtol=1e-4)
+    sign = np.sign((got["weight"] * ref["weight"]).sum(-1, keepdims=True))
+    assert (sign != 0).all()
+    err = np.abs(got["weight"] * sign - ref["weight"]).max(-1) / np.abs(ref["weight"]).max(-1)
+    assert err.max() < 1e-3
+    # errors
+    with pytest.raises(RuntimeError):
+        build_octree(16, 512.0, 1.5, c2w[:, :2], intri, bounds)

@@ -36,9 +36,8 @@ def test_library_registers_the_reference_class_names():
     assert abs(s.get_ray_march_fineness_() - 16.0) < 1e-5
     s.UpdateRayMarch(10000)
     assert s.get_ray_march_fineness_() == 1.0
-    with pytest.raises(RuntimeError, match="persoctree"):
-        s.InitSampler(1.5, [2000], 1000, 1024, 0.01, True, 10, 1.0 / 256, 16, torch.zeros(1, 3, 4), torch.zeros(1, 3, 4),
-                      torch.zeros(1, 3, 3), torch.zeros(1, 2), 0, 512, 1.0, 16.0, 10000)
+    for name in ("ProcOctree", "MarkInvisibleNodes"):
+        assert hasattr(s, name), name
     assert hasattr(mc, "Hash3DAnchored")
 
 
@@ -98,3 +97,45 @@ def test_perssampler_class_equals_python_core():
     wp = torch.rand(50, 3).cuda()
     nodes = a[5][0, :50, 1].contiguous()
     assert torch.equal(cc.trans_query_frame(wp, nodes), py.TransQueryFrame(wp, nodes))
+
+
+@pytest.mark.gpu
+def test_init_sampler_builds_the_fixture_octree_and_maintains_it():
+    """InitSampler with the reference's argument list (gfnerf/perssampler.py:103-123): the octree comes from the C++
+    host builder; then a vote with a subdivision milestone due (UpdateOctNodes -> ProcOctree / MarkInvisibleNodes)
+    against the Python host layer fed with the same blobs."""
+    from gfnerf_b200.persoctree import rig_rays
+    from tests.helpers import load_rig, make_sampler
+    mc = load()
+    rig = load_rig("rig8")
+    c2w = torch.from_numpy(rig["c2w"])
+    w2c4 = torch.eye(4).repeat(c2w.shape[0], 1, 1)
+    w2c4[:, :3, :] = c2w
+    w2c = torch.linalg.inv(w2c4)[:, :3, :].contiguous()
+    cc = mc.PersSampler()
+    cc.InitSampler(1.5, [3, 4000], 1000, 1024, 0.01, True, 10, 1.0 / 256, 16, c2w, w2c, torch.from_numpy(rig["intri"]),
+                   torch.from_numpy(rig["bounds"]), 1, 512, 1.0, 16.0, 10000)
+    st = cc.States()
+    assert torch.equal(st[0].cpu(), torch.from_numpy(rig["tree_nodes"]))          # node blob: the fixture, byte for byte
+    assert st[1].numel() == rig["pers_trans"].size and st[3].cpu().tolist() == [4000, 3]
+    # same blobs into the Python layer; one vote at step 3 = first milestone: subdivide, prune invisible, compact
+    py = make_sampler(rig, mode=1)
+    py.LoadStates([s.clone() for s in st], 0)
+    assert py.sub_div_milestones_ == [4000, 3]
+    o, d, _ = rig_rays(rig["c2w"], rig["intri"], 400, seed=3)
+    to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    bounds = torch.zeros(400, 2).cuda()
+    a, b = cc.GetSamples(to, td, bounds), py.GetSamples(to, td, bounds)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    w = torch.rand(400, 1024, 1, generator=torch.Generator().manual_seed(1)).cuda() * (a[3] > 0).unsqueeze(-1)
+    se = a[6].unsqueeze(1).expand(-1, 1024, -1).contiguous()
+    cc.UpdateOctNodes(a[5], se, w, w, 3)
+    py.UpdateOctNodes(a[5], se, w, w, 3)
+    sc, sp = cc.States(), py.States()
+    assert sc[0].numel() > st[0].numel()                                            # leaves were split
+    assert torch.equal(sc[0], sp[0]) and torch.equal(sc[2], sp[2])
+    assert sc[3].cpu().tolist() == [4000] == sp[3].cpu().tolist()
+    a2, b2 = cc.GetSamples(to, td, bounds), py.GetSamples(to, td, bounds)
+    for x, y in zip(a2, b2):
+        assert torch.equal(x, y)

@@ -61,5 +61,34 @@ def full(src, dst, title, cmd):
             f.write("\n")
 
 
+NAMES = [("sample_rays_kernel", "sample_rays"), ("compact_kernel", "compact"), ("hash_fwd_kernel", "hash_fwd"),
+         ("hash_bwd_kernel", "hash_bwd"), ("mlp_tc_kernel<0>", "mlp_fwd"), ("mlp_tc_kernel<2>", "mlp_bwd"),
+         ("mlp_tc_kernel<1>", "mlp_bwd_frozen"), ("composite_fwd_kernel", "composite_fwd"),
+         ("composite_bwd_kernel", "composite_bwd"), ("adam_kernel<1>", "adam_table")]
+
+
+def traffic(src, dst, title, cmd):
+    """per-kernel DRAM bytes per launch (first captured launch of each kernel) as JSON, read by bench.py"""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index('Kernel Name')
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {}
+    for r in rows[2:]:
+        for pat, key in NAMES:
+            if pat in r[ki] and key not in res:
+                tot = 0.0
+                for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                    i = hdr.index(m)
+                    tot += float(r[i].replace(',', '')) * scale[units[i]]
+                i = hdr.index('gpu__time_duration.sum')
+                t = float(r[i].replace(',', '')) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[units[i]]
+                res[key] = {"dram_bytes_per_launch": int(tot), "gpu_time_ms": t}
+    with open(dst, 'w') as f:
+        json.dump({"source": title, "command": cmd, "kernels": res}, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:6])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:6])
