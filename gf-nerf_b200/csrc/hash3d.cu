@@ -127,7 +127,7 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
                 const int32_t* __restrict__ prim_pool, const float* __restrict__ bias_pool,
                 const float* __restrict__ scales, const float* __restrict__ pts,
                 const AnchorT* __restrict__ anchors, const void* __restrict__ grad_in_v,
-                float* __restrict__ grad_table, int aggregate) {
+                float* __restrict__ grad_table, int aggregate, int level_begin, int level_end) {
   if (d_n_ptr) {
     int64_t dn = *d_n_ptr;
     n = dn < n ? dn : n;
@@ -151,7 +151,7 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
       vol = (int)anchors[i];
     }
 #pragma unroll 1
-    for (int l = 0; l < GF_N_LEVELS; l++) {
+    for (int l = level_begin; l < level_end; l++) {
       // this level's two gradients, quantised like the reference: fp16(g*128)  (:209)
       __half2 gh = __float2half2_rn(0.f);
       if (valid) {
@@ -283,9 +283,21 @@ int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64
                      const int32_t* prim_pool, const float* bias_pool, const float* level_scales,
                      const float* pts, const void* anchors, int anchor_i64, const void* grad_in,
                      int grad_in_is_scaled_f16, float* grad_table, void* stream) {
+  return gf_hash_backward_levels(n, d_n_ptr, n_volumes, local_size, prim_pool, bias_pool, level_scales, pts, anchors,
+                                 anchor_i64, grad_in, grad_in_is_scaled_f16, grad_table, 0, GF_N_LEVELS, stream);
+}
+
+int gf_hash_backward_levels(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                            const int32_t* prim_pool, const float* bias_pool, const float* level_scales,
+                            const float* pts, const void* anchors, int anchor_i64, const void* grad_in,
+                            int grad_in_is_scaled_f16, float* grad_table, int level_begin, int level_end,
+                            void* stream) {
   GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL,
              "gf_hash_backward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
              (long long)local_size);
+  GF_REQUIRE(0 <= level_begin && level_begin <= level_end && level_end <= GF_N_LEVELS,
+             "gf_hash_backward: bad level range [%d, %d)", level_begin, level_end);
+  if (level_begin == level_end) return GF_OK;
   if (n == 0) return GF_OK;
   GF_REQUIRE(prim_pool && level_scales && pts && anchors && grad_in && grad_table, "gf_hash_backward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -297,7 +309,8 @@ int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64
 #define GF_BWD(P2, AT, G16, HB, US)                                                                              \
   hash_bwd_kernel<P2, AT, G16, HB, US><<<grid, kHashBlock, 0, st>>>(n, d_n_ptr, n_volumes, (uint32_t)local_size, \
                                                                     prim_pool, bias_pool, level_scales, pts,     \
-                                                                    (const AT*)anchors, grad_in, grad_table, aggregate)
+                                                                    (const AT*)anchors, grad_in, grad_table, aggregate,  \
+                                                                    level_begin, level_end)
 #define GF_BWD_U(P2, AT, G16, HB)                  \
   do {                                             \
     if (unscale) GF_BWD(P2, AT, G16, HB, true);    \

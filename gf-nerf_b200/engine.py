@@ -85,6 +85,8 @@ class StepOutputs:
 class GFNeRFEngine:
     """Global-stage model state (hash table, MLPs, appearance embedding) + the fused step."""
 
+    LEVEL_GROUP = 4   # levels per scatter launch / all-reduce message when world > 1 (17 MB at log2T = 19)
+
     def __init__(self, sampler: PersSamplerCore, log2_table_size: int = 19, num_images: int = 1, hidden: int = HIDDEN,
                  use_appearance_embedding: bool = True, lr_table: float = 1e-2, lr_mlp: float = 1e-2,
                  seed: int = 0, dist_group=None, nan_guard: bool = True, s3im_loss_mult: float = 0.0,
@@ -266,7 +268,7 @@ class GFNeRFEngine:
         return rgb, depth, acc
 
     # ---- sampling one batch ahead ----------------------------------------------------------------------------
-    def _presample(self, rays_o, rays_d):
+    def _presample(self, rays_o, rays_d, vote=None):
         """Launches the ray sampling of the NEXT batch on a side stream, ordered after everything issued so far on the
         current stream (in particular this step's octree vote, the only thing the sampler depends on).  The sampler
         is a latency-bound kernel that leaves most issue slots of an SM idle; the backward kernels of the current
@@ -280,6 +282,12 @@ class GFNeRFEngine:
         self._pre_stream.wait_stream(cur)
         hook, self.sampler.stage_hook = getattr(self.sampler, "stage_hook", None), None   # events are per stream
         with torch.cuda.stream(self._pre_stream):
+            if vote is not None:
+                # the octree feedback of the current batch (and, data parallel, its MAX all-reduce with the rank
+                # skew it absorbs) only gates the NEXT sampling: off the stream that runs the backward pass
+                vcs, weights, alphas, step = vote
+                self.sampler.update_oct_nodes_compact(vcs, weights, alphas, step)
+                self.sampler.UpdateRayMarch(step)
             cs = self.sampler.sample_compact(rays_o, rays_d, slot=slot)
             done = self._pre_stream.record_event()
         self.sampler.stage_hook = hook
@@ -329,13 +337,17 @@ class GFNeRFEngine:
                                          patch_h, ks, stride, mult, _lib.ptr(g_rgb), _lib.ptr(loss), st), "gf_s3im")
             # training feedback (gfnerf/nerfacto.py:598-616).  It only needs the forward's weights, so it is issued
             # here: its (tiny) MAX all-reduce over ranks must not queue behind the gradient all-reduce below
+            vote = None
             if update_octree and self.stage == "init_stage":   # the octree is only updated in the init stage (:605)
-                with self._stage("octree_vote"):
-                    self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
-                    self.sampler.UpdateRayMarch(step)
+                if next_rays is not None:
+                    vote = (cs, weights, alphas, step)        # issued with the next batch's sampling, see _presample
+                else:
+                    with self._stage("octree_vote"):
+                        self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
+                        self.sampler.UpdateRayMarch(step)
             presample_late = next_rays is not None and getattr(self, "presample_after_mlp", True)
             if next_rays is not None and not presample_late:
-                self._presample(next_rays[0], next_rays[1])
+                self._presample(next_rays[0], next_rays[1], vote)
             # backward
             d_sigma = self._buf("d_sigma", (cap,), torch.float32)
             d_rgb = self._buf("d_rgb", (cap, 3), torch.float32)
@@ -356,7 +368,7 @@ class GFNeRFEngine:
             if presample_late:
                 # issued behind the MLP backward: that kernel is resident first (2 CTAs / SM, tensor pipe + epilogue,
                 # ~25 % of the issue slots) and the sampler's CTAs fill the registers it leaves free
-                self._presample(next_rays[0], next_rays[1])
+                self._presample(next_rays[0], next_rays[1], vote)
             if block:
                 with self._stage("hash_bwd"):
                     self.res.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_res.grad.view(-1, 2),
@@ -377,11 +389,26 @@ class GFNeRFEngine:
                     if d_ray_emb is not None:
                         self.opt_emb.grad.view(-1, APPEARANCE_DIM).index_add_(0, rel_camera_indices.to(torch.int64),
                                                                               d_ray_emb)
-                with self._stage("hash_bwd"):
-                    self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_table.grad.view(-1, 2),
-                                             d_n_ptr=cs.total, keep_x128=True)
-                if optimizer_step:
-                    self._reduce_and_step(lr_scale)
+                g_table = self.opt_table.grad.view(-1, 2)
+                if self.world > 1 and optimizer_step:
+                    # data parallel: the small bucket's all-reduce starts now, the table is scattered in level groups
+                    # and every group's all-reduce starts while the next group is being scattered -- only the last
+                    # group's reduce is left after the backward pass (the table is level-major: groups are contiguous)
+                    self.sync.start_sum([self._small_grads])
+                    rows = self.enc.local_size_
+                    with self._stage("hash_bwd"):
+                        for l0 in range(0, 16, self.LEVEL_GROUP):
+                            l1 = min(l0 + self.LEVEL_GROUP, 16)
+                            self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, g_table, d_n_ptr=cs.total,
+                                                     keep_x128=True, levels=(l0, l1))
+                            self.sync.start_sum([g_table[l0 * rows:l1 * rows]])
+                    self._deferred = lr_scale
+                else:
+                    with self._stage("hash_bwd"):
+                        self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, g_table, d_n_ptr=cs.total,
+                                                 keep_x128=True)
+                    if optimizer_step:
+                        self._reduce_and_step(lr_scale)
             self.step_count += 1
         return StepOutputs(out_rgb, depth, acc, loss, cs.total)
 
@@ -464,7 +491,7 @@ class GFNeRFEngine:
         With more than one rank the all-reduce is launched on the comm stream and the Adam step is DEFERRED to the
         point where the parameters are next needed (after the next batch's ray sampling, which reads neither the
         table nor the MLP), so NVLink time hides behind the sampler kernel."""
-        if self.world > 1:
+        if self.world > 1:   # (train_step pipelines this per level group; this is the one-shot form)
             self.sync.start_sum([self._small_grads, self.opt_table.grad])
             self._deferred = lr_scale
         else:
@@ -472,6 +499,9 @@ class GFNeRFEngine:
 
     def flush(self):
         """Completes a deferred optimizer step (call before reading parameters, checkpointing or timing)."""
+        pre = getattr(self, "_pre", None)
+        if pre is not None:   # an octree vote / sampling issued ahead on the side stream
+            torch.cuda.current_stream(self.device).wait_event(pre[4])
         if self._deferred is not None:
             self.sync.wait()
             self._apply_adam(self._deferred)

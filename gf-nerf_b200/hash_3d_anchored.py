@@ -173,15 +173,15 @@ class Hash3DAnchoredCore:
                 _lib.ptr(base_f16), _lib.ptr(out_f16), _lib.cur_stream()), "gf_hash_forward_residual")
 
     def launch_backward(self, points, anchors, grad_in, grad_is_scaled_f16, grad_table, d_n_ptr=None,
-                        keep_x128=False):
+                        keep_x128=False, levels=(0, 16)):
         """keep_x128: leave grad_table at the reference's x128 gradient scale (Hash3DAnchored_cuda.cu:209) for a
         caller that divides in its optimizer step (the fused engine: `_Adam.grad_scale`)."""
         with torch.cuda.device(points.device):
-            _lib.check(_lib.lib().gf_hash_backward(
+            _lib.check(_lib.lib().gf_hash_backward_levels(
                 points.shape[0], _lib.ptr(d_n_ptr), self.n_volumes_, self.local_size_, _lib.ptr(self.prim_pool_),
                 _lib.ptr(self._bias()), _lib.ptr(self.level_scales_), _lib.ptr(points), _lib.ptr(anchors),
                 int(anchors.dtype == torch.int64), _lib.ptr(grad_in), int(bool(grad_is_scaled_f16)) | (2 if keep_x128 else 0),
-                _lib.ptr(grad_table), _lib.cur_stream()), "gf_hash_backward")
+                _lib.ptr(grad_table), int(levels[0]), int(levels[1]), _lib.cur_stream()), "gf_hash_backward")
 
     # ---- reference method surface (bindings.cpp:300-357) ----------------
     def AnchoredQuery(self, points: torch.Tensor, anchors: torch.Tensor) -> torch.Tensor:

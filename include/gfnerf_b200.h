@@ -102,6 +102,15 @@ int gf_hash_backward(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64
                      const void* grad_in, int grad_in_is_scaled_f16,
                      float* grad_table, void* stream);
 
+/* The same for the levels [level_begin, level_end) only (rows level * local_size ... of grad_table): data-parallel
+ * training scatters the table gradient in level groups and starts each group's all-reduce while the next group is
+ * being scattered. */
+int gf_hash_backward_levels(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes, int64_t local_size,
+                            const int32_t* prim_pool, const float* bias_pool, const float* level_scales,
+                            const float* pts, const void* anchors, int anchor_i64,
+                            const void* grad_in, int grad_in_is_scaled_f16,
+                            float* grad_table, int level_begin, int level_end, void* stream);
+
 /* Parity probe: rows int32 [n,16,8] = table row (level offset included) of the 8 corners of
  * every (point, level), order 000,001,...,111 (:48-55).  Not on the hot path. */
 int gf_hash_corner_rows(int64_t n, int32_t n_volumes, int64_t local_size, const int32_t* prim_pool,

@@ -98,6 +98,11 @@ def test_backward_matches_oracle(n, n_vol, log2T, along):
     gt = torch.zeros_like(core.feat_pool_)
     core.launch_backward(tp, ta.to(torch.int32), g16, True, gt)
     assert np.all(np.abs(gt.double().cpu().numpy() - ref) <= 1e-5 * np.abs(ref) + 1e-6 * scale)
+    # level groups (data-parallel training scatters and all-reduces the table group by group): same table
+    gt.zero_()
+    for l0 in range(0, 16, 4):
+        core.launch_backward(tp, ta.to(torch.int32), g16, True, gt, levels=(l0, l0 + 4))
+    assert np.all(np.abs(gt.double().cpu().numpy() - ref) <= 1e-5 * np.abs(ref) + 1e-6 * scale)
     # table left at the reference's x128 scale (the fused engine folds the division into Adam): same sums, x128
     gt.zero_()
     core.launch_backward(tp, ta.to(torch.int32), g16, True, gt, keep_x128=True)
