@@ -238,11 +238,17 @@ class GFNeRFEngine:
 
     # ---- public API ------------------------------------------------------------------------
     @torch.no_grad()
-    def render(self, rays_o, rays_d, rel_camera_indices=None, noise=None) -> StepOutputs:
-        """Forward-only (eval) pass: GFNeRFModel.get_outputs without the training feedback."""
+    def render(self, rays_o, rays_d, rel_camera_indices=None, noise=None, next_rays=None) -> StepOutputs:
+        """Forward-only (eval) pass: GFNeRFModel.get_outputs without the training feedback.  next_rays: the rays of
+        the next call, sampled on the side stream underneath this call's encode / MLP / composite (`_presample`;
+        nothing changes the octree in between)."""
         with torch.cuda.device(self.device):
-            cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise)
+            cs = self._take_presampled(rays_o, rays_d) if noise is None else None
+            if cs is None:
+                cs = self.sampler.sample_compact(rays_o, rays_d, noise=noise, slot=getattr(self, "_cs_slot", 0))
             self.flush()
+            if next_rays is not None:
+                self._presample(next_rays[0], next_rays[1])
             _, sigma, rgb, _ = self._field_forward(cs, self._ray_emb(rel_camera_indices))
             out_rgb, depth, acc, _, _, _ = self._composite(cs, sigma, rgb, keep=False)
             # RGBRenderer in eval mode: nan_to_num + clamp (renderers.py:131-137)
@@ -250,7 +256,7 @@ class GFNeRFEngine:
         return StepOutputs(out_rgb, depth, acc, None, cs.total)
 
     @torch.no_grad()
-    def render_image(self, rays_o, rays_d, rel_camera_index: int = 0, chunk: int = 32768):
+    def render_image(self, rays_o, rays_d, rel_camera_index: int = 0, chunk: int = 32768, sample_ahead: bool = True):
         """Full-image render in chunks: Model.get_outputs_for_camera_ray_bundle (nerfstudio/models/base_model.py:
         166-190, eval_num_rays_per_chunk = 2048 in the reference, gfnerf/config.py:109; here the chunk is as large
         as the workspace allows and there is no host sync inside it).  Returns rgb [N,3], depth [N], acc [N]."""
@@ -263,7 +269,8 @@ class GFNeRFEngine:
             cam = torch.full((chunk,), int(rel_camera_index), dtype=torch.int64, device=self.device)
         for a in range(0, N, chunk):
             b = min(a + chunk, N)
-            out = self.render(rays_o[a:b], rays_d[a:b], None if cam is None else cam[:b - a])
+            nxt = (rays_o[b:b + chunk], rays_d[b:b + chunk]) if (b < N and sample_ahead) else None
+            out = self.render(rays_o[a:b], rays_d[a:b], None if cam is None else cam[:b - a], next_rays=nxt)
             rgb[a:b], depth[a:b], acc[a:b] = out.rgb, out.depth, out.accumulation
         return rgb, depth, acc
 

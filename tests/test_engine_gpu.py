@@ -118,6 +118,9 @@ def test_render_image_chunking_is_invisible():
     one = eng.render(to, td, cam)
     assert torch.equal(rgb, one.rgb) and torch.equal(acc, one.accumulation) and torch.equal(depth, one.depth)
     assert torch.isfinite(rgb).all() and float(rgb.min()) >= 0 and float(rgb.max()) <= 1
+    # chunk k + 1 is sampled on a side stream underneath chunk k's encode / MLP / composite: same image without it
+    rgb2, depth2, acc2 = eng.render_image(to, td, rel_camera_index=3, chunk=1000, sample_ahead=False)
+    assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2) and torch.equal(acc, acc2)
 
 
 def test_full_size_step_properties():
