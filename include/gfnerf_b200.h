@@ -329,6 +329,17 @@ int gf_adam_step_guarded(int64_t n, float* param, float* grad, float* exp_avg, f
                          void* shadow_f16, float lr, float beta1, float beta2, float eps,
                          int64_t step, float grad_div, int zero_grad, const int32_t* skip_flag, void* stream);
 
+/* ---- ray generation (the step before the path) --------
+ * Cameras.generate_rays for PERSPECTIVE cameras without distortion (nerfstudio/cameras/cameras.py:583-727, with
+ * GF-NeRF's lookat_directions :704,723): cam_idx int64 [n], coords_yx f32 [n,2] = pixel (y, x) as the pixel samplers
+ * give them (index + 0.5); c2w f32 [n_cams,3,4]; fx, fy, cx, cy f32 [n_cams].  Outputs f32: origins [n,3] = c2w[:, 3],
+ * directions [n,3] (unit), lookat [n,3] = c2w[:, 2], pixel_area [n] = dx * dy from the one-pixel-offset directions,
+ * dir_norm [n] (metadata["directions_norm"]); lookat / pixel_area / dir_norm may be NULL. */
+int gf_generate_rays(int64_t n_rays, const int64_t* cam_idx, const float* coords_yx, const float* c2w,
+                     const float* fx, const float* fy, const float* cx, const float* cy, int64_t n_cams,
+                     float* origins, float* directions, float* lookat, float* pixel_area, float* dir_norm,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -972,3 +972,50 @@ void orc_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, f
     param[i] = (float)((double)param[i] - step_size * ((double)m / denom));
   }
 }
+
+/* ---- ray generation ---------------------------------------------------------------------------
+ * Cameras.generate_rays for PERSPECTIVE cameras without distortion (reference
+ * nerfstudio/cameras/cameras.py:583-727, the path GF-NeRF's datamanager takes): per ray its camera index and pixel
+ * coordinates (y, x) -> origin c2w[:, 3], unit direction, lookat direction c2w[:, 2] (GF-NeRF's addition, :704),
+ * pixel_area = dx * dy from the two one-pixel-offset directions (:711-716), directions_norm.
+ * torch evaluates every op separately in fp32: no contraction; sums over the last dim of 3 left to right. */
+static inline float sum3(float a, float b, float c) { return (a + b) + c; }
+
+void orc_generate_rays(int64_t n_rays, const int64_t* cam_idx, const float* coords_yx, const float* c2w,
+                       const float* fx, const float* fy, const float* cx, const float* cy, float* origins,
+                       float* directions, float* lookat, float* pixel_area, float* dir_norm) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_rays; i++) {
+    const int64_t c = cam_idx[i];
+    const float y = coords_yx[2 * i], x = coords_yx[2 * i + 1];
+    const float* m = c2w + c * 12;
+    /* :606-608 image-plane coordinates of the pixel and of its +1 neighbours in x and in y */
+    const float cam[3][2] = {{(x - cx[c]) / fx[c], -(y - cy[c]) / fy[c]},
+                             {((x - cx[c]) + 1.f) / fx[c], -(y - cy[c]) / fy[c]},
+                             {(x - cx[c]) / fx[c], -((y - cy[c]) + 1.f) / fy[c]}};
+    float d[3][3];
+    for (int k = 0; k < 3; k++) {
+      /* :697-699 sum(dir[None, :] * rotation, -1), then normalize_with_norm (camera_utils.py:240-252) */
+      float w[3];
+      for (int r = 0; r < 3; r++) w[r] = sum3(cam[k][0] * m[4 * r], cam[k][1] * m[4 * r + 1], -1.f * m[4 * r + 2]);
+      /* torch.linalg.vector_norm accumulates x*x with FMAs (checked against the reference's output bit for bit) */
+      float nrm = sqrtf(fmaf(w[2], w[2], fmaf(w[1], w[1], w[0] * w[0])));
+      if (nrm < 8.8817842e-16f) nrm = 8.8817842e-16f; /* _EPS = 4 eps(float64), camera_utils.py:28 */
+      for (int r = 0; r < 3; r++) d[k][r] = w[r] / nrm;
+      if (k == 0 && dir_norm) dir_norm[i] = nrm;
+    }
+    for (int r = 0; r < 3; r++) {
+      origins[3 * i + r] = m[4 * r + 3];
+      directions[3 * i + r] = d[0][r];
+      lookat[3 * i + r] = m[4 * r + 2];
+    }
+    float ex[3], ey[3];
+    for (int r = 0; r < 3; r++) {
+      ex[r] = d[0][r] - d[1][r];
+      ey[r] = d[0][r] - d[2][r];
+    }
+    const float dx = sqrtf(sum3(ex[0] * ex[0], ex[1] * ex[1], ex[2] * ex[2]));
+    const float dy = sqrtf(sum3(ey[0] * ey[0], ey[1] * ey[1], ey[2] * ey[2]));
+    pixel_area[i] = dx * dy;
+  }
+}

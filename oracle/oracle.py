@@ -225,3 +225,19 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
     """In place on param / exp_avg / exp_avg_sq (float32, contiguous)."""
     lib().orc_adam_step(C.c_int64(param.size), _p(param), _p(_f32(grad)), _p(exp_avg), _p(exp_avg_sq),
                         C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_int64(step))
+
+
+# ---------------------------------------------------------------- ray generation
+def generate_rays(cam_idx, coords_yx, c2w, fx, fy, cx, cy):
+    """Cameras.generate_rays, perspective / no distortion (nerfstudio/cameras/cameras.py:583-727)."""
+    cam_idx = np.ascontiguousarray(cam_idx, np.int64).reshape(-1)
+    n = cam_idx.shape[0]
+    coords_yx, c2w = _f32(coords_yx).reshape(n, 2), _f32(c2w)
+    fx, fy, cx, cy = (_f32(a).reshape(-1) for a in (fx, fy, cx, cy))
+    out = {k: np.zeros((n, 3), np.float32) for k in ("origins", "directions", "lookat")}
+    out["pixel_area"] = np.zeros(n, np.float32)
+    out["dir_norm"] = np.zeros(n, np.float32)
+    lib().orc_generate_rays(C.c_int64(n), _p(cam_idx), _p(coords_yx), _p(c2w), _p(fx), _p(fy), _p(cx), _p(cy),
+                            _p(out["origins"]), _p(out["directions"]), _p(out["lookat"]), _p(out["pixel_area"]),
+                            _p(out["dir_norm"]))
+    return out
