@@ -450,6 +450,8 @@ class PersSampler(nn.Module):
         self.n_split_dataset = n_split_dataset
         self.steps_per_split_dataset = steps_per_split_dataset
         self.steps_perssampler_init = steps_perssampler_init
+        self.register_buffer("c2w", c2w.to(self.sampler.device), persistent=False)      # perssampler.py:130
+        self.cameras_labels = None    # int64 [n_cams,1] block label of every camera, set by the clustering (:236-237)
         self._register_state_dict_hook(self.state_dict_hook)
 
     def state_dict_hook(self, *args):
@@ -466,15 +468,34 @@ class PersSampler(nn.Module):
         self.sampler.LoadStates([state_dict[pre + k] for k in
                                  ("tree_nodes_gpu", "pers_trans_gpu", "tree_visit_cnt", "milestones_ts")], 0)
 
+    # ---- eval-mode block routing (perssampler.py:138-165, 244-260): the block / appearance embedding of a render
+    # chunk is the one of the training camera nearest to the chunk's first ray origin
+    def get_nearest_split_dataset(self, origin, direction=None):
+        dists = torch.linalg.norm(self.c2w[:, 0:3, -1] - origin.to(self.c2w.device), dim=1)
+        nearest_image_idx = int(torch.argmin(dists).item())
+        return int(self.cameras_labels.reshape(-1)[nearest_image_idx].item()), nearest_image_idx
+
+    def get_nearest_split_dataset_orig(self, origin):
+        n_images_per_split_dataset = self.c2w.shape[0] // self.n_split_dataset
+        dists = torch.linalg.norm(self.c2w[:, 0:3, -1] - origin.to(self.c2w.device), dim=1)
+        nearest_image_idx = int(torch.argmin(dists).item())
+        cur_split_idx = min(nearest_image_idx // max(n_images_per_split_dataset, 1), self.n_split_dataset - 1)
+        return cur_split_idx, nearest_image_idx
+
     def generate_ray_samples(self, ray_bundle):
         from .rays import Frustums, RaySamples, WarpedSamples
         rays_o, rays_d = ray_bundle.origins, ray_bundle.directions
         S = self.max_pts_per_ray
-        cur_step, cur_split_idx = -1, -1
+        cur_step, cur_split_idx, nearest_image_idx = -1, -1, None
         if ray_bundle.steps is not None:
             cur_step = int(ray_bundle.steps.reshape(-1)[0].item())
             if cur_step >= self.steps_perssampler_init:
                 cur_split_idx = ((cur_step - self.steps_perssampler_init) // self.steps_per_split_dataset) % self.n_split_dataset
+        if cur_split_idx == -1 and rays_o.shape[0] > 0:       # eval mode or init stage (:367-376)
+            if self.cameras_labels is not None:
+                cur_split_idx, nearest_image_idx = self.get_nearest_split_dataset(rays_o[0])
+            else:
+                cur_split_idx, nearest_image_idx = self.get_nearest_split_dataset_orig(rays_o[0])
         bounds = self.bounds[0, :].to(rays_o.device).repeat((rays_o.shape[0], 1))
         world, warp, dirs, dists, ts, anchors, start_end, first = self.sampler.GetSamples(rays_o, rays_d, bounds)
         f2 = WarpedSamples(sampled_world_pts=world, sampled_pts=warp, sampled_dirs=dirs, sampled_dists=dists.unsqueeze(-1),
@@ -485,7 +506,12 @@ class PersSampler(nn.Module):
                       starts=ts.unsqueeze(-1), ends=ts.unsqueeze(-1),
                       pixel_area=None if ray_bundle.pixel_area is None else ray_bundle.pixel_area.unsqueeze(1).expand(-1, S, -1))
         cam = None if ray_bundle.camera_indices is None else ray_bundle.camera_indices.unsqueeze(1).expand(-1, S, -1)
-        rel = None if ray_bundle.rel_camera_indices is None else ray_bundle.rel_camera_indices.unsqueeze(1).expand(-1, S, -1)
+        if ray_bundle.rel_camera_indices is not None:
+            rel = ray_bundle.rel_camera_indices.unsqueeze(1).expand(-1, S, -1)
+        elif cam is not None and nearest_image_idx is not None:   # test mode: the nearest training image's embedding (:429-432)
+            rel = torch.ones_like(cam) * nearest_image_idx
+        else:
+            rel = None
         return RaySamples(f2samples=f2, frustums=fr, camera_indices=cam, rel_camera_indices=rel,
                           deltas=dists.unsqueeze(-1), cur_step=cur_step, cur_split_dataset_idx=cur_split_idx)
 

@@ -189,3 +189,36 @@ def test_get_weights_f2nerf_matches_torch_formula_with_autograd():
     assert torch.allclose(w, w_ref, rtol=1e-5, atol=1e-7) and torch.allclose(a, al, rtol=1e-5, atol=1e-7)
     assert torch.allclose(T, tr, rtol=1e-5, atol=1e-7)
     assert float((got - dens.grad).abs().max()) <= 1e-5 * float(dens.grad.abs().max())
+
+
+def test_eval_mode_block_routing():
+    """Render-time routing of the reference (gfnerf/perssampler.py:138-165, 244-260, 367-376, 429-432): without
+    `steps` the chunk's block is the label of the training camera nearest to its first ray origin (or its index
+    bucket when no clustering exists), and without `rel_camera_indices` every sample takes that camera's embedding."""
+    import gfnerf_b200 as gf
+    rig = load_rig("rig8")
+    eng, model = build(rig)
+    ps = model.persampler
+    n_cams = rig["c2w"].shape[0]
+    rb, o, d, cam = bundle(rig, 64, seed=9)
+    k = 37
+    origin = torch.from_numpy(rig["c2w"][k, :, 3]).cuda()
+    rb_eval = gf.RayBundle(origins=origin[None].repeat(64, 1) + 1e-3, directions=rb.directions,
+                           lookat_directions=rb.directions, pixel_area=rb.pixel_area, camera_indices=rb.camera_indices)
+    rs = ps.generate_ray_samples(rb_eval)
+    assert rs.cur_step == -1
+    assert rs.cur_split_dataset_idx == min(k // (n_cams // ps.n_split_dataset), ps.n_split_dataset - 1)
+    assert rs.rel_camera_indices.shape == (64, 1024, 1) and int(rs.rel_camera_indices.min()) == k == int(rs.rel_camera_indices.max())
+    labels = torch.arange(n_cams).view(-1, 1) % 8
+    ps.cameras_labels = labels.cuda()
+    rs = ps.generate_ray_samples(rb_eval)
+    assert rs.cur_split_dataset_idx == int(labels[k]) and ps.get_nearest_split_dataset(origin) == (int(labels[k]), k)
+    # training-time schedule (:361-364): the block follows the step counter after the init stage
+    rb_eval.steps = torch.full((64, 1), ps.steps_perssampler_init + 3 * ps.steps_per_split_dataset + 5).cuda()
+    rb_eval.rel_camera_indices = rb.rel_camera_indices
+    assert ps.generate_ray_samples(rb_eval).cur_split_dataset_idx == 3
+    # the routed bundle renders
+    model.eval()
+    rb_eval.steps, rb_eval.rel_camera_indices = None, None
+    out = model.get_outputs(rb_eval)
+    assert torch.isfinite(out["rgb"]).all()
