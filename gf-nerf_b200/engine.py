@@ -14,6 +14,7 @@ The reference evaluates all R*1024 padded slots; here only the V valid samples e
 valid sample are identical (padding contributes weight 0 in the reference because its delta is 0).
 """
 import contextlib
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -85,7 +86,11 @@ class StepOutputs:
 class GFNeRFEngine:
     """Global-stage model state (hash table, MLPs, appearance embedding) + the fused step."""
 
-    LEVEL_GROUP = 4   # levels per scatter launch / all-reduce message when world > 1 (17 MB at log2T = 19)
+    # Levels per scatter launch / all-reduce message when world > 1.  16 = one scatter, one 67 MB all-reduce after it.
+    # Smaller groups start reducing while the rest is still being scattered, but on 8 B200s NCCL's CTAs next to the
+    # issue-bound scatter cost more than the hidden transfer saves: 5.70 ms/step with groups of 4, 5.57 with 8,
+    # 5.46 with 16 (GF_LEVEL_GROUP to experiment).
+    LEVEL_GROUP = int(os.environ.get("GF_LEVEL_GROUP", "16"))
 
     def __init__(self, sampler: PersSamplerCore, log2_table_size: int = 19, num_images: int = 1, hidden: int = HIDDEN,
                  use_appearance_embedding: bool = True, lr_table: float = 1e-2, lr_mlp: float = 1e-2,
@@ -398,9 +403,8 @@ class GFNeRFEngine:
                                                                               d_ray_emb)
                 g_table = self.opt_table.grad.view(-1, 2)
                 if self.world > 1 and optimizer_step:
-                    # data parallel: the small bucket's all-reduce starts now, the table is scattered in level groups
-                    # and every group's all-reduce starts while the next group is being scattered -- only the last
-                    # group's reduce is left after the backward pass (the table is level-major: groups are contiguous)
+                    # data parallel: the small bucket's all-reduce starts now and runs under the scatter; the table is
+                    # scattered and all-reduced in LEVEL_GROUP-level groups (level-major table: a group is contiguous)
                     self.sync.start_sum([self._small_grads])
                     rows = self.enc.local_size_
                     with self._stage("hash_bwd"):
