@@ -402,6 +402,12 @@ def main():
     roofline = {k: top[k] for k in ("bound", "achieved", "peak", "unit", "frac")}
     roofline.update({"kernel": top["kernel"], "traffic": top.get("traffic"), "peak_source": peaks["src"],
                      "ms": top["ms"]})
+    if top["kernel"] == "sample_rays":
+        # the schema knows "hbm" and "tensor"; this kernel is neither: a serial recurrence per ray,
+        # bound by instruction issue / latency, and in the step it runs a batch ahead underneath the backward pass
+        roofline["note"] = ("latency / issue-bound serial march (52 % issue-active, 0.4 GB DRAM per launch), not "
+                            "HBM-bound; overlapped with the backward when sample_ahead is on. Largest HBM-bound "
+                            "kernels: see kernels[] (hash_bwd, hash_fwd)")
     if rank == 0 and args.breakdown:
         for k in kernels:
             print(k, file=sys.stderr)

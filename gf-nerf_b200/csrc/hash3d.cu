@@ -14,8 +14,9 @@
 //  * the table is an fp16 shadow that is only re-cast when feat_pool changes,
 //    not on every forward as the reference does (:185);
 //  * backward: lanes that fall into the same grid cell (contiguous runs along the
-//    ray) are summed with a segmented shuffle reduction and ONE lane issues the
-//    8 vectorised fp32 reductions (red.global.add.v2.f32) for the run.
+//    ray) are summed first -- by a 1-2 step segmented shuffle reduction for short
+//    runs, through shared memory for long ones -- and the run issues its 8
+//    vectorised fp32 reductions (red.global.add.v2.f32) once (hash_common.cuh).
 //
 // Arithmetic follows the oracle's FMA convention exactly (oracle/gf_oracle.c).
 #include <stdlib.h>
@@ -163,7 +164,7 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
         }
       }
       hash_scatter_level<POW2, HAS_BIAS, UNSCALE>(l, x, y, z, vol, valid, gh, lane, n_volumes, local_size, prim_pool,
-                                                  bias_pool, s_scale[l], grad_table, aggregate != 0,
+                                                  bias_pool, s_scale[l], grad_table, aggregate,
                                                   s_stage + (threadIdx.x >> 5) * kScatterWarpWords);
     }
   }
@@ -303,8 +304,9 @@ int gf_hash_backward_levels(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stride_grid(n, kHashBlock, 4, 4);
   const bool p2 = is_pow2(local_size);
-  // GF_HASH_AGG=0 disables the warp-aggregated reduction (profiling A/B only)
-  static const int aggregate = [] { const char* e = getenv("GF_HASH_AGG"); return e ? atoi(e) : 1; }();
+  // Run aggregation: 0 = off (every lane scatters on its own; profiling A/B only), n > 0 = runs of up to n lanes go
+  // through the segmented shuffle reduction, longer ones through shared memory.  GF_HASH_AGG overrides (A/B).
+  static const int aggregate = [] { const char* e = getenv("GF_HASH_AGG"); return e ? atoi(e) : 4; }();
   const bool g16 = (grad_in_is_scaled_f16 & 1) != 0, unscale = (grad_in_is_scaled_f16 & 2) == 0;
 #define GF_BWD(P2, AT, G16, HB, US)                                                                              \
   hash_bwd_kernel<P2, AT, G16, HB, US><<<grid, kHashBlock, 0, st>>>(n, d_n_ptr, n_volumes, (uint32_t)local_size, \

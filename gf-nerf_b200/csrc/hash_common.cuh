@@ -1,5 +1,5 @@
-// Device helpers of the Hash3DAnchored encode shared by hash3d.cu (stand-alone gather / scatter) and mlp_tc.cu (the
-// scatter fused into the MLP backward).  Arithmetic follows the oracle's FMA convention exactly (oracle/gf_oracle.c);
+// Device helpers of the Hash3DAnchored encode (cell / corner rows / weights, and one level of the backward scatter)
+// used by the kernels of hash3d.cu.  Arithmetic follows the oracle's FMA convention exactly (oracle/gf_oracle.c);
 // line references are to the reference's field/Hash3DAnchored_cuda.cu.
 #pragma once
 #include "common.cuh"
@@ -65,9 +65,6 @@ __device__ __forceinline__ void weights(const Cell& c, float (&w)[8]) {
   w[7] = __fmul_rn(ab, c.c);
 }
 
-// fp16 round trip of a product, :148-151  (__half)(w0 * ws[d])
-__device__ __forceinline__ float q16(float v) { return __half2float(__float2half_rn(v)); }
-
 // ---- backward scatter ---------------------------------------------------------------------------------------
 // Shared-memory staging of the run reduction: one row per lane = 8 x (float2 contribution) + 8 x (u32 table row),
 // padded to 26 words so that the four lane quarters of a column read fall into disjoint bank halves.
@@ -132,7 +129,7 @@ __device__ __forceinline__ void hash_scatter_level(int l, float x, float y, floa
                                                    int lane, int32_t n_volumes, uint32_t local_size,
                                                    const int32_t* __restrict__ prim_pool,
                                                    const float* __restrict__ bias_pool, float scale,
-                                                   float* __restrict__ grad_table, bool aggregate,
+                                                   float* __restrict__ grad_table, int aggregate,
                                                    float* __restrict__ s_warp) {
   const int tr = (l * n_volumes + vol) * 3;
   const Cell c = cell_of(x, y, z, scale, HAS_BIAS ? bias_pool + tr : nullptr);
@@ -164,7 +161,7 @@ __device__ __forceinline__ void hash_scatter_level(int l, float x, float y, floa
     end = above ? (__ffs(above) - 1) : 32;
     maxrun = (int)__reduce_max_sync(0xffffffffu, head ? (unsigned)(end - lane) : 0u);
   }
-  if (maxrun > 4) {  // warp-uniform
+  if (maxrun > aggregate) {  // warp-uniform; aggregate = longest run the shuffle path still takes (4)
     float* row = s_warp + lane * kScatterRowWords;
 #pragma unroll
     for (int d = 0; d < 8; d++) {

@@ -19,6 +19,7 @@ def build():
     spec = importlib.util.spec_from_file_location("gf_build", os.path.join(ROOT, "gf-nerf_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
     cmd = [mod.NVCC] + mod.FLAGS + ["-DGF_MLP_TRACE", "-shared", "-o", SO] + srcs
     subprocess.check_call(cmd)
 
