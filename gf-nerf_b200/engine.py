@@ -280,7 +280,7 @@ class GFNeRFEngine:
         return rgb, depth, acc
 
     # ---- sampling one batch ahead ----------------------------------------------------------------------------
-    def _presample(self, rays_o, rays_d, vote=None):
+    def _presample(self, rays_o, rays_d, vote=None, after=None):
         """Launches the ray sampling of the NEXT batch on a side stream, ordered after everything issued so far on the
         current stream (in particular this step's octree vote, the only thing the sampler depends on).  The sampler
         is a latency-bound kernel that leaves most issue slots of an SM idle; the backward kernels of the current
@@ -291,7 +291,13 @@ class GFNeRFEngine:
             self._cs_slot = 0
         cur = torch.cuda.current_stream(self.device)
         slot = self._cs_slot ^ 1
-        self._pre_stream.wait_stream(cur)
+        # `after`: an event recorded where the side stream's inputs were complete (the forward).  Waiting on the
+        # whole current stream instead would also wait for whatever was launched since -- the MLP backward this work
+        # is meant to run underneath.
+        if after is not None:
+            self._pre_stream.wait_event(after)
+        else:
+            self._pre_stream.wait_stream(cur)
         hook, self.sampler.stage_hook = getattr(self.sampler, "stage_hook", None), None   # events are per stream
         with torch.cuda.stream(self._pre_stream):
             if vote is not None:
@@ -358,8 +364,9 @@ class GFNeRFEngine:
                         self.sampler.update_oct_nodes_compact(cs, weights, alphas, step)
                         self.sampler.UpdateRayMarch(step)
             presample_late = next_rays is not None and getattr(self, "presample_after_mlp", True)
+            fwd_done = torch.cuda.current_stream(self.device).record_event() if presample_late else None
             if next_rays is not None and not presample_late:
-                self._presample(next_rays[0], next_rays[1], vote)
+                self._presample(next_rays[0], next_rays[1], vote, after=fwd_done)
             # backward
             d_sigma = self._buf("d_sigma", (cap,), torch.float32)
             d_rgb = self._buf("d_rgb", (cap, 3), torch.float32)
@@ -380,7 +387,7 @@ class GFNeRFEngine:
             if presample_late:
                 # issued behind the MLP backward: that kernel is resident first (2 CTAs / SM, tensor pipe + epilogue,
                 # ~25 % of the issue slots) and the sampler's CTAs fill the registers it leaves free
-                self._presample(next_rays[0], next_rays[1], vote)
+                self._presample(next_rays[0], next_rays[1], vote, after=fwd_done)
             if block:
                 with self._stage("hash_bwd"):
                     self.res.launch_backward(cs.pts01, cs.anchor, d_feat, True, self.opt_res.grad.view(-1, 2),
