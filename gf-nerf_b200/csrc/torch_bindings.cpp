@@ -20,6 +20,7 @@
 #include <c10/cuda/CUDAStream.h>
 
 #include <cmath>
+#include <fstream>
 #include <random>
 
 #include "../../include/gfnerf_b200.h"
@@ -370,6 +371,104 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     return out;
   }
 
+  // QueryTreeNodeCenterKernel (:984-1028): centre of the node each anchor names (zeros for an anchor out of range)
+  Tensor QueryTreeNodeCenters(const Tensor& anchors) {
+    c10::cuda::CUDAGuard guard(tree_nodes_.device());
+    auto idx = anchors.reshape({-1}).to(torch::kInt64).to(tree_nodes_.device());
+    auto center = tree_nodes_.view({-1, GF_TREE_NODE_BYTES}).slice(1, 0, 12).contiguous().view(torch::kFloat32);
+    auto ok = (idx >= 0) & (idx < n_nodes());
+    return center.index_select(0, idx.clamp(0, n_nodes() - 1)) * ok.unsqueeze(1).to(torch::kFloat32);
+  }
+
+  // PersOctree::UpdateBlockIdxs + SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-798): nearest block centre
+  void UpdateBlockIdxs(const Tensor& centers) {
+    c10::cuda::CUDAGuard guard(tree_nodes_.device());
+    auto nodes = tree_nodes_.view({-1, GF_TREE_NODE_BYTES});
+    auto center = nodes.slice(1, 0, 12).contiguous().view(torch::kFloat32).to(torch::kFloat64);
+    auto c = centers.to(tree_nodes_.device()).to(torch::kFloat64);
+    auto d = torch::linalg_norm(center.unsqueeze(1) - c.unsqueeze(0), 2, {-1}, false);
+    auto best = torch::argmin(d, -1).to(torch::kInt64).contiguous();
+    nodes.slice(1, 104, 112).copy_(best.view({-1, 1}).view(torch::kUInt8));
+    ProcOctree(true, false, false);
+  }
+
+  // PersSampler::VisOctree (PersSampler.cpp:478-514): the leaves' boxes as an .obj wireframe
+  void VisOctree(std::string base_exp_dir) {
+    auto nodes = tree_nodes_.cpu().contiguous();
+    const uint8_t* p = nodes.data_ptr<uint8_t>();
+    const int64_t n = n_nodes();
+    std::ofstream f(base_exp_dir + "/octree.obj", std::ios::out);
+    TORCH_CHECK(f.good(), "VisOctree: cannot write ", base_exp_dir, "/octree.obj");
+    for (int64_t i = 0; i < n; i++) {
+      const float* cs = reinterpret_cast<const float*>(p + i * GF_TREE_NODE_BYTES);
+      for (int st = 0; st < 8; st++)
+        f << "v " << cs[0] + (((st >> 2) & 1) - 0.5f) * cs[3] << " " << cs[1] + (((st >> 1) & 1) - 0.5f) * cs[3] << " "
+          << cs[2] + ((st & 1) - 0.5f) * cs[3] << std::endl;
+    }
+    for (int64_t i = 0; i < n; i++) {
+      if (!p[i * GF_TREE_NODE_BYTES + 88]) continue;  // is_leaf_node
+      for (int a = 0; a < 8; a++)
+        for (int b = a + 1; b < 8; b++) {
+          const int st = a ^ b;
+          if (st == 1 || st == 2 || st == 4) f << "l " << i * 8 + a + 1 << " " << i * 8 + b + 1 << std::endl;
+        }
+    }
+  }
+
+  // introspection (bindings.cpp:86-299): nested lists, as the reference returns them
+  std::vector<int64_t> get_sub_div_milestones_() { return sub_div_milestones_; }
+  template <typename T, typename Out>
+  std::vector<Out> node_field(int64_t offset) {
+    auto nodes = tree_nodes_.cpu().contiguous();
+    const uint8_t* p = nodes.data_ptr<uint8_t>();
+    std::vector<Out> out((size_t)n_nodes());
+    for (int64_t i = 0; i < n_nodes(); i++) {
+      T v;
+      memcpy(&v, p + i * GF_TREE_NODE_BYTES + offset, sizeof(T));
+      out[(size_t)i] = (Out)v;
+    }
+    return out;
+  }
+  std::vector<std::vector<double>> get_tree_nodes_center_() {
+    auto x = node_field<float, double>(0), y = node_field<float, double>(4), z = node_field<float, double>(8);
+    std::vector<std::vector<double>> out(x.size());
+    for (size_t i = 0; i < x.size(); i++) out[i] = {x[i], y[i], z[i]};
+    return out;
+  }
+  std::vector<double> get_tree_nodes_side_len_() { return node_field<float, double>(12); }
+  std::vector<bool> get_tree_nodes_is_leaf_node_() {
+    auto v = node_field<uint8_t, int64_t>(88);
+    return std::vector<bool>(v.begin(), v.end());
+  }
+  std::vector<int64_t> get_tree_nodes_trans_idx_() { return node_field<int64_t, int64_t>(96); }
+  std::vector<int64_t> get_tree_nodes_block_idx_() { return node_field<int64_t, int64_t>(104); }
+  // (w2xz [n][12][2][4], weight [n][3][12], center [n][3], side_len [n], dis_summary [n])
+  std::tuple<std::vector<std::vector<std::vector<std::vector<double>>>>, std::vector<std::vector<std::vector<double>>>,
+             std::vector<std::vector<double>>, std::vector<double>, std::vector<double>>
+  get_pers_trans_info() {
+    auto tr = pers_trans_.cpu().contiguous();
+    const uint8_t* p = tr.data_ptr<uint8_t>();
+    const int64_t n = n_trans();
+    std::vector<std::vector<std::vector<std::vector<double>>>> w2xz((size_t)n);
+    std::vector<std::vector<std::vector<double>>> weight((size_t)n);
+    std::vector<std::vector<double>> center((size_t)n);
+    std::vector<double> side((size_t)n), dis((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+      const float* f = reinterpret_cast<const float*>(p + i * GF_TRANS_INFO_BYTES);
+      w2xz[(size_t)i].assign(GF_N_PROS, std::vector<std::vector<double>>(2, std::vector<double>(4)));
+      for (int k = 0; k < GF_N_PROS; k++)
+        for (int a = 0; a < 2; a++)
+          for (int b = 0; b < 4; b++) w2xz[(size_t)i][k][a][b] = f[(k * 2 + a) * 4 + b];
+      weight[(size_t)i].assign(3, std::vector<double>(GF_N_PROS));
+      for (int r = 0; r < 3; r++)
+        for (int k = 0; k < GF_N_PROS; k++) weight[(size_t)i][r][k] = f[96 + r * GF_N_PROS + k];
+      center[(size_t)i] = {f[132], f[133], f[134]};
+      side[(size_t)i] = f[135];
+      dis[(size_t)i] = f[136];
+    }
+    return std::make_tuple(w2xz, weight, center, side, dis);
+  }
+
   int64_t get_compact_freq_() { return compact_freq_; }
   int64_t get_max_oct_intersect_per_ray_() { return max_oct_; }
   double get_global_near_() { return global_near_; }
@@ -417,5 +516,15 @@ TORCH_LIBRARY(my_classes, m) {  // same names as gfnerf/bindings/hashanchored/bi
       .def("get_n_volumes_", &PersSamplerImpl::get_n_volumes_)
       .def("get_sampled_oct_per_ray_", &PersSamplerImpl::get_sampled_oct_per_ray_)
       .def("get_ray_march_fineness_", &PersSamplerImpl::get_ray_march_fineness_)
-      .def("trans_query_frame", &PersSamplerImpl::TransQueryFrame);
+      .def("trans_query_frame", &PersSamplerImpl::TransQueryFrame)
+      .def("qurey_tree_nodes_centers", &PersSamplerImpl::QueryTreeNodeCenters)  // (sic) bindings.cpp:376
+      .def("UpdateBlockIdxs", &PersSamplerImpl::UpdateBlockIdxs)
+      .def("VisOctree", &PersSamplerImpl::VisOctree)
+      .def("get_sub_div_milestones_", &PersSamplerImpl::get_sub_div_milestones_)
+      .def("get_tree_nodes_center_", &PersSamplerImpl::get_tree_nodes_center_)
+      .def("get_tree_nodes_side_len_", &PersSamplerImpl::get_tree_nodes_side_len_)
+      .def("get_tree_nodes_is_leaf_node_", &PersSamplerImpl::get_tree_nodes_is_leaf_node_)
+      .def("get_tree_nodes_trans_idx_", &PersSamplerImpl::get_tree_nodes_trans_idx_)
+      .def("get_tree_nodes_block_idx_", &PersSamplerImpl::get_tree_nodes_block_idx_)
+      .def("get_pers_trans_info", &PersSamplerImpl::get_pers_trans_info);
 }

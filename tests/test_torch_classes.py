@@ -36,7 +36,10 @@ def test_library_registers_the_reference_class_names():
     assert abs(s.get_ray_march_fineness_() - 16.0) < 1e-5
     s.UpdateRayMarch(10000)
     assert s.get_ray_march_fineness_() == 1.0
-    for name in ("ProcOctree", "MarkInvisibleNodes"):
+    for name in ("ProcOctree", "MarkInvisibleNodes", "qurey_tree_nodes_centers", "UpdateBlockIdxs", "VisOctree",
+                 "get_sub_div_milestones_", "get_tree_nodes_center_", "get_tree_nodes_side_len_",
+                 "get_tree_nodes_is_leaf_node_", "get_tree_nodes_trans_idx_", "get_tree_nodes_block_idx_",
+                 "get_pers_trans_info"):
         assert hasattr(s, name), name
     assert hasattr(mc, "Hash3DAnchored")
 
@@ -139,3 +142,42 @@ def test_init_sampler_builds_the_fixture_octree_and_maintains_it():
     a2, b2 = cc.GetSamples(to, td, bounds), py.GetSamples(to, td, bounds)
     for x, y in zip(a2, b2):
         assert torch.equal(x, y)
+
+
+@pytest.mark.gpu
+def test_cold_surface_equals_python_core(tmp_path):
+    """The introspection / cold methods the reference's Python wrapper calls (gfnerf/perssampler.py:448-640):
+    getters as nested lists, get_pers_trans_info, qurey_tree_nodes_centers (sic), UpdateBlockIdxs, VisOctree."""
+    from tests.helpers import load_rig, make_sampler
+    mc = load()
+    rig = load_rig("rig8")
+    py = make_sampler(rig, mode=1)
+    cc = mc.PersSampler()
+    cc.Configure(1000, 1024, 0.01, True, 1.0 / 256, 1, 1.0, 16.0, 10000)
+    cc.LoadStates(py.States(), 0)
+    assert cc.get_sub_div_milestones_() == py.sub_div_milestones_
+    assert np.allclose(np.array(cc.get_tree_nodes_center_(), np.float32), np.array(py.get_tree_nodes_center_(), np.float32))
+    assert cc.get_tree_nodes_side_len_() == py.get_tree_nodes_side_len_()
+    assert cc.get_tree_nodes_trans_idx_() == py.get_tree_nodes_trans_idx_()
+    assert cc.get_tree_nodes_block_idx_() == py.get_tree_nodes_block_idx_()
+    assert list(cc.get_tree_nodes_is_leaf_node_()) == py.get_tree_nodes_is_leaf_node_()
+    w2xz, weight, center, side, dis = cc.get_pers_trans_info()
+    tr = py.pers_trans_gpu_.cpu().numpy().view(np.float32).reshape(-1, 144)
+    assert np.array_equal(np.array(w2xz, np.float32).reshape(-1, 96), tr[:, :96])
+    assert np.array_equal(np.array(weight, np.float32).reshape(-1, 36), tr[:, 96:132])
+    assert np.array_equal(np.array(center, np.float32), tr[:, 132:135])
+    assert np.array_equal(np.array(side, np.float32), tr[:, 135]) and np.array_equal(np.array(dis, np.float32), tr[:, 136])
+    anchors = torch.tensor([[0], [5], [17], [10 ** 9], [-1]], dtype=torch.int64).cuda()
+    got = cc.qurey_tree_nodes_centers(anchors)
+    ref = py.QueryTreeNodeCenters(anchors[:3, 0])
+    assert torch.equal(got[:3], ref) and not got[3:].any()                # out-of-range anchors leave zeros (:998)
+    centers = torch.tensor([[-2.0, -2.0, 0.0], [2.0, 2.0, 0.0], [2.0, -2.0, 0.0]]).cuda()
+    cc.UpdateBlockIdxs(centers)
+    py.UpdateBlockIdxs(centers)
+    assert torch.equal(cc.States()[0], py.States()[0])
+    assert set(cc.get_tree_nodes_block_idx_()) <= {0, 1, 2}
+    cc.VisOctree(str(tmp_path))
+    lines = (tmp_path / "octree.obj").read_text().splitlines()
+    n = len(cc.get_tree_nodes_side_len_())
+    assert sum(l.startswith("v ") for l in lines) == 8 * n
+    assert sum(l.startswith("l ") for l in lines) == 12 * sum(cc.get_tree_nodes_is_leaf_node_())
