@@ -5,6 +5,7 @@
 // reference: compaction keeps the survivors in their old order, subdivision renumbers depth first with the eight new
 // children of a split leaf directly behind it.  Plain C++ (no Eigen, no torch); the blob layout is
 // PersSampler.h:31-49 as verified in SURVEY.md section 8b.
+#include <math.h>
 #include <string.h>
 
 #include <vector>
@@ -189,5 +190,58 @@ extern "C" int gf_octree_proc(const void* nodes_in, int64_t n_in, const int64_t*
   memcpy(nodes_out, nn.data(), nn.size() * sizeof(TreeNodeBlob));
   memcpy(weight_stats_out, nw.data(), nw.size() * sizeof(int64_t));
   memcpy(alpha_stats_out, na.data(), na.size() * sizeof(int64_t));
+  return GF_OK;
+}
+
+// PersOctree::ConstructEdgePool (PersSampler.cpp:833-893): for every pair of valid leaves, the faces of the smaller
+// one whose centre lies on (inside, with 1e-4 slack) the larger one -> a 64-byte EdgePool record
+// {t_idx_a, t_idx_b, face centre, the two in-face half-edge vectors} (PersSampler.h:50-56).  Host code, O(leaves^2)
+// like the reference.  edges_out == NULL: size query.
+extern "C" int gf_octree_edge_pool(const void* nodes_in, int64_t n_nodes, void* edges_out, int64_t capacity,
+                                   int64_t* n_out) {
+  GF_REQUIRE(nodes_in && n_nodes > 0 && n_out, "gf_octree_edge_pool: null input / empty tree");
+  struct EdgeB {
+    int64_t t_idx_a, t_idx_b;
+    float center[3], dir_0[3], dir_1[3];
+    uint8_t pad[12];
+  };
+  static_assert(sizeof(EdgeB) == 64, "EdgePool blob layout");
+  const TreeNodeBlob* nodes = (const TreeNodeBlob*)nodes_in;
+  std::vector<int64_t> valid;
+  for (int64_t i = 0; i < n_nodes; i++)
+    if (nodes[i].trans_idx >= 0) valid.push_back(i);
+  std::vector<EdgeB> pool;
+  auto is_inside = [](const TreeNodeBlob& nd, const float* pt) {
+    float m = 0.f;
+    for (int k = 0; k < 3; k++) m = fmaxf(m, fabsf((pt[k] - nd.center[k]) / nd.side_len * 2.f));
+    return m < (1.f + 1e-4f);
+  };
+  for (size_t ia = 0; ia < valid.size(); ia++)
+    for (size_t ib = ia + 1; ib < valid.size(); ib++) {
+      const int64_t a = valid[ia], b = valid[ib];
+      int64_t u = a, v = b;
+      if (nodes[u].side_len > nodes[v].side_len) std::swap(u, v);
+      const float len = nodes[u].side_len * .5f;
+      for (int axis = 0; axis < 3; axis++)
+        for (int sgn = 0; sgn < 2; sgn++) {  // +x, -x, +y, -y, +z, -z, the reference's order
+          float pt[3] = {nodes[u].center[0], nodes[u].center[1], nodes[u].center[2]};
+          pt[axis] = sgn == 0 ? pt[axis] + len : pt[axis] - len;
+          if (!is_inside(nodes[v], pt)) continue;
+          EdgeB e;
+          memset(&e, 0, sizeof(e));
+          e.t_idx_a = nodes[a].trans_idx;
+          e.t_idx_b = nodes[b].trans_idx;
+          memcpy(e.center, pt, sizeof(pt));
+          const int d0 = axis == 0 ? 1 : 0, d1 = axis == 2 ? 1 : 2;  // the two in-face axes, in x < y < z order
+          e.dir_0[d0] = len;
+          e.dir_1[d1] = len;
+          pool.push_back(e);
+        }
+    }
+  *n_out = (int64_t)pool.size();
+  if (!edges_out) return GF_OK;
+  GF_REQUIRE(capacity >= (int64_t)pool.size(), "gf_octree_edge_pool: output capacity %lld < %lld edges",
+             (long long)capacity, (long long)pool.size());
+  memcpy(edges_out, pool.data(), pool.size() * sizeof(EdgeB));
   return GF_OK;
 }

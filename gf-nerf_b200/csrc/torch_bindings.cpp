@@ -168,6 +168,8 @@ Tensor Hash3DAnchoredImpl::AnchoredQuery(const Tensor& points, const Tensor& anc
 struct PersSamplerImpl : torch::CustomClassHolder {
   Tensor tree_nodes_, pers_trans_, visit_cnt_, weight_stats_, alpha_stats_, search_order_;
   Tensor w2c_, intri_, bound_;               // cameras, for MarkInvisibleNodes at the subdivision milestones
+  Tensor edge_pool_;                         // 64-byte EdgePool records of the octree edge_pool_key_ points at
+  const void* edge_pool_key_ = nullptr;
   std::vector<int64_t> sub_div_milestones_;  // reversed: the next milestone is at the back
   double global_near_ = 0.01, sample_l_ = 1.0 / 256, fineness_ = 1.0, init_fineness_ = 16.0, decay_end_ = 10000.0;
   double sampled_oct_per_ray_ = 512.0;
@@ -371,6 +373,44 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     return out;
   }
 
+  // PersSampler::GetPointsAnchors (:924-980)
+  Tensor GetPointsAnchors(const Tensor& rays_origins, const Tensor& rays_dirs, const Tensor& t_starts,
+                          const Tensor& t_ends) {
+    c10::cuda::CUDAGuard guard(rays_origins.device());
+    const int64_t R = t_starts.size(0), S = t_starts.size(1);
+    auto t_cur = ((t_starts.to(torch::kFloat32) + t_ends.to(torch::kFloat32)) / 2.0).reshape({R, S}).contiguous();
+    auto o = rays_origins.contiguous().to(torch::kFloat32), d = rays_dirs.contiguous().to(torch::kFloat32);
+    auto anchors = torch::empty({R, S, 1}, o.options().dtype(torch::kInt64));
+    GF_CHECK(gf_sampler_points_anchors(R, S, o.data_ptr<float>(), d.data_ptr<float>(), t_cur.data_ptr<float>(),
+                                       tree_nodes_.data_ptr(), n_nodes(), anchors.data_ptr<int64_t>(), stream()));
+    return anchors;
+  }
+
+  // PersSampler::GetEdgeSamples (:479-516); the edge pool (PersSampler.cpp:833-893) is rebuilt when the octree changed
+  std::tuple<Tensor, Tensor> GetEdgeSamples(int64_t n_pts) {
+    c10::cuda::CUDAGuard guard(tree_nodes_.device());
+    if (!edge_pool_.defined() || edge_pool_key_ != tree_nodes_.data_ptr()) {
+      auto nodes = tree_nodes_.cpu().contiguous();
+      int64_t n = 0;
+      GF_CHECK(gf_octree_edge_pool(nodes.data_ptr(), n_nodes(), nullptr, 0, &n));
+      auto pool = torch::empty({std::max<int64_t>(n, 1) * 64}, torch::kUInt8);
+      GF_CHECK(gf_octree_edge_pool(nodes.data_ptr(), n_nodes(), pool.data_ptr(), n, &n));
+      edge_pool_ = pool.slice(0, 0, n * 64).to(torch::kCUDA);
+      edge_pool_key_ = tree_nodes_.data_ptr();
+    }
+    const int64_t n_edges = edge_pool_.numel() / 64;
+    TORCH_CHECK(n_edges > 0, "GetEdgeSamples: the octree has no pair of neighbouring valid leaves");
+    auto i64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA);
+    auto edge_idx = torch::randint(0, n_edges, {n_pts}, i64).contiguous();                                  // :498
+    auto coords = (torch::rand({n_pts, 2}, i64.dtype(torch::kFloat32)) * 2.f - 1.f).contiguous();            // :499
+    auto out_pts = torch::empty({n_pts, 2, 3}, coords.options());
+    auto out_idx = torch::empty({n_pts, 2}, i64);
+    GF_CHECK(gf_sampler_edge_samples(n_pts, edge_pool_.data_ptr(), n_edges, pers_trans_.data_ptr(),
+                                     edge_idx.data_ptr<int64_t>(), coords.data_ptr<float>(), out_pts.data_ptr<float>(),
+                                     out_idx.data_ptr<int64_t>(), stream()));
+    return std::make_tuple(out_pts, out_idx);
+  }
+
   // QueryTreeNodeCenterKernel (:984-1028): centre of the node each anchor names (zeros for an anchor out of range)
   Tensor QueryTreeNodeCenters(const Tensor& anchors) {
     c10::cuda::CUDAGuard guard(tree_nodes_.device());
@@ -518,6 +558,8 @@ TORCH_LIBRARY(my_classes, m) {  // same names as gfnerf/bindings/hashanchored/bi
       .def("get_ray_march_fineness_", &PersSamplerImpl::get_ray_march_fineness_)
       .def("trans_query_frame", &PersSamplerImpl::TransQueryFrame)
       .def("qurey_tree_nodes_centers", &PersSamplerImpl::QueryTreeNodeCenters)  // (sic) bindings.cpp:376
+      .def("get_points_anchors", &PersSamplerImpl::GetPointsAnchors)
+      .def("GetEdgeSamples", &PersSamplerImpl::GetEdgeSamples)
       .def("UpdateBlockIdxs", &PersSamplerImpl::UpdateBlockIdxs)
       .def("VisOctree", &PersSamplerImpl::VisOctree)
       .def("get_sub_div_milestones_", &PersSamplerImpl::get_sub_div_milestones_)

@@ -386,6 +386,59 @@ class PersSamplerCore:
                 "gf_sampler_trans_query_frame")
         return out
 
+    def GetPointsAnchors(self, rays_origins, rays_dirs, t_starts, t_ends) -> torch.Tensor:
+        """PersSampler::GetPointsAnchors (PersSampler_cuda.cu:924-980, proposal-sampler variant): i64 [R,S,1], the leaf
+        containing each sample's mid-point t, -1 if none."""
+        _lib.require_cuda(rays_origins, rays_dirs, t_starts, t_ends)
+        R, S = t_starts.shape[0], t_starts.shape[1]
+        t_cur = ((t_starts.float() + t_ends.float()) / 2.0).reshape(R, S).contiguous()     # :944
+        anchors = torch.empty((R, S, 1), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gf_sampler_points_anchors(
+                R, S, _lib.ptr(rays_origins.contiguous().float()), _lib.ptr(rays_dirs.contiguous().float()),
+                _lib.ptr(t_cur), _lib.ptr(self.tree_nodes_gpu_), self.n_nodes, _lib.ptr(anchors), _lib.cur_stream()),
+                "gf_sampler_points_anchors")
+        return anchors
+
+    def edge_pool(self) -> torch.Tensor:
+        """PersOctree::ConstructEdgePool (PersSampler.cpp:833-893) over the current octree: uint8 [n_edges * 64] on
+        the device, rebuilt when the node blob changed (the reference builds it once, at construction)."""
+        import ctypes as C
+        key = self.tree_nodes_gpu_.data_ptr()
+        cached = getattr(self, "_edge_pool", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        nodes = self.tree_nodes_gpu_.cpu().contiguous()
+        n, L = C.c_int64(0), _lib.lib()
+        _lib.check(L.gf_octree_edge_pool(_lib.ptr(nodes), self.n_nodes, None, 0, C.byref(n)), "gf_octree_edge_pool")
+        pool = torch.empty(max(n.value, 1) * 64, dtype=torch.uint8)
+        _lib.check(L.gf_octree_edge_pool(_lib.ptr(nodes), self.n_nodes, _lib.ptr(pool), n.value, C.byref(n)),
+                   "gf_octree_edge_pool")
+        dev = pool[:n.value * 64].to(self.device)
+        self._edge_pool = (key, dev)
+        return dev
+
+    def GetEdgeSamples(self, n_pts: int, edge_idx: torch.Tensor = None, edge_coords: torch.Tensor = None):
+        """PersSampler::GetEdgeSamples (PersSampler_cuda.cu:479-516): n_pts random points on faces shared by
+        neighbouring leaves, warped by both leaves' transforms -> (f32 [n,2,3], i64 [n,2]).  edge_idx / edge_coords
+        override the random draws (:498-499) for tests."""
+        pool = self.edge_pool()
+        n_edges = pool.numel() // 64
+        if n_edges == 0:
+            raise RuntimeError("GetEdgeSamples: the octree has no pair of neighbouring valid leaves")
+        if edge_idx is None:
+            edge_idx = torch.randint(0, n_edges, (n_pts,), device=self.device, dtype=torch.int64)
+        if edge_coords is None:
+            edge_coords = torch.rand((n_pts, 2), device=self.device) * 2.0 - 1.0
+        out_pts = torch.empty((n_pts, 2, 3), dtype=torch.float32, device=self.device)
+        out_idx = torch.empty((n_pts, 2), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gf_sampler_edge_samples(
+                n_pts, _lib.ptr(pool), n_edges, _lib.ptr(self.pers_trans_gpu_), _lib.ptr(edge_idx.contiguous()),
+                _lib.ptr(edge_coords.contiguous().float()), _lib.ptr(out_pts), _lib.ptr(out_idx), _lib.cur_stream()),
+                "gf_sampler_edge_samples")
+        return out_pts, out_idx
+
     def QueryTreeNodeCenters(self, anchors: torch.Tensor) -> torch.Tensor:
         center = self.tree_nodes_gpu_.view(-1, 128)[:, :12].contiguous().view(torch.float32)
         return center[anchors.to(torch.int64).clamp(0, self.n_nodes - 1)]
@@ -534,6 +587,12 @@ class PersSampler(nn.Module):
 
     def query_tree_nodes_centers(self, anchors):
         return self.sampler.QueryTreeNodeCenters(anchors)
+
+    def get_points_anchors(self, rays_o, rays_d, t_starts, t_ends):
+        return self.sampler.GetPointsAnchors(rays_o, rays_d, t_starts, t_ends)
+
+    def get_edge_samples(self, n_pts: int):
+        return self.sampler.GetEdgeSamples(n_pts)
 
     def states(self):
         return self.sampler.States()

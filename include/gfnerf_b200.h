@@ -216,6 +216,24 @@ int gf_octree_proc(const void* nodes_in, int64_t n_in, const int64_t* weight_sta
                    const int64_t* visit_cnt_in, int compact, int subdivide, int brute_force, void* nodes_out,
                    int64_t* weight_stats_out, int64_t* alpha_stats_out, int64_t capacity, int64_t* n_out);
 
+/* PersSampler::GetPointsAnchors (GetRaysTreeNodesIntersectsKernel + GetTreeNodeIdxFromTsKernel, :799-853, 924-980;
+ * the proposal-sampler variant, cold): anchors i64 [n_rays, n_pts_per_ray] = index of the LEAF whose slab interval
+ * along the ray contains t_cur (= (t_start + t_end) / 2, f32 [n_rays, n_pts_per_ray]), -1 if none; a sample exactly
+ * on a face shared by two leaves gets the larger index (the reference's stores race there). */
+int gf_sampler_points_anchors(int64_t n_rays, int64_t n_pts_per_ray, const float* rays_o, const float* rays_d,
+                              const float* t_cur, const void* tree_nodes, int64_t n_nodes, int64_t* anchors,
+                              void* stream);
+
+/* PersOctree::ConstructEdgePool (PersSampler.cpp:833-893), HOST code: the faces shared by neighbouring valid leaves
+ * as 64-byte EdgePool records (PersSampler.h:50-56).  edges_out == NULL: size query. */
+int gf_octree_edge_pool(const void* nodes_in, int64_t n_nodes, void* edges_out, int64_t capacity, int64_t* n_out);
+/* GetEdgeSamplesKernel (:479-495): point edge_idx[i] / edge_coords[i] (f32 [n,2] in [-1,1]^2) of the edge pool
+ * (device copy), warped by the transforms of both leaves: out_pts f32 [n,2,3], out_idx i64 [n,2] (trans indices).
+ * The random draws (:498-499) stay with the caller. */
+int gf_sampler_edge_samples(int64_t n_pts, const void* edge_pool, int64_t n_edges, const void* pers_trans,
+                            const int64_t* edge_idx, const float* edge_coords, float* out_pts, int64_t* out_idx,
+                            void* stream);
+
 /* QueryFrameTransform for arbitrary points (TransQueryFrameKernel, :854-922) */
 int gf_sampler_trans_query_frame(int64_t n_pts, const void* tree_nodes, int64_t n_nodes,
                                  const void* pers_trans, const int64_t* anchors,

@@ -1019,3 +1019,44 @@ void orc_generate_rays(int64_t n_rays, const int64_t* cam_idx, const float* coor
     pixel_area[i] = dx * dy;
   }
 }
+
+/* ---- cold sampler queries --------------------------------------------------------------------
+ * PersSampler::GetPointsAnchors (GetRaysTreeNodesIntersectsKernel + GetTreeNodeIdxFromTsKernel,
+ * PersSampler_cuda.cu:799-853, 924-980): for every sample its leaf; where several leaves contain t (a sample exactly
+ * on a shared face) the reference's stores race -- the largest node index is taken here. */
+void orc_points_anchors(int64_t n_rays, int64_t n_pts_per_ray, const float* rays_o, const float* rays_d,
+                        const float* t_cur, const void* tree_nodes_blob, int64_t n_nodes, int64_t* anchors) {
+  const tree_node* nodes = (const tree_node*)tree_nodes_blob;
+  for (int64_t i = 0; i < n_rays * n_pts_per_ray; i++) anchors[i] = -1;
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < n_rays; r++) {
+    for (int64_t u = 0; u < n_nodes; u++) {
+      if (!nodes[u].is_leaf_node) continue;
+      float near = -1e6f, far = 1e6f;
+      get_intersection(rays_o + 3 * r, rays_d + 3 * r, nodes[u].center, nodes[u].side_len, &near, &far);
+      if (far <= near) continue;
+      for (int64_t i = 0; i < n_pts_per_ray; i++) {
+        const float t = t_cur[r * n_pts_per_ray + i];
+        if (t >= near && t <= far && u > anchors[r * n_pts_per_ray + i]) anchors[r * n_pts_per_ray + i] = u;
+      }
+    }
+  }
+}
+
+/* GetEdgeSamplesKernel (:479-495) over 64-byte EdgePool records (PersSampler.h:50-56) */
+void orc_edge_samples(int64_t n_pts, const void* edge_pool_blob, const void* pers_trans_blob, const int64_t* edge_idx,
+                      const float* edge_coords, float* out_pts, int64_t* out_idx) {
+  const trans_info* transes = (const trans_info*)pers_trans_blob;
+  for (int64_t i = 0; i < n_pts; i++) {
+    const char* e = (const char*)edge_pool_blob + edge_idx[i] * 64;
+    int64_t ab[2];
+    memcpy(ab, e, 16);
+    const float* f = (const float*)(e + 16);
+    float p[3];
+    for (int k = 0; k < 3; k++) p[k] = fmaf(f[6 + k], edge_coords[2 * i + 1], fmaf(f[3 + k], edge_coords[2 * i], f[k]));
+    for (int s = 0; s < 2; s++) {
+      query_frame_transform(transes + ab[s], p, out_pts + (2 * i + s) * 3);
+      out_idx[2 * i + s] = ab[s];
+    }
+  }
+}

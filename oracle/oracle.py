@@ -241,3 +241,25 @@ def generate_rays(cam_idx, coords_yx, c2w, fx, fy, cx, cy):
                             _p(out["origins"]), _p(out["directions"]), _p(out["lookat"]), _p(out["pixel_area"]),
                             _p(out["dir_norm"]))
     return out
+
+
+# ---------------------------------------------------------------- cold sampler queries
+def points_anchors(rays_o, rays_d, t_cur, tree_nodes_blob):
+    rays_o, rays_d, t_cur = _f32(rays_o), _f32(rays_d), _f32(t_cur)
+    R, S = t_cur.shape[0], t_cur.shape[1]
+    nodes = np.ascontiguousarray(tree_nodes_blob, np.uint8)
+    out = np.zeros((R, S), np.int64)
+    lib().orc_points_anchors(C.c_int64(R), C.c_int64(S), _p(rays_o), _p(rays_d), _p(t_cur), _p(nodes),
+                             C.c_int64(nodes.size // 128), _p(out))
+    return out
+
+
+def edge_samples(edge_pool_blob, pers_trans_blob, edge_idx, edge_coords):
+    edge_idx = np.ascontiguousarray(edge_idx, np.int64)
+    edge_coords = _f32(edge_coords)
+    n = edge_idx.shape[0]
+    pts, idx = np.zeros((n, 2, 3), np.float32), np.zeros((n, 2), np.int64)
+    lib().orc_edge_samples(C.c_int64(n), _p(np.ascontiguousarray(edge_pool_blob, np.uint8)),
+                           _p(np.ascontiguousarray(pers_trans_blob, np.uint8)), _p(edge_idx), _p(edge_coords), _p(pts),
+                           _p(idx))
+    return pts, idx

@@ -107,3 +107,49 @@ def test_builder_reproduces_the_fixture():
     # errors
     with pytest.raises(RuntimeError):
         build_octree(16, 512.0, 1.5, c2w[:, :2], intri, bounds)
+
+
+def test_edge_pool_matches_numpy_restatement():
+    """gf_octree_edge_pool (PersOctree::ConstructEdgePool, PersSampler.cpp:833-893) against a vectorised numpy
+    restatement of the same pair loop: identical 64-byte records in the same order."""
+    from gfnerf_b200 import _lib
+    rig = load_rig("rig8")
+    oc = _octree(rig)
+    nodes = np.ascontiguousarray(oc.nodes).view(np.uint8).reshape(-1).copy()
+    n = C.c_int64(0)
+    L = _lib.lib()
+    _lib.check(L.gf_octree_edge_pool(nodes.ctypes.data, oc.nodes.shape[0], None, 0, C.byref(n)))
+    pool = np.zeros(n.value * 64, np.uint8)
+    _lib.check(L.gf_octree_edge_pool(nodes.ctypes.data, oc.nodes.shape[0], pool.ctypes.data, n.value, C.byref(n)))
+    edge_dt = np.dtype({"names": ["a", "b", "center", "dir_0", "dir_1"],
+                        "formats": ["<i8", "<i8", ("<f4", 3), ("<f4", 3), ("<f4", 3)],
+                        "offsets": [0, 8, 16, 28, 40], "itemsize": 64})
+    got = pool.view(edge_dt)
+    valid = np.nonzero(oc.nodes["trans_idx"] >= 0)[0]
+    c, s, t = oc.nodes["center"][valid], oc.nodes["side_len"][valid], oc.nodes["trans_idx"][valid]
+    ref = []
+    for ia in range(len(valid)):
+        ib = np.arange(ia + 1, len(valid))
+        if ib.size == 0:
+            continue
+        a_small = s[ia] <= s[ib]                                   # u = the smaller of the pair (a on ties)
+        cu = np.where(a_small[:, None], c[ia][None], c[ib])
+        su = np.where(a_small, s[ia], s[ib])
+        cv = np.where(a_small[:, None], c[ib], c[ia][None])
+        sv = np.where(a_small, s[ib], s[ia])
+        ln = (su * np.float32(.5)).astype(np.float32)
+        for j in range(ib.size):
+            for axis in range(3):
+                for sgn in (1, -1):
+                    pt = cu[j].copy()
+                    pt[axis] = pt[axis] + ln[j] if sgn > 0 else pt[axis] - ln[j]
+                    bias = np.abs((pt - cv[j]) / sv[j] * np.float32(2.)).max()
+                    if bias < np.float32(1. + 1e-4):
+                        d0, d1 = np.zeros(3, np.float32), np.zeros(3, np.float32)
+                        d0[1 if axis == 0 else 0] = ln[j]
+                        d1[1 if axis == 2 else 2] = ln[j]
+                        ref.append((t[ia], t[ib[j]], pt.astype(np.float32), d0, d1))
+    assert len(ref) == got.shape[0] > 0
+    assert np.array_equal(got["a"], np.array([r[0] for r in ref])) and np.array_equal(got["b"], np.array([r[1] for r in ref]))
+    for k, name in ((2, "center"), (3, "dir_0"), (4, "dir_1")):
+        assert np.array_equal(got[name], np.stack([r[k] for r in ref])), name

@@ -154,3 +154,45 @@ def test_proc_octree_roundtrip_and_resample():
     assert np.array_equal(counts, ref["counts"])
     m = valid_mask(counts)
     assert np.array_equal(out2[5].cpu().numpy()[m], ref["anchors"][m])
+
+
+def test_cold_queries_match_oracle():
+    """get_points_anchors (GetRaysTreeNodesIntersects + GetTreeNodeIdxFromTs, PersSampler_cuda.cu:799-853, 924-980)
+    and GetEdgeSamples (:479-516) against the oracle, through the Python core."""
+    import ctypes as C
+    rig = load_rig("rig8")
+    s = make_sampler(rig, mode=1)
+    from gfnerf_b200.persoctree import rig_rays
+    R, S = 200, 48
+    o, d, _ = rig_rays(rig["c2w"], rig["intri"], R, seed=12)
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    rng = np.random.RandomState(3)
+    t0 = np.sort(rng.uniform(0.05, 12.0, size=(R, S + 1)).astype(np.float32), axis=1)
+    ts, te = t0[:, :-1, None].copy(), t0[:, 1:, None].copy()
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    got = s.GetPointsAnchors(T(o), T(d.astype(np.float32)), T(ts), T(te))
+    assert got.shape == (R, S, 1) and got.dtype == torch.int64
+    t_cur = ((torch.from_numpy(ts) + torch.from_numpy(te)) / 2.0).numpy()[:, :, 0]
+    ref = orc.points_anchors(o, d.astype(np.float32), t_cur, rig["tree_nodes"])
+    assert np.array_equal(got.cpu().numpy()[:, :, 0], ref)
+    assert (ref >= 0).mean() > 0.3                                     # most samples do fall into a leaf
+    # every anchor is a leaf whose box contains the sample (up to fp slack)
+    nodes = rig["tree_nodes"].view(np.uint8).reshape(-1, 128)
+    cs = nodes[:, :16].copy().view(np.float32)
+    m = ref >= 0
+    p = o[:, None, :] + d[:, None, :] * t_cur[:, :, None]
+    box = cs[ref[m]]
+    assert np.all(np.abs(p[m] - box[:, :3]).max(-1) <= box[:, 3] * 0.5 * (1 + 1e-3) + 1e-4)
+    # edge samples with given draws
+    pool = s.edge_pool()
+    n_edges = pool.numel() // 64
+    assert n_edges > 0
+    n = 500
+    eidx = rng.randint(0, n_edges, size=n).astype(np.int64)
+    ecoord = rng.uniform(-1, 1, size=(n, 2)).astype(np.float32)
+    pts, idx = s.GetEdgeSamples(n, T(eidx), T(ecoord))
+    rpts, ridx = orc.edge_samples(pool.cpu().numpy(), rig["pers_trans"], eidx, ecoord)
+    assert np.array_equal(idx.cpu().numpy(), ridx) and np.array_equal(pts.cpu().numpy(), rpts)
+    pts2, idx2 = s.GetEdgeSamples(64)                                  # random draws: shapes, valid transform ids
+    assert pts2.shape == (64, 2, 3) and int(idx2.min()) >= 0 and int(idx2.max()) < rig["pers_trans"].size // 576
+    assert torch.isfinite(pts2).all()

@@ -39,7 +39,7 @@ def test_library_registers_the_reference_class_names():
     for name in ("ProcOctree", "MarkInvisibleNodes", "qurey_tree_nodes_centers", "UpdateBlockIdxs", "VisOctree",
                  "get_sub_div_milestones_", "get_tree_nodes_center_", "get_tree_nodes_side_len_",
                  "get_tree_nodes_is_leaf_node_", "get_tree_nodes_trans_idx_", "get_tree_nodes_block_idx_",
-                 "get_pers_trans_info"):
+                 "get_pers_trans_info", "get_points_anchors", "GetEdgeSamples"):
         assert hasattr(s, name), name
     assert hasattr(mc, "Hash3DAnchored")
 
@@ -171,6 +171,16 @@ def test_cold_surface_equals_python_core(tmp_path):
     got = cc.qurey_tree_nodes_centers(anchors)
     ref = py.QueryTreeNodeCenters(anchors[:3, 0])
     assert torch.equal(got[:3], ref) and not got[3:].any()                # out-of-range anchors leave zeros (:998)
+    from gfnerf_b200.persoctree import rig_rays
+    o, d, _ = rig_rays(rig["c2w"], rig["intri"], 64, seed=2)
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+    t0 = torch.sort(torch.rand(64, 33, generator=torch.Generator().manual_seed(0)) * 10 + 0.05, dim=1).values
+    ts, te = t0[:, :-1, None].contiguous().cuda(), t0[:, 1:, None].contiguous().cuda()
+    to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    assert torch.equal(cc.get_points_anchors(to, td, ts, te), py.GetPointsAnchors(to, td, ts, te))
+    epts, eidx = cc.GetEdgeSamples(32)
+    assert epts.shape == (32, 2, 3) and eidx.shape == (32, 2) and torch.isfinite(epts).all()
+    assert int(eidx.min()) >= 0 and int(eidx.max()) < py.pers_trans_gpu_.numel() // 576
     centers = torch.tensor([[-2.0, -2.0, 0.0], [2.0, 2.0, 0.0], [2.0, -2.0, 0.0]]).cuda()
     cc.UpdateBlockIdxs(centers)
     py.UpdateBlockIdxs(centers)
