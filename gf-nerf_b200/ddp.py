@@ -11,8 +11,9 @@ gfnerf/hash_3d_anchored.py:26,73-78) and the octree's occupancy votes.  Here eve
     bit-identical.
 
 Backend-agnostic on purpose: NCCL over NVLink on the GPU box, gloo in the CPU tests (tests/test_ddp_gloo.py).
-On CUDA the gradient reduce runs on a side stream so that it overlaps whatever the compute stream does next
-(octree vote, the next batch's ray sampling, which needs neither the table nor the MLP).
+On CUDA the gradient reduce runs on a side stream so that it overlaps whatever the compute stream does next that
+needs neither the table nor the MLP (the small bucket's reduce runs under the hash scatter; without sampling ahead,
+the table's reduce runs under the next batch's ray sampling).
 """
 from typing import List, Optional, Sequence
 

@@ -507,8 +507,9 @@ class GFNeRFEngine:
         """DDP semantics (mean over ranks) for ALL parameters -- including the hash table, which the reference's
         DDP wrapper silently skips because feat_pool is not a registered nn.Parameter.
         With more than one rank the all-reduce is launched on the comm stream and the Adam step is DEFERRED to the
-        point where the parameters are next needed (after the next batch's ray sampling, which reads neither the
-        table nor the MLP), so NVLink time hides behind the sampler kernel."""
+        point where the parameters are next needed: the start of the next iteration's forward (`flush`).  With
+        `next_rays` the next batch's sampling has moved underneath the backward pass, so there the reduce is exposed
+        (DESIGN.md section 6)."""
         if self.world > 1:   # (train_step pipelines this per level group; this is the one-shot form)
             self.sync.start_sum([self._small_grads, self.opt_table.grad])
             self._deferred = lr_scale
