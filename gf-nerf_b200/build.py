@@ -15,6 +15,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fopenmp",      # host loops of the octree builder (csrc/octree_build.cu)
 ]
 
 
@@ -48,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
         # static cudart (nvcc default): independent of whichever libcudart torch brings along
-        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fopenmp",
+                               "-o", LIB] + objs)
     return LIB
 
 

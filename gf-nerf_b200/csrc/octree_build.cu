@@ -269,7 +269,11 @@ struct Builder {
       hi[k] = center[k] + side_len * .5f;
     }
     const double radius = (double)side_len * 0.8660254 + 1e-6;
-    for (int64_t cam : candidates) {
+    std::vector<char> seen(candidates.size(), 0);
+    // cameras are independent: flags in parallel, gathered in candidate order (same list whatever the thread count)
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t ci = 0; ci < (int64_t)candidates.size(); ci++) {
+      const int64_t cam = candidates[(size_t)ci];
       // conservative view-cone reject (a pure speed-up: a rejected camera has no grid ray through the cell)
       const float* m = c2w + cam * 12;
       double rel[3], dist = 0.0, dot = 0.0;
@@ -283,8 +287,10 @@ struct Builder {
         const double ang = acos(std::max(-1.0, std::min(1.0, dot / dist))) - asin(std::min(1.0, radius / dist));
         if (ang > half_diag_fov + 1e-4) continue;
       }
-      if (camera_sees(cam, lo, hi)) out.push_back(cam);
+      if (camera_sees(cam, lo, hi)) seen[(size_t)ci] = 1;
     }
+    for (size_t ci = 0; ci < candidates.size(); ci++)
+      if (seen[ci]) out.push_back(candidates[ci]);
     return out;
   }
 
@@ -399,29 +405,49 @@ struct Builder {
     // the 12 projections of the sample points and their Jacobians (:779-812), PCA of the projections
     const int64_t n = (int64_t)rand_pts.size() / 3;
     std::vector<double> v((size_t)n * kNPros), dvd((size_t)n * kNPros * 3);
-    double mean[kNPros] = {0};
-    for (int64_t i = 0; i < n; i++) {
-      const float* pt = &rand_pts[(size_t)i * 3];
-      for (int p = 0; p < kNPros; p++) {
-        double t0 = frame[p][0][3], t1 = frame[p][1][3];
-        for (int c = 0; c < 3; c++) {
-          t0 += frame[p][0][c] * pt[c];
-          t1 += frame[p][1][c] * pt[c];
+    // The sums over the sample points are taken over kChunks fixed slices, each sequentially, and the slices are
+    // combined in order: the result does not depend on the number of threads.
+    constexpr int kChunks = 64;
+    const int64_t per = (n + kChunks - 1) / kChunks;
+    double mean_c[kChunks][kNPros];
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int ch = 0; ch < kChunks; ch++) {
+      for (int p = 0; p < kNPros; p++) mean_c[ch][p] = 0.0;
+      for (int64_t i = ch * per; i < std::min(n, (ch + 1) * per); i++) {
+        const float* pt = &rand_pts[(size_t)i * 3];
+        for (int p = 0; p < kNPros; p++) {
+          double t0 = frame[p][0][3], t1 = frame[p][1][3];
+          for (int c = 0; c < 3; c++) {
+            t0 += frame[p][0][c] * pt[c];
+            t1 += frame[p][1][c] * pt[c];
+          }
+          if (!(t1 < 0)) bad |= 1;  // :795 a sample point behind a virtual camera
+          const double da = 1.0 / t1, db = t0 / -(t1 * t1);
+          for (int c = 0; c < 3; c++) dvd[((size_t)i * kNPros + p) * 3 + c] = da * frame[p][0][c] + db * frame[p][1][c];
+          v[(size_t)i * kNPros + p] = t0 / t1;
+          mean_c[ch][p] += t0 / t1;
         }
-        if (!(t1 < 0)) return false;  // :795 a sample point behind a virtual camera
-        const double da = 1.0 / t1, db = t0 / -(t1 * t1);
-        for (int c = 0; c < 3; c++) dvd[((size_t)i * kNPros + p) * 3 + c] = da * frame[p][0][c] + db * frame[p][1][c];
-        v[(size_t)i * kNPros + p] = t0 / t1;
-        mean[p] += t0 / t1;
       }
     }
+    if (bad) return false;
+    double mean[kNPros] = {0};
+    for (int ch = 0; ch < kChunks; ch++)
+      for (int p = 0; p < kNPros; p++) mean[p] += mean_c[ch][p];
     for (int p = 0; p < kNPros; p++) mean[p] /= (double)n;
+    std::vector<double> cov_c((size_t)kChunks * kNPros * kNPros, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int ch = 0; ch < kChunks; ch++) {
+      double* cc = &cov_c[(size_t)ch * kNPros * kNPros];
+      for (int64_t i = ch * per; i < std::min(n, (ch + 1) * per); i++)
+        for (int a = 0; a < kNPros; a++) {
+          const double ma = v[(size_t)i * kNPros + a] - mean[a];
+          for (int b = a; b < kNPros; b++) cc[a * kNPros + b] += ma * (v[(size_t)i * kNPros + b] - mean[b]);
+        }
+    }
     double cov[kNPros * kNPros] = {0};
-    for (int64_t i = 0; i < n; i++)
-      for (int a = 0; a < kNPros; a++) {
-        const double ma = v[(size_t)i * kNPros + a] - mean[a];
-        for (int b = a; b < kNPros; b++) cov[a * kNPros + b] += ma * (v[(size_t)i * kNPros + b] - mean[b]);
-      }
+    for (int ch = 0; ch < kChunks; ch++)
+      for (int k = 0; k < kNPros * kNPros; k++) cov[k] += cov_c[(size_t)ch * kNPros * kNPros + k];
     for (int a = 0; a < kNPros; a++)
       for (int b = a; b < kNPros; b++) {
         cov[a * kNPros + b] /= (double)n;
@@ -436,27 +462,39 @@ struct Builder {
     for (int r = 0; r < 3; r++)
       for (int p = 0; p < kNPros; p++) W[r][p] = (double)(float)V[p * kNPros + order[r]];
     // mean over the points of 1 / max_k |d v_k / d warp_c|, the inverse Jacobian through the 3 components
-    double mean_step[3] = {0, 0, 0};
-    for (int64_t i = 0; i < n; i++) {
-      double jac[9];
-      for (int r = 0; r < 3; r++)
+    double step_c[kChunks][3];
+    int singular = 0;
+#pragma omp parallel for schedule(static) reduction(| : singular)
+    for (int ch = 0; ch < kChunks; ch++) {
+      step_c[ch][0] = step_c[ch][1] = step_c[ch][2] = 0.0;
+      for (int64_t i = ch * per; i < std::min(n, (ch + 1) * per); i++) {
+        double jac[9];
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) {
+            double s = 0;
+            for (int p = 0; p < kNPros; p++) s += W[r][p] * dvd[((size_t)i * kNPros + p) * 3 + c];
+            jac[3 * r + c] = s;
+          }
+        double ji[9];
+        if (!inv3(jac, ji)) {
+          singular |= 1;
+          continue;
+        }
         for (int c = 0; c < 3; c++) {
-          double s = 0;
-          for (int p = 0; p < kNPros; p++) s += W[r][p] * dvd[((size_t)i * kNPros + p) * 3 + c];
-          jac[3 * r + c] = s;
+          double mx = 0;
+          for (int p = 0; p < kNPros; p++) {
+            double s = 0;
+            for (int q = 0; q < 3; q++) s += dvd[((size_t)i * kNPros + p) * 3 + q] * ji[3 * q + c];
+            mx = std::max(mx, fabs(s));
+          }
+          step_c[ch][c] += 1.0 / mx;
         }
-      double ji[9];
-      if (!inv3(jac, ji)) return false;
-      for (int c = 0; c < 3; c++) {
-        double mx = 0;
-        for (int p = 0; p < kNPros; p++) {
-          double s = 0;
-          for (int q = 0; q < 3; q++) s += dvd[((size_t)i * kNPros + p) * 3 + q] * ji[3 * q + c];
-          mx = std::max(mx, fabs(s));
-        }
-        mean_step[c] += 1.0 / mx;
       }
     }
+    if (singular) return false;
+    double mean_step[3] = {0, 0, 0};
+    for (int ch = 0; ch < kChunks; ch++)
+      for (int c = 0; c < 3; c++) mean_step[c] += step_c[ch][c];
     memset(&out, 0, sizeof(out));
     for (int r = 0; r < 3; r++) {
       mean_step[r] /= (double)n;

@@ -2,6 +2,7 @@
 numpy restatement `PersOctree.proc_octree` on the same blobs: byte-identical node blobs and statistics.  Host code,
 runs without a GPU."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -82,14 +83,15 @@ def test_errors():
     assert rc != 0 and b"capacity" in L.gf_last_error()
 
 
-def test_builder_reproduces_the_fixture():
+@pytest.mark.parametrize("name", ["rig8", "rig20"])
+def test_builder_reproduces_the_fixture(name):
     """gf_octree_build (C++, csrc/octree_build.cu = PersOctree::PersOctree + ConstructTreeNode + ConstructTrans,
     PersSampler.cpp:92-152, 516-831) on the 64-camera rig against the committed fixture, which the numpy restatement
     `PersOctree(...)` built from the same cameras and the same (replayed) random draws: the node blob byte for byte,
     the leaf transforms to fp32 rounding -- PCA components up to their sign, which an eigen-decomposition leaves open."""
     from gfnerf_b200.persoctree import TRANS_INFO_DTYPE, aerial_rig, search_order_table
     from gfnerf_b200.perssampler import build_octree
-    rig = load_rig("rig8")
+    rig = load_rig(name)          # 64 cameras (parity tests) / 400 cameras (the bench rig, BASELINE config 2)
     c2w, intri, bounds = aerial_rig(n_side=int(rig["n_side"]), extent=float(rig["extent"]), seed=1)
     assert np.array_equal(c2w, rig["c2w"])
     oc = build_octree(16, 512.0, 1.5, c2w, intri, bounds, seed=0)
@@ -104,9 +106,21 @@ def test_builder_reproduces_the_fixture():
     assert (sign != 0).all()
     err = np.abs(got["weight"] * sign - ref["weight"]).max(-1) / np.abs(ref["weight"]).max(-1)
     assert err.max() < 1e-3
-    # errors
-    with pytest.raises(RuntimeError):
-        build_octree(16, 512.0, 1.5, c2w[:, :2], intri, bounds)
+    if name == "rig8":
+        # the host loops are OpenMP-parallel with fixed-slice sums: the same bytes whatever the thread count
+        import subprocess
+        import sys
+        code = ("import sys, hashlib; sys.path.insert(0, %r); from gfnerf_b200.persoctree import aerial_rig; "
+                "from gfnerf_b200.perssampler import build_octree; c, i, b = aerial_rig(n_side=8, extent=4.0, seed=1); "
+                "o = build_octree(16, 512.0, 1.5, c, i, b, seed=0); "
+                "print(hashlib.sha1(o.pers_trans_blob().tobytes() + o.tree_nodes_blob().tobytes()).hexdigest())")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        outs = {subprocess.check_output([sys.executable, "-c", code % root], env=dict(os.environ, OMP_NUM_THREADS=t),
+                                        text=True).strip().splitlines()[-1] for t in ("1", "5")}
+        assert len(outs) == 1, outs
+        # errors
+        with pytest.raises(RuntimeError):
+            build_octree(16, 512.0, 1.5, c2w[:, :2], intri, bounds)
 
 
 def test_edge_pool_matches_numpy_restatement():
