@@ -51,3 +51,37 @@ def test_product_package_does_not_touch_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "libgf_oracle" not in text, f
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: include/gfnerf_b200.h compiles as C99 with gcc (no C++, no torch, no CUDA headers) and
+    a C program calling through it links against libgfnerf_b200.so and runs the host-only entry points (argument
+    validation, the octree's child search order, the error string) on a machine without a GPU."""
+    from gfnerf_b200 import _lib
+    src = tmp_path / "demo.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gfnerf_b200.h"
+int main(void) {
+  unsigned char order[64];
+  if (gf_octree_search_order(order) != GF_OK) return 1;
+  /* ray octant 0: children farthest-first in bit-reversed order */
+  if (order[0] != 7 || order[7] != 0) return 2;
+  int64_t n_out = 0;
+  if (gf_octree_proc(NULL, 0, NULL, NULL, NULL, 1, 0, 0, NULL, NULL, NULL, 0, &n_out) == GF_OK) return 3;
+  if (!strstr(gf_last_error(), "gf_octree_proc")) return 4;
+  if (gf_mlp_param_count(64) != 11603) return 5;
+  printf("%s\n", gf_version());
+  return 0;
+}
+''')
+    exe = tmp_path / "demo"
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", lib_dir, "-lgfnerf_b200", f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "sm_100a" in r.stdout
