@@ -168,8 +168,7 @@ Tensor Hash3DAnchoredImpl::AnchoredQuery(const Tensor& points, const Tensor& anc
 struct PersSamplerImpl : torch::CustomClassHolder {
   Tensor tree_nodes_, pers_trans_, visit_cnt_, weight_stats_, alpha_stats_, search_order_;
   Tensor w2c_, intri_, bound_;               // cameras, for MarkInvisibleNodes at the subdivision milestones
-  Tensor edge_pool_;                         // 64-byte EdgePool records of the octree edge_pool_key_ points at
-  const void* edge_pool_key_ = nullptr;
+  Tensor edge_pool_;                         // 64-byte EdgePool records (built lazily, see GetEdgeSamples)
   std::vector<int64_t> sub_div_milestones_;  // reversed: the next milestone is at the back
   double global_near_ = 0.01, sample_l_ = 1.0 / 256, fineness_ = 1.0, init_fineness_ = 16.0, decay_end_ = 10000.0;
   double sampled_oct_per_ray_ = 512.0;
@@ -234,6 +233,7 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     tree_nodes_ = states[idx++].clone().to(torch::kCUDA).contiguous();
     pers_trans_ = states[idx++].clone().to(torch::kCUDA).contiguous();
     visit_cnt_ = states[idx++].clone().to(torch::kCUDA).contiguous();
+    edge_pool_ = Tensor();
     auto ms = states[idx++].to(torch::kCPU).to(torch::kInt64).contiguous();
     sub_div_milestones_.assign(ms.data_ptr<int64_t>(), ms.data_ptr<int64_t>() + ms.numel());
     auto i64 = torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA);
@@ -386,17 +386,18 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     return anchors;
   }
 
-  // PersSampler::GetEdgeSamples (:479-516); the edge pool (PersSampler.cpp:833-893) is rebuilt when the octree changed
+  // PersSampler::GetEdgeSamples (:479-516).  The edge pool (PersSampler.cpp:833-893) is built at the first use after
+  // InitSampler / LoadStates and kept while the octree is pruned and subdivided, as the reference keeps the one its
+  // constructor built (the records name transforms, which are never removed).
   std::tuple<Tensor, Tensor> GetEdgeSamples(int64_t n_pts) {
     c10::cuda::CUDAGuard guard(tree_nodes_.device());
-    if (!edge_pool_.defined() || edge_pool_key_ != tree_nodes_.data_ptr()) {
+    if (!edge_pool_.defined()) {
       auto nodes = tree_nodes_.cpu().contiguous();
       int64_t n = 0;
       GF_CHECK(gf_octree_edge_pool(nodes.data_ptr(), n_nodes(), nullptr, 0, &n));
       auto pool = torch::empty({std::max<int64_t>(n, 1) * 64}, torch::kUInt8);
       GF_CHECK(gf_octree_edge_pool(nodes.data_ptr(), n_nodes(), pool.data_ptr(), n, &n));
       edge_pool_ = pool.slice(0, 0, n * 64).to(torch::kCUDA);
-      edge_pool_key_ = tree_nodes_.data_ptr();
     }
     const int64_t n_edges = edge_pool_.numel() / 64;
     TORCH_CHECK(n_edges > 0, "GetEdgeSamples: the octree has no pair of neighbouring valid leaves");

@@ -107,6 +107,7 @@ class PersSamplerCore:
             octree = build_octree(int(max_level), float(1 << (int(bbox_levels) - 1)), float(np.float32(split_dist_thres)),
                                   to_np(c2w), to_np(intri), to_np(bounds), seed=seed)
         self.octree = octree
+        self._edge_pool = None
         self.n_volumes_ = int(octree.trans.shape[0])
         self._upload_octree(stats=True)
         self.search_order_ = torch.from_numpy(octree.search_order.copy()).to(self.device)
@@ -367,6 +368,7 @@ class PersSamplerCore:
         self.pers_trans_gpu_ = states[idx].clone().to(self.device).contiguous(); idx += 1
         self.tree_visit_cnt_ = states[idx].clone().to(self.device).contiguous(); idx += 1
         self.sub_div_milestones_ = [int(v) for v in states[idx].cpu().tolist()]; idx += 1
+        self._edge_pool = None
         self.octree.load_blobs(self.tree_nodes_gpu_.cpu().numpy(), self.pers_trans_gpu_.cpu().numpy())
         n = self.n_nodes
         self.tree_weight_stats_ = torch.full((n,), INIT_NODE_STAT, dtype=torch.int64, device=self.device)
@@ -401,22 +403,22 @@ class PersSamplerCore:
         return anchors
 
     def edge_pool(self) -> torch.Tensor:
-        """PersOctree::ConstructEdgePool (PersSampler.cpp:833-893) over the current octree: uint8 [n_edges * 64] on
-        the device, rebuilt when the node blob changed (the reference builds it once, at construction)."""
+        """PersOctree::ConstructEdgePool (PersSampler.cpp:833-893): uint8 [n_edges * 64] on the device.  The reference
+        builds it once, in the PersOctree constructor, and keeps it while the octree is pruned and subdivided (the
+        records name transforms, which are never removed); here it is built at the first use after InitSampler /
+        LoadStates and kept the same way."""
         import ctypes as C
-        key = self.tree_nodes_gpu_.data_ptr()
         cached = getattr(self, "_edge_pool", None)
-        if cached is not None and cached[0] == key:
-            return cached[1]
+        if cached is not None:
+            return cached
         nodes = self.tree_nodes_gpu_.cpu().contiguous()
         n, L = C.c_int64(0), _lib.lib()
         _lib.check(L.gf_octree_edge_pool(_lib.ptr(nodes), self.n_nodes, None, 0, C.byref(n)), "gf_octree_edge_pool")
         pool = torch.empty(max(n.value, 1) * 64, dtype=torch.uint8)
         _lib.check(L.gf_octree_edge_pool(_lib.ptr(nodes), self.n_nodes, _lib.ptr(pool), n.value, C.byref(n)),
                    "gf_octree_edge_pool")
-        dev = pool[:n.value * 64].to(self.device)
-        self._edge_pool = (key, dev)
-        return dev
+        self._edge_pool = pool[:n.value * 64].to(self.device)
+        return self._edge_pool
 
     def GetEdgeSamples(self, n_pts: int, edge_idx: torch.Tensor = None, edge_coords: torch.Tensor = None):
         """PersSampler::GetEdgeSamples (PersSampler_cuda.cu:479-516): n_pts random points on faces shared by
