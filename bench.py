@@ -146,6 +146,22 @@ def time_oracle(rays, steps, warmup, log2T=LOG2T):
     return rays * steps / dt, dt / steps * 1e3, orc.num_threads(), n_samples / steps
 
 
+def time_reference_cpu_path():
+    """BASELINE.json configs[0] -- the reference's own CPU-runnable path (nerfstudio torch hash encoding + MLPs +
+    renderer, 4096 rays x 48 samples, fwd+bwd), the number the north star asks to be reported next to the GPU one:
+    oracle/nerfacto_cpu.py (pinned to the reference's classes by tests/test_nerfacto_cpu.py), all host threads.
+    A different workload from the GPU arm's (48 uniform samples per ray, no octree), hence its own key."""
+    try:
+        from oracle import nerfacto_cpu as nc
+        rays_s, ms, threads = nc.time_cfg1(steps=5, warmup=2)
+        return {"value": rays_s, "unit": "rays/s", "ms_per_step": ms, "cores": threads, "kind": "port",
+                "workload": "BASELINE.json configs[0]: nerfstudio nerfacto, torch hash-encoding backend, "
+                            "4096 rays x 48 samples, log2T=19, fwd+bwd (no optimizer), torch CPU",
+                "sample": "median of 5 steps after 2 warm-ups"}
+    except Exception as e:  # a reported side number must never take the bench line down with it
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -161,6 +177,7 @@ def reference_arm(args):
         "config": {"workload": workload_name(), "rays_per_step": rays, "log2T": LOG2T},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_reference_path": time_reference_cpu_path(),
     }))
 
 
@@ -412,8 +429,9 @@ def main():
         for k in kernels:
             print(k, file=sys.stderr)
 
-    cpu_baseline = None
+    cpu_baseline = cpu_reference_path = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_reference_path = time_reference_cpu_path()
         cv, cms, cores, cvs = time_oracle(256, 3, 1)
         cpu_baseline = {"value": cv, "unit": "rays/s", "cores": cores, "kind": "port",
                         "sample": f"256 rays/step ({cvs:.0f} samples), 3 steps after 1 warm-up, same rig / table / MLP shapes"}
@@ -442,6 +460,7 @@ def main():
             "roofline": roofline,
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
+            "cpu_reference_path": cpu_reference_path,
         }))
     if world > 1:
         dist.destroy_process_group()

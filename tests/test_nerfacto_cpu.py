@@ -1,0 +1,111 @@
+"""oracle/nerfacto_cpu.py (the restatement of BASELINE.json configs[0], the reference's own CPU-runnable torch path
+that bench.py times next to the GPU numbers) against vectors produced by RUNNING the reference's unmodified classes
+(tests/golden/make_golden_cfg1.py -> tests/golden/ref_cfg1.npz).  CPU only."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerfacto_cpu as nc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-5   # BASELINE.json north_star: 1e-5 relative for fp32 values
+
+
+def close(a, b, rtol=RTOL, what=""):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, f"{what}: {a.shape} vs {b.shape}"
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(a - b).max())
+    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    d = np.load(os.path.join(GOLD, "ref_cfg1.npz"))
+    return {k: d[k] for k in d.files}
+
+
+def from_fixture(g):
+    params = {k[2:]: g[k] for k in g if k.startswith("p_")}
+    inp = {k[3:]: g[k] for k in g if k.startswith("in_")}
+    return nc.NerfactoCPU(log2_hashmap_size=int(g["log2_hashmap_size"]), params=params), inp
+
+
+def test_level_scalings_match_reference(gold):
+    assert np.array_equal(nc.level_scalings().numpy(), gold["p_scalings"])
+    assert nc.level_scalings()[0] == 16 and nc.level_scalings()[-1] in (2047, 2048)
+
+
+def test_hash_rows_are_the_reference_rows(gold):
+    """Index parity, bit-exact: a table whose row r holds (r, -r) turns the blend into a weighted mean of row numbers;
+    with one-hot positions on cell corners the encoding IS the row number."""
+    log2 = 8
+    size = 1 << log2
+    rows = torch.arange(size * nc.N_LEVELS, dtype=torch.float64)
+    table = torch.stack([rows, -rows], dim=-1)
+    sc = nc.level_scalings().double()
+    # positions that are exact lattice points of level 0 (scale 16): ceil == floor, so all 8 corners coincide
+    ijk = torch.tensor([[0, 0, 0], [1, 2, 3], [15, 7, 9], [16, 16, 16]], dtype=torch.float64)
+    enc = nc.hash_encode(table, sc, ijk / 16.0, log2)
+    i = ijk.long() * torch.tensor(nc.PRIMES)
+    expect = ((i[:, 0] ^ i[:, 1] ^ i[:, 2]) % size).double()
+    assert torch.equal(enc[:, 0], expect) and torch.equal(enc[:, 1], -expect)
+
+
+def test_forward_matches_reference(gold):
+    model, inp = from_fixture(gold)
+    with torch.no_grad():
+        out = model.forward(inp)
+    for k in ("density", "sample_rgb", "weights", "rgb", "accumulation", "depth", "loss"):
+        close(out[k].numpy(), gold[f"out_{k}"], what=k)
+
+
+def test_backward_matches_reference_autograd(gold):
+    model, inp = from_fixture(gold)
+    loss = model.step(inp)
+    close(loss, gold["out_loss"], what="loss")
+    for k, v in model.p.items():
+        ref = gold[f"g_{k}"]
+        close(v.grad.numpy(), ref, rtol=2e-5, what=f"grad {k}")
+    # the zero pattern of the table gradient is index parity again: same rows touched
+    assert np.array_equal(model.p["hash_table"].grad.numpy() != 0, gold["g_hash_table"] != 0)
+
+
+def test_default_init_has_reference_shapes_and_ranges():
+    m = nc.NerfactoCPU(log2_hashmap_size=10, n_images=4, seed=3)
+    assert m.p["hash_table"].shape == (16 << 10, 2)
+    assert float(m.p["hash_table"].detach().abs().max()) <= 1e-3          # encodings.py:257-258, hash_init_scale 1e-3
+    assert [tuple(m.p[f"w{i}"].shape) for i in range(7)] == list(nc.LAYERS)
+    assert m.p["embedding"].shape == (4, 40)
+
+
+def test_time_cfg1_runs_small():
+    rays_s, ms, threads = nc.time_cfg1(steps=1, warmup=0, R=64, S=48, log2_hashmap_size=12, threads=2)
+    assert rays_s > 0 and ms > 0 and threads == 2
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/nerfstudio"), reason="reference tree only in the build container")
+def test_full_size_against_the_reference_itself():
+    """BASELINE.json configs[0] at its real size (4096 x 48, log2T = 19): the reference's classes and the restatement
+    on the same parameters and inputs."""
+    spec = importlib.util.spec_from_file_location("make_golden_cfg1", os.path.join(GOLD, "make_golden_cfg1.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ref = mg.import_reference()
+    torch.manual_seed(5)
+    model = mg.ReferenceCfg1(ref, log2_hashmap_size=19, n_images=16)
+    model.train()
+    with torch.no_grad():
+        model.position_encoding.hash_table.mul_(300.0)
+    inp = nc.synthetic_inputs(4096, 48, 16, seed=1234)
+    out = model(inp)
+    out["loss"].backward()
+    mine = nc.NerfactoCPU(log2_hashmap_size=19, params=model.export_params())
+    loss = mine.step(inp)
+    close(loss, out["loss"].detach().numpy(), what="loss")
+    g = model.export_grads()
+    for k, v in mine.p.items():
+        close(v.grad.numpy(), g[f"g_{k}"], rtol=5e-5, what=f"grad {k}")
