@@ -46,6 +46,7 @@ _SIGS = {
     "gf_sampler_edge_samples": [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_sampler_trans_query_frame": [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "gf_generate_rays": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gf_error_map_update": [_i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     "gf_composite_forward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_composite_backward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_mlp_ray_bias": [_i64, _int, _vp, _vp, _vp, _vp, _vp],

@@ -69,9 +69,49 @@ generate_rays_kernel(int64_t n, const int64_t* __restrict__ cam_idx, const float
   }
 }
 
+// Error-map feedback of the focal (block) stage: error = sum_c |gt - pred| per ray (gfnerf/gf_pipeline.py:180-184)
+// written to error_map[image, y, x] (nerfstudio/data/utils/dataloaders.py:140-142) -- the abs / sum / index_put chain
+// as one pass.  One thread per ray.  Duplicate (image, y, x) triples in one batch store the same pixel more than
+// once; like torch's index_put without accumulate, which of the duplicates lands last is unspecified.
+__global__ void __launch_bounds__(256)
+error_map_update_kernel(int64_t n, const int64_t* __restrict__ idx, const float* __restrict__ pred,
+                        const float* __restrict__ gt, int64_t n_images, int64_t height, int64_t width,
+                        float* __restrict__ error_map, float* __restrict__ error_out, int* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float e = __fadd_rn(__fadd_rn(fabsf(__fsub_rn(gt[3 * i], pred[3 * i])),
+                                        fabsf(__fsub_rn(gt[3 * i + 1], pred[3 * i + 1]))),
+                              fabsf(__fsub_rn(gt[3 * i + 2], pred[3 * i + 2])));
+    if (error_out) error_out[i] = e;
+    int64_t c = idx[3 * i], y = idx[3 * i + 1], x = idx[3 * i + 2];
+    // torch indexing wraps negative indices once and raises beyond that; out-of-range rows are skipped and flagged
+    if (c < 0) c += n_images;
+    if (y < 0) y += height;
+    if (x < 0) x += width;
+    if (c < 0 || c >= n_images || y < 0 || y >= height || x < 0 || x >= width) {
+      if (bad) *bad = 1;
+      continue;
+    }
+    error_map[(c * height + y) * width + x] = e;
+  }
+}
+
 }  // namespace gf
 
 using namespace gf;
+
+extern "C" int gf_error_map_update(int64_t n_rays, const int64_t* indices, const float* pred_rgb,
+                                   const float* gt_rgb, int64_t n_images, int64_t height, int64_t width,
+                                   float* error_map, float* error_out, int32_t* bad_index_flag, void* stream) {
+  GF_REQUIRE(n_rays >= 0 && n_images > 0 && height > 0 && width > 0,
+             "gf_error_map_update: bad sizes n_rays=%lld map=[%lld,%lld,%lld]", (long long)n_rays,
+             (long long)n_images, (long long)height, (long long)width);
+  if (n_rays == 0) return GF_OK;
+  GF_REQUIRE(indices && pred_rgb && gt_rgb && error_map, "gf_error_map_update: null pointer");
+  error_map_update_kernel<<<stride_grid(n_rays, 256, 8, 4), 256, 0, (cudaStream_t)stream>>>(
+      n_rays, indices, pred_rgb, gt_rgb, n_images, height, width, error_map, error_out, bad_index_flag);
+  return check_launch("error_map_update_kernel");
+}
 
 extern "C" int gf_generate_rays(int64_t n_rays, const int64_t* cam_idx, const float* coords_yx, const float* c2w,
                                 const float* fx, const float* fy, const float* cx, const float* cy, int64_t n_cams,

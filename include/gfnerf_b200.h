@@ -358,6 +358,18 @@ int gf_generate_rays(int64_t n_rays, const int64_t* cam_idx, const float* coords
                      float* origins, float* directions, float* lookat, float* pixel_area, float* dir_norm,
                      void* stream);
 
+/* ---- error-map feedback of the focal stage -------------
+ * gfnerf/gf_pipeline.py:180-185 + TrainDataloader._update_error_map (nerfstudio/data/utils/dataloaders.py:140-142):
+ * error[i] = sum over the 3 channels of |gt - pred|; error_map[indices[i,0], indices[i,1], indices[i,2]] = error[i].
+ * indices int64 [n,3] = (image slot in the cached batch, y, x) as the pixel sampler drew them; error_map f32
+ * [n_images, height, width] (the reference's trailing singleton channel is a view of the same memory).
+ * error_out f32 [n] (may be NULL) also receives the per-ray error.  An index out of range (after one wrap of a
+ * negative index, as torch does) writes nothing and sets *bad_index_flag (device int32, may be NULL, caller zeroes)
+ * -- torch raises IndexError there; the host wrapper turns the flag into the same error. */
+int gf_error_map_update(int64_t n_rays, const int64_t* indices, const float* pred_rgb, const float* gt_rgb,
+                        int64_t n_images, int64_t height, int64_t width, float* error_map, float* error_out,
+                        int32_t* bad_index_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

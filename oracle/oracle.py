@@ -263,3 +263,13 @@ def edge_samples(edge_pool_blob, pers_trans_blob, edge_idx, edge_coords):
                            _p(np.ascontiguousarray(pers_trans_blob, np.uint8)), _p(edge_idx), _p(edge_coords), _p(pts),
                            _p(idx))
     return pts, idx
+
+
+def error_map_update(error_map, indices, pred_rgb, gt_rgb):
+    """gfnerf/gf_pipeline.py:180-185 + nerfstudio/data/utils/dataloaders.py:140-142 in numpy: error = sum_c |gt - pred|
+    (fp32, channel order 0,1,2), error_map[idx0, idx1, idx2] = error; in place on error_map [n,h,w]; returns error."""
+    d = np.abs(np.asarray(gt_rgb, np.float32) - np.asarray(pred_rgb, np.float32))
+    err = ((d[:, 0] + d[:, 1]).astype(np.float32) + d[:, 2]).astype(np.float32)
+    idx = np.asarray(indices, np.int64)
+    error_map[idx[:, 0], idx[:, 1], idx[:, 2]] = err
+    return err
