@@ -81,7 +81,7 @@ hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
                        pc = (uint32_t)__ldg(prim_pool + tr + 2);
         uint32_t pos[8];
         corners<POW2>(c, pa, pb, pc, local_size, pos);
-        const __half2* tab = feat + (int64_t)l * local_size;
+        const __half2* tab = feat + level_base_row(l, local_size);
         __half2 f[8];
 #pragma unroll
         for (int d = 0; d < 8; d++) f[d] = __ldg(tab + pos[d]);
@@ -187,7 +187,7 @@ hash_rows_kernel(int64_t n, int32_t n_volumes, uint32_t local_size, const int32_
       corners<POW2>(c, (uint32_t)__ldg(prim_pool + tr), (uint32_t)__ldg(prim_pool + tr + 1),
                     (uint32_t)__ldg(prim_pool + tr + 2), local_size, pos);
 #pragma unroll
-      for (int d = 0; d < 8; d++) rows[(i * GF_N_LEVELS + l) * 8 + d] = (int32_t)((int64_t)l * local_size + pos[d]);
+      for (int d = 0; d < 8; d++) rows[(i * GF_N_LEVELS + l) * 8 + d] = (int32_t)(level_base_row(l, local_size) + pos[d]);
     }
   }
 }
@@ -233,8 +233,8 @@ static int hash_forward_impl(int64_t n, const int32_t* d_n_ptr, int32_t n_volume
                              const void* feat_f16, const int32_t* prim_pool, const float* bias_pool,
                              const float* level_scales, const float* pts, const void* anchors, int anchor_i64,
                              void* out_f16, float* out_f32, const void* base_f16, void* stream) {
-  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL,
-             "gf_hash_forward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
+  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL && local_size % 2 == 0,
+             "gf_hash_forward: bad sizes n=%lld n_volumes=%d local_size=%lld (must be even)", (long long)n, n_volumes,
              (long long)local_size);
   GF_REQUIRE((int64_t)n_volumes * GF_N_LEVELS * 3 <= 0x7fffffffLL, "gf_hash_forward: n_volumes too large");
   GF_REQUIRE(out_f16 || out_f32, "gf_hash_forward: no output buffer");
@@ -293,8 +293,8 @@ int gf_hash_backward_levels(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes
                             const float* pts, const void* anchors, int anchor_i64, const void* grad_in,
                             int grad_in_is_scaled_f16, float* grad_table, int level_begin, int level_end,
                             void* stream) {
-  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL,
-             "gf_hash_backward: bad sizes n=%lld n_volumes=%d local_size=%lld", (long long)n, n_volumes,
+  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size <= 0x7fffffffLL && local_size % 2 == 0,
+             "gf_hash_backward: bad sizes n=%lld n_volumes=%d local_size=%lld (must be even)", (long long)n, n_volumes,
              (long long)local_size);
   GF_REQUIRE(0 <= level_begin && level_begin <= level_end && level_end <= GF_N_LEVELS,
              "gf_hash_backward: bad level range [%d, %d)", level_begin, level_end);
@@ -343,8 +343,9 @@ int gf_hash_backward_levels(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes
 int gf_hash_corner_rows(int64_t n, int32_t n_volumes, int64_t local_size, const int32_t* prim_pool,
                         const float* bias_pool, const float* level_scales, const float* pts,
                         const void* anchors, int anchor_i64, int32_t* rows, void* stream) {
-  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size * GF_N_LEVELS <= 0x7fffffffLL,
-             "gf_hash_corner_rows: bad sizes");
+  GF_REQUIRE(n >= 0 && n_volumes > 0 && local_size > 0 && local_size * GF_N_LEVELS <= 0x7fffffffLL &&
+                 local_size % 2 == 0,
+             "gf_hash_corner_rows: bad sizes (local_size must be even)");
   if (n == 0) return GF_OK;
   GF_REQUIRE(prim_pool && level_scales && pts && anchors && rows, "gf_hash_corner_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream;

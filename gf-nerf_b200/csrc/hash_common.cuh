@@ -6,6 +6,17 @@
 
 namespace gf {
 
+// First table ROW of level l.  The reference's kernels offset the table pointer by feat_local_idx[l] = l * local_size
+// (Hash3DAnchored.cpp:66-70) while that pointer is a pointer to SCALARS (`T* feat_pool`, Hash3DAnchored_cuda.cu:38,
+// :105), and then index it with pos * N_CHANNELS + k: level l's window therefore starts at row l * local_size / 2 and
+// is local_size rows long -- consecutive levels overlap by half a window and rows >= 8.5 * local_size are never
+// touched.  Found by running the reference's own kernel bodies on the host (oracle/ref_driver.cpp); reproduced here
+// because a table trained by the reference is only meaningful under this addressing.  local_size is even (the
+// reference rounds it to a multiple of 16); the C-ABI rejects odd sizes.
+__host__ __device__ __forceinline__ int64_t level_base_row(int l, uint32_t local_size) {
+  return ((int64_t)l * (int64_t)local_size) >> 1;
+}
+
 template <bool POW2>
 __device__ __forceinline__ uint32_t wrap(uint32_t h, uint32_t local_size) {
   if (POW2) return h & (local_size - 1u);
@@ -147,7 +158,7 @@ __device__ __forceinline__ void hash_scatter_level(int l, float x, float y, floa
     const __half2 h = __floats2half2_rn(__fmul_rn(g0, w[d]), __fmul_rn(g1, w[d]));
     cq[d] = *reinterpret_cast<const uint32_t*>(&h);
   }
-  const char* tab = reinterpret_cast<const char*>(grad_table) + (uint64_t)l * local_size * 8u;
+  const char* tab = reinterpret_cast<const char*>(grad_table) + (uint64_t)level_base_row(l, local_size) * 8u;
   int maxrun = 1;
   uint32_t heads = 0xffffffffu;
   int end = lane + 1;

@@ -86,7 +86,8 @@ class StepOutputs:
 class GFNeRFEngine:
     """Global-stage model state (hash table, MLPs, appearance embedding) + the fused step."""
 
-    # Levels per scatter launch / all-reduce message when world > 1.  16 = one scatter, one 67 MB all-reduce after it.
+    # Levels per scatter launch / all-reduce message when world > 1.  16 = one scatter, one all-reduce after it (of the
+    # 8.5 * local_size rows the reference's level addressing can reach, 36 MB at log2T = 19; see level_base_row).
     # Smaller groups start reducing while the rest is still being scattered, but on 8 B200s NCCL's CTAs next to the
     # issue-bound scatter cost more than the hidden transfer saves: 5.70 ms/step with groups of 4, 5.57 with 8,
     # 5.46 with 16 (GF_LEVEL_GROUP to experiment).
@@ -411,15 +412,18 @@ class GFNeRFEngine:
                 g_table = self.opt_table.grad.view(-1, 2)
                 if self.world > 1 and optimizer_step:
                     # data parallel: the small bucket's all-reduce starts now and runs under the scatter; the table is
-                    # scattered and all-reduced in LEVEL_GROUP-level groups (level-major table: a group is contiguous)
+                    # scattered and all-reduced in LEVEL_GROUP-level groups.  Level l owns rows [l*T/2, l*T/2 + T)
+                    # (level_base_row: windows overlap by half), so once levels < l1 are scattered the rows below
+                    # l1*T/2 are final; the last group takes the rest of the reachable rows.
                     self.sync.start_sum([self._small_grads])
-                    rows = self.enc.local_size_
+                    half = self.enc.local_size_ // 2
                     with self._stage("hash_bwd"):
                         for l0 in range(0, 16, self.LEVEL_GROUP):
                             l1 = min(l0 + self.LEVEL_GROUP, 16)
                             self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, g_table, d_n_ptr=cs.total,
                                                      keep_x128=True, levels=(l0, l1))
-                            self.sync.start_sum([g_table[l0 * rows:l1 * rows]])
+                            r1 = l1 * half if l1 < 16 else self.enc.used_rows_
+                            self.sync.start_sum([g_table[l0 * half:r1]])
                     self._deferred = lr_scale
                 else:
                     with self._stage("hash_bwd"):
@@ -511,7 +515,8 @@ class GFNeRFEngine:
         `next_rays` the next batch's sampling has moved underneath the backward pass, so there the reduce is exposed
         (DESIGN.md section 6)."""
         if self.world > 1:   # (train_step pipelines this per level group; this is the one-shot form)
-            self.sync.start_sum([self._small_grads, self.opt_table.grad])
+            # rows past used_rows_ never receive a gradient on any rank (level_base_row): nothing to exchange there
+            self.sync.start_sum([self._small_grads, self.opt_table.grad.view(-1, 2)[:self.enc.used_rows_]])
             self._deferred = lr_scale
         else:
             self._apply_adam(lr_scale)

@@ -113,7 +113,12 @@ class Hash3DAnchoredCore:
         local_size = (local_size >> 4) << 4
         self.local_size_ = local_size
         self.feat_local_size_ = torch.full((N_LEVELS,), local_size, dtype=torch.int32, device=self.device)
+        # Hash3DAnchored.cpp:66-70.  NB the reference's kernels add this offset to a pointer to SCALARS
+        # (Hash3DAnchored_cuda.cu:38, :105), so level l's window starts at ROW l * local_size / 2: consecutive levels
+        # overlap by half a window and only the first 8.5 * local_size rows of feat_pool are ever read or given a
+        # gradient (csrc/hash_common.cuh level_base_row; pinned by tests/test_ref_kernels.py).
         self.feat_local_idx_ = (torch.cumsum(self.feat_local_size_, 0) - local_size).to(torch.int32)
+        self.used_rows_ = (N_LEVELS - 1) * local_size // 2 + local_size
         self.level_scales_ = torch.empty(N_LEVELS, dtype=torch.float32, device=self.device)
         self.level_scales_host = np.zeros(N_LEVELS, np.float32)
         with torch.cuda.device(self.device):

@@ -87,6 +87,13 @@ typedef struct {
   float w[8];
 } hash_cell;
 
+/* First table ROW of level l.  Hash3DAnchored.cpp:66-70 computes feat_local_idx[l] = l * local_size, but the
+ * kernels add it to a pointer to SCALARS (`T* feat_pool`, Hash3DAnchored_cuda.cu:38; `T* grad_out`, :105) and then
+ * index pos * N_CHANNELS + k: level l starts at row l * local_size / 2, consecutive levels overlap by half a
+ * window, rows >= 8.5 * local_size are never used.  PINNED by the reference's own kernel bodies run on the host
+ * (oracle/ref_driver.cpp, tests/test_ref_kernels.py).  local_size is even (the reference makes it a multiple of 16). */
+static inline int64_t level_base_row(int l, int64_t local_size) { return ((int64_t)l * local_size) >> 1; }
+
 /* index + weight math shared by forward and backward, Hash3DAnchored_cuda.cu:26-69 / 97-140 */
 static inline void hash_cell_eval(const float* pt, float mul, const float* bias, const int32_t* prim,
                                   uint32_t local_size, hash_cell* c) {
@@ -131,7 +138,7 @@ void orc_hash_forward(int64_t n, int32_t n_volumes, int64_t local_size, const fl
       int64_t tr = (int64_t)l * n_volumes + vol;
       hash_cell_eval(pts + 3 * i, scales[l], bias_pool + 3 * tr, prim_pool + 3 * tr,
                      (uint32_t)local_size, &c);
-      const float* tab = feat_f32 + (int64_t)l * local_size * N_CHANNELS;
+      const float* tab = feat_f32 + (int64_t)l * local_size; /* :38 the pointer is a SCALAR pointer, see level_base_row */
       for (int k = 0; k < N_CHANNELS; k++) {
         float f[8];
         for (int d = 0; d < 8; d++) f[d] = h2f(f2h(tab[(int64_t)c.pos[d] * N_CHANNELS + k]));
@@ -143,7 +150,7 @@ void orc_hash_forward(int64_t n, int32_t n_volumes, int64_t local_size, const fl
       }
       if (idx_out)
         for (int d = 0; d < 8; d++)
-          idx_out[(i * N_LEVELS + l) * 8 + d] = (int32_t)((int64_t)l * local_size + c.pos[d]);
+          idx_out[(i * N_LEVELS + l) * 8 + d] = (int32_t)(level_base_row(l, local_size) + c.pos[d]);
     }
   }
 }
@@ -174,7 +181,7 @@ void orc_hash_backward(int64_t n, int32_t n_volumes, int64_t local_size, const i
       float g0 = h2f(f2h(grad_out[i * 32 + l * 2 + 0] * 128.f));
       float g1 = h2f(f2h(grad_out[i * 32 + l * 2 + 1] * 128.f));
       if (g0 != 0.f || g1 != 0.f) {
-        double* tab = grad_table + (int64_t)l * local_size * N_CHANNELS;
+        double* tab = grad_table + (int64_t)l * local_size; /* :105 scalar offset, as in the forward */
         for (int d = 0; d < 8; d++) {
           double a0 = (double)h2f(f2h(g0 * c.w[d])) / 128.0, a1 = (double)h2f(f2h(g1 * c.w[d])) / 128.0;
 #pragma omp atomic

@@ -1,0 +1,144 @@
+"""ctypes wrapper of oracle/_ref/libgf_ref_host*.so -- the REFERENCE's own kernel bodies (extracted at build time from
+/root/reference by oracle/ref_extract.py) compiled for the host by oracle/ref_driver.cpp.  TEST INFRASTRUCTURE ONLY.
+
+Two flavours are built (oracle/Makefile target `ref`): "off" = -ffp-contract=off (every fp32 operation rounded on its
+own) and "fma" = -ffp-contract=fast -mfma (g++ fuses mul+add pairs where it likes, as nvcc -fmad=true does where IT
+likes).  The shared objects are git-ignored but travel to the GPU box with the snapshot, like every built .so.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+_libs = {}
+
+_vp, _i64, _f32, _int = C.c_void_p, C.c_int64, C.c_float, C.c_int
+
+
+def path(flavour="off"):
+    return os.path.join(REF_DIR, "libgf_ref_host.so" if flavour == "off" else "libgf_ref_host_fma.so")
+
+
+def available(flavour="off"):
+    return os.path.exists(path(flavour))
+
+
+def lib(flavour="off"):
+    if flavour not in _libs:
+        L = C.CDLL(path(flavour))
+        L.ref_build_flavour.restype = C.c_char_p
+        L.ref_sizeof_edge_pool.restype = C.c_int64
+        _libs[flavour] = L
+    return _libs[flavour]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def hash_forward(feat_f32, prim_pool, bias_pool, pts, anchors, flavour="off"):
+    """Hash3DAnchoredFunction::forward: table cast to fp16, kernel, output widened to fp32.  -> [n,32] fp32"""
+    n, n_vol = pts.shape[0], prim_pool.shape[1]
+    local = feat_f32.shape[0] // 16
+    table = _c(feat_f32, np.float32).astype(np.float16)
+    prim, bias = _c(prim_pool, np.int32), _c(bias_pool, np.float32)
+    fidx = (np.arange(16) * local).astype(np.int32)
+    fsize = np.full(16, local, np.int32)
+    out = np.zeros((n, 32), np.float16)
+    pts, anchors = _c(pts, np.float32), _c(anchors, np.int64)
+    lib(flavour).ref_hash_forward(_int(n), _int(n_vol), _p(table), _p(prim), _p(fidx), _p(fsize), _p(bias), _p(pts),
+                                  _p(anchors), _p(out))
+    return out.astype(np.float32)
+
+
+def hash_backward(local_size, prim_pool, bias_pool, pts, anchors, grad_out, flavour="off"):
+    """Hash3DAnchoredFunction::backward: (grad * 128) -> fp16, kernel with fp16 half2 atomics (serial order), result
+    widened and divided by 128.  -> [16*local_size, 2] fp32"""
+    n, n_vol = pts.shape[0], prim_pool.shape[1]
+    prim, bias = _c(prim_pool, np.int32), _c(bias_pool, np.float32)
+    fidx = (np.arange(16) * local_size).astype(np.int32)
+    fsize = np.full(16, local_size, np.int32)
+    gin = (_c(grad_out, np.float32) * np.float32(128.0)).astype(np.float16)
+    gout = np.zeros((16 * local_size, 2), np.float16)
+    pts, anchors = _c(pts, np.float32), _c(anchors, np.int64)
+    lib(flavour).ref_hash_backward(_int(n), _int(n_vol), _p(prim), _p(fidx), _p(fsize), _p(bias), _p(pts),
+                                   _p(anchors), _p(gin), _p(gout))
+    return gout.astype(np.float32) / np.float32(128.0)
+
+
+def get_samples(rays_o, rays_d_unit, noise, tree_nodes, pers_trans, search_order, global_near=0.01,
+                sample_l=1.0 / 256, scale_by_dis=True, max_oct=1024, flavour="off"):
+    R, S = rays_o.shape[0], 1024
+    rays_o, rays_d_unit, noise = _c(rays_o, np.float32), _c(rays_d_unit, np.float32), _c(noise, np.float32)
+    nodes, trans = _c(tree_nodes, np.uint8).copy(), _c(pers_trans, np.uint8).copy()
+    so = _c(search_order, np.uint8)
+    out = dict(world_pts=np.zeros((R, S, 3), np.float32), warp_pts=np.zeros((R, S, 3), np.float32),
+               dirs=np.zeros((R, S, 3), np.float32), dists=np.zeros((R, S), np.float32),
+               ts=np.zeros((R, S), np.float32), anchors=np.zeros((R, S, 3), np.int64),
+               pts_idx_start_end=np.zeros((R, 2), np.int64), first_oct_dis=np.zeros(R, np.float32),
+               n_oct=np.zeros(R, np.int64), oct_idx=np.full((R, max_oct), -1, np.int64),
+               oct_nf=np.zeros((R, max_oct, 2), np.float32))
+    lib(flavour).ref_get_samples(_i64(R), _p(rays_o), _p(rays_d_unit), _p(noise), _p(nodes), _p(trans), _p(so),
+                                 _f32(global_near), _f32(sample_l), _int(int(scale_by_dis)), _i64(max_oct),
+                                 _p(out["world_pts"]), _p(out["warp_pts"]), _p(out["dirs"]), _p(out["dists"]),
+                                 _p(out["ts"]), _p(out["anchors"]), _p(out["pts_idx_start_end"]),
+                                 _p(out["first_oct_dis"]), _p(out["n_oct"]), _p(out["oct_idx"]), _p(out["oct_nf"]))
+    se = out["pts_idx_start_end"]
+    out["counts"] = (se[:, 1] - se[:, 0]).astype(np.int32)
+    return out
+
+
+def update_oct_nodes(pts_idx_start_end, oct_indices, weights, alphas, tree_nodes, weight_stats, alpha_stats, visit_cnt,
+                     flavour="off"):
+    """In place on tree_nodes (uint8 blob) and the three int64 stat arrays."""
+    R = pts_idx_start_end.shape[0]
+    lib(flavour).ref_update_oct_nodes(_i64(R), _p(_c(pts_idx_start_end, np.int64)), _p(_c(oct_indices, np.int64)),
+                                      _p(_c(weights, np.float32)), _p(_c(alphas, np.float32)), _p(tree_nodes),
+                                      _i64(tree_nodes.size // 128), _p(weight_stats), _p(alpha_stats), _p(visit_cnt))
+
+
+def trans_query_frame(tree_nodes, pers_trans, anchors, world_pts, flavour="off"):
+    n = world_pts.shape[0]
+    nodes, trans = _c(tree_nodes, np.uint8), _c(pers_trans, np.uint8)
+    out = np.zeros((n, 3), np.float32)
+    lib(flavour).ref_trans_query_frame(_i64(n), _p(nodes), _i64(nodes.size // 128), _p(trans),
+                                       _p(_c(anchors, np.int64)), _p(_c(world_pts, np.float32)), _p(out))
+    return out
+
+
+def points_anchors(rays_o, rays_d, t_cur, tree_nodes, flavour="off"):
+    t_cur = _c(t_cur, np.float32)
+    R, S = t_cur.shape[0], t_cur.shape[1]
+    nodes = _c(tree_nodes, np.uint8)
+    out = np.full((R, S), -1, np.int64)
+    lib(flavour).ref_points_anchors(_i64(R), _i64(S), _p(_c(rays_o, np.float32)), _p(_c(rays_d, np.float32)),
+                                    _p(t_cur), _p(nodes), _i64(nodes.size // 128), _p(out))
+    return out
+
+
+def edge_samples(edge_pool, pers_trans, edge_idx, edge_coords, flavour="off"):
+    edge_idx = _c(edge_idx, np.int64)
+    n = edge_idx.shape[0]
+    pts, idx = np.zeros((n, 2, 3), np.float32), np.zeros((n, 2), np.int64)
+    lib(flavour).ref_edge_samples(_i64(n), _p(_c(edge_pool, np.uint8)), _p(_c(pers_trans, np.uint8)), _p(edge_idx),
+                                  _p(_c(edge_coords, np.float32)), _p(pts), _p(idx))
+    return pts, idx
+
+
+def mark_invisible_nodes(tree_nodes, intri, w2c, bounds, flavour="off"):
+    """In place on tree_nodes."""
+    lib(flavour).ref_mark_invisible_nodes(_i64(tree_nodes.size // 128), _i64(intri.shape[0]), _p(tree_nodes),
+                                          _p(_c(intri, np.float32)), _p(_c(w2c, np.float32)),
+                                          _p(_c(bounds, np.float32)))
+
+
+def set_block_idxs(tree_nodes, centers, flavour="off"):
+    """In place on tree_nodes."""
+    centers = _c(centers, np.float32)
+    lib(flavour).ref_set_block_idxs(_i64(tree_nodes.size // 128), _i64(centers.shape[0]), _p(tree_nodes), _p(centers))

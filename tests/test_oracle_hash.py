@@ -26,7 +26,9 @@ def numpy_hash(feat, prim, bias, pts, anchors, scales):
             dx, dy, dz = (d >> 2) & 1, (d >> 1) & 1, d & 1
             h = ((pos[:, 0] + np.uint32(dx)) * pr[:, 0]) ^ ((pos[:, 1] + np.uint32(dy)) * pr[:, 1]) ^ \
                 ((pos[:, 2] + np.uint32(dz)) * pr[:, 2])
-            rows[:, l, d] = l * local + (h % np.uint32(local))
+            # the level offset l * local is added to a SCALAR pointer in the reference (Hash3DAnchored_cuda.cu:38):
+            # in rows that is l * local / 2 -- consecutive levels overlap by half a window
+            rows[:, l, d] = (l * local) // 2 + (h % np.uint32(local))
             wa = frac[:, 0] if dx else one - frac[:, 0]
             wb = frac[:, 1] if dy else one - frac[:, 1]
             wc = frac[:, 2] if dz else one - frac[:, 2]
@@ -73,9 +75,9 @@ def test_non_pow2_local_size_and_edges():
     pts = np.array([[0, 0, 0], [1, 1, 1], [0.5, 0.25, 0.125], [0.999999, 0, 1]], np.float32)
     anchors = np.array([0, 1, 1, 0], np.int64)
     out, idx = orc.hash_forward(feat, prim, bias, pts, anchors, want_idx=True)
-    assert idx.min() >= 0 and idx.max() < 16 * local
-    lv = idx // local
-    assert np.array_equal(lv, np.broadcast_to(np.arange(16).reshape(1, 16, 1), lv.shape))
+    # level l reaches rows [l * local / 2, l * local / 2 + local): nothing beyond 8.5 * local
+    base = (np.arange(16) * local // 2).reshape(1, 16, 1)
+    assert np.all(idx >= base) and np.all(idx < base + local) and idx.max() < 17 * local // 2
     # a point exactly on a lattice node takes the value of corner 000 (weights 1,0,..)
     f16 = feat.astype(np.float16).astype(np.float32)
     np.testing.assert_array_equal(out[0, 0:2], f16[idx[0, 0, 0]])
