@@ -52,7 +52,11 @@ int64_t gf_launch_count(void);
  * (field/Hash3DAnchored_cuda.cu:11-79, 81-155, 160-239).
  *
  * Layouts (all row-major, contiguous):
- *   feat_f16   __half [n_levels*local_size, 2]   fp16 shadow of feat_pool
+ *   feat_f16   __half [n_levels*local_size, 2]   fp16 shadow of feat_pool.  Level l reads / scatters rows
+ *              [l*local_size/2, l*local_size/2 + local_size): the reference adds feat_local_idx[l] = l*local_size
+ *              (Hash3DAnchored.cpp:66-70) to a pointer to SCALARS (Hash3DAnchored_cuda.cu:38, :105), so consecutive
+ *              levels overlap by half a window and rows >= 8.5*local_size are never touched.  Reproduced (a table
+ *              trained by the reference only means something under this addressing); local_size must be even.
  *   prim_pool  int32  [16, n_volumes, 3]
  *   bias_pool  float  [16*n_volumes, 3], or NULL = all zeros (what the reference always has,
  *              Hash3DAnchored.cpp:57-62: rand_bias is never set) -- same arithmetic, three loads fewer per level

@@ -8,12 +8,25 @@
  * tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference)
  * do.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, KATs or tests for
- * Hash3DAnchored / PersSampler and its native code cannot be
- * built here (needs un-vendored tiny-cuda-nn and a patched Eigen).  The pieces
- * of the path that ARE importable from the reference (get_weights_f2nerf,
- * renderers, MLPNetwork, trunc_exp, CharbonnierLoss) pin the composite / MLP /
- * loss functions below through tests/golden/ (made by tests/golden/make_golden.py).
+ * HOW PARITY IS PINNED.  The reference ships no golden vectors, KATs or tests
+ * for Hash3DAnchored / PersSampler and its own build cannot
+ * run here (un-vendored tiny-cuda-nn, a patched Eigen).  But its DEVICE CODE
+ * needs neither: `make -C oracle ref` extracts the __global__ / __device__
+ * bodies of Hash3DAnchored_cuda.cu and PersSampler_cuda.cu where they lie under
+ * /root/reference and compiles them for the host between a CUDA shim and a
+ * fixed-size Eigen subset (oracle/ref_driver.cpp, ref_shim/, -> oracle/_ref/).
+ * tests/test_ref_kernels.py holds the hash / traversal / march / vote / cold-
+ * query functions below to that code: live where /root/reference exists, and
+ * through tests/golden/ref_kernels.npz (its outputs) everywhere.  Integer
+ * results are identical; the hash blend is identical bit for bit; the march
+ * agrees to 1e-4 (fp contraction is the compiler's choice: nvcc's for the
+ * reference binary, g++'s for the host build, spelled out here for nvcc).
+ * What stays UNPINNED: the last bit of fp32 results that depend on nvcc's
+ * contraction and on Eigen's evaluation order inside the shim (our reading of
+ * Eigen 3.4), and the tcnn SH-4 encoding (un-vendored third party).
+ * The pieces of the path that are importable Python (get_weights_f2nerf,
+ * renderers, MLPNetwork, trunc_exp, CharbonnierLoss, S3IM, Adam) pin the
+ * composite / MLP / loss functions below through tests/golden/make_golden.py.
  *
  * Floating-point convention (what "bit-exact" means for indices / node ids /
  * sample counts): fp32 everywhere, IEEE div/sqrt, and the FMA contraction nvcc
@@ -335,7 +348,8 @@ static inline float norm3(float x, float y, float z) {
 /*
  * Evaluation order of the reference's fixed-size Eigen expressions (Eigen 3.4.0, scalar device path;
  * restated from the structure of Eigen's Redux.h / ProductEvaluators.h / GeneralProduct.h, from memory --
- * Eigen itself is not in this image, so this stays part of "PARITY UNPINNED"):
+ * Eigen itself is not in this image; oracle/ref_shim/eigen_subset.h implements the same reading, so the
+ * host build of the reference kernels cannot confirm it -- the last-bit part of parity that stays unpinned):
  *   - small products (2x4 * 4x1, 1x2 * 2x3, 3x3 * 3x1, and 3x12 * 12x3 which falls under
  *     EIGEN_GEMM_TO_COEFFBASED_THRESHOLD) are coefficient-based: lhs.row(i).cwiseProduct(rhs.col(j)).sum(),
  *     and a fully unrolled sum() splits its range in halves recursively (redux_novec_unroller):

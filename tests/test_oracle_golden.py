@@ -1,7 +1,7 @@
 """The oracle against golden vectors produced by RUNNING the reference's own Python code
 (tests/golden/make_golden.py: get_weights_f2nerf, the renderers, trunc_exp, MLPNetwork, CharbonnierLoss,
 torch.optim.Adam).  CPU only.  This is what pins the composite / MLP / loss / optimizer part of the oracle;
-Hash3DAnchored and PersSampler stay "parity unpinned" (no reference vectors exist)."""
+Hash3DAnchored and PersSampler are pinned separately, by the reference's own device code (tests/test_ref_kernels.py)."""
 import os
 
 import numpy as np
