@@ -142,3 +142,76 @@ def set_block_idxs(tree_nodes, centers, flavour="off"):
     """In place on tree_nodes."""
     centers = _c(centers, np.float32)
     lib(flavour).ref_set_block_idxs(_i64(tree_nodes.size // 128), _i64(centers.shape[0]), _p(tree_nodes), _p(centers))
+
+
+# ---------------------------------------------------------------- the same bodies compiled by nvcc (GPU box only)
+CUDA_LIB = os.path.join(REF_DIR, "libgf_ref_cuda.so")
+_cuda_lib = None
+
+
+def cuda_available():
+    return os.path.exists(CUDA_LIB)
+
+
+def cuda_lib():
+    """oracle/_ref/libgf_ref_cuda.so (`make -C oracle ref_cuda`): the reference's device functions as real CUDA for
+    sm_100a.  Entry points take torch CUDA tensors' data_ptr()s; see oracle/ref_driver_cuda.cu."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        _cuda_lib = C.CDLL(CUDA_LIB)
+    return _cuda_lib
+
+
+def _dp(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def cuda_hash_forward(feat_f32, prim_pool, bias_pool, pts, anchors):
+    """torch CUDA tensors in, fp32 [n,32] out (Hash3DAnchoredFunction::forward with the reference's casts)."""
+    import torch
+    n, n_vol, local = pts.shape[0], prim_pool.shape[1], feat_f32.shape[0] // 16
+    dev = pts.device
+    table = feat_f32.to(torch.float16).contiguous()
+    fidx = (torch.arange(16, device=dev) * local).to(torch.int32)
+    fsize = torch.full((16,), local, dtype=torch.int32, device=dev)
+    out = torch.zeros((n, 32), dtype=torch.float16, device=dev)
+    rc = cuda_lib().refcu_hash_forward(_int(n), _int(n_vol), _dp(table), _dp(prim_pool.int().contiguous()), _dp(fidx),
+                                       _dp(fsize), _dp(bias_pool.float().contiguous()), _dp(pts.float().contiguous()),
+                                       _dp(anchors.long().contiguous()), _dp(out))
+    assert rc == 0, f"refcu_hash_forward: cudaError {rc}"
+    return out.float()
+
+
+def cuda_hash_backward(local_size, prim_pool, bias_pool, pts, anchors, grad_out):
+    import torch
+    n, n_vol, dev = pts.shape[0], prim_pool.shape[1], pts.device
+    fidx = (torch.arange(16, device=dev) * local_size).to(torch.int32)
+    fsize = torch.full((16,), local_size, dtype=torch.int32, device=dev)
+    gin = (grad_out.float() * 128.0).to(torch.float16).contiguous()
+    gout = torch.zeros((16 * local_size, 2), dtype=torch.float16, device=dev)
+    rc = cuda_lib().refcu_hash_backward(_int(n), _int(n_vol), _dp(prim_pool.int().contiguous()), _dp(fidx), _dp(fsize),
+                                        _dp(bias_pool.float().contiguous()), _dp(pts.float().contiguous()),
+                                        _dp(anchors.long().contiguous()), _dp(gin), _dp(gout))
+    assert rc == 0, f"refcu_hash_backward: cudaError {rc}"
+    return gout.float() / 128.0
+
+
+def cuda_get_samples(rays_o, rays_d_unit, noise, tree_nodes, pers_trans, search_order, global_near=0.01,
+                     sample_l=1.0 / 256, scale_by_dis=True, max_oct=1024):
+    """torch CUDA tensors in; dict of torch CUDA tensors out (dense reference layout)."""
+    import torch
+    R, S, dev = rays_o.shape[0], 1024, rays_o.device
+    z = lambda *sh, dt=torch.float32: torch.zeros(sh, dtype=dt, device=dev)
+    out = dict(world_pts=z(R, S, 3), warp_pts=z(R, S, 3), dirs=z(R, S, 3), dists=z(R, S), ts=z(R, S),
+               anchors=z(R, S, 3, dt=torch.int64), pts_idx_start_end=z(R, 2, dt=torch.int64), first_oct_dis=z(R),
+               oct_idx_start_end=z(R, 2, dt=torch.int64))
+    rc = cuda_lib().refcu_get_samples(
+        _i64(R), _dp(rays_o.float().contiguous()), _dp(rays_d_unit.float().contiguous()), _dp(noise.float().contiguous()),
+        _dp(tree_nodes), _dp(pers_trans), _dp(search_order), _f32(global_near), _f32(sample_l),
+        _int(int(scale_by_dis)), _i64(max_oct), _dp(out["world_pts"]), _dp(out["warp_pts"]), _dp(out["dirs"]),
+        _dp(out["dists"]), _dp(out["ts"]), _dp(out["anchors"]), _dp(out["pts_idx_start_end"]),
+        _dp(out["first_oct_dis"]), _dp(out["oct_idx_start_end"]))
+    assert rc == 0, f"refcu_get_samples: cudaError {rc}"
+    se = out["pts_idx_start_end"]
+    out["counts"] = (se[:, 1] - se[:, 0]).to(torch.int32)
+    return out

@@ -20,11 +20,17 @@
 #include <cmath>
 #include <type_traits>
 
+#ifdef __CUDACC__
+#define GF_HD __host__ __device__
+#else
+#define GF_HD
+#endif
+
 namespace Eigen {
 enum { ColMajor = 0, RowMajor = 1 };
 
 template <typename T, int Start, int Len, typename F>
-inline T tree_sum(const F& term) {
+GF_HD inline T tree_sum(const F& term) {
   if constexpr (Len == 1) {
     return term(Start);
   } else {
@@ -36,12 +42,28 @@ inline T tree_sum(const F& term) {
 template <typename T, int R, int C, int Opt = ColMajor>
 struct Matrix;
 
+GF_HD inline float sqrt_of(float v) { return sqrtf(v); }
+GF_HD inline double sqrt_of(double v) { return sqrt(v); }
+
+template <typename T>
+struct SquareTerm { /* k -> d[k]^2 */
+  const T* d;
+  GF_HD T operator()(int k) const { return d[k] * d[k]; }
+};
+template <typename T, typename A, typename B>
+struct ProductTerm { /* k -> a(i,k) * b(k,j) */
+  const A& a;
+  const B& b;
+  int i, j;
+  GF_HD T operator()(int k) const { return a(i, k) * b(k, j); }
+};
+
 template <typename T, int BR, int BC, typename M>
 struct BlockRef {
   M& m;
   int r0, c0;
   template <int O2>
-  BlockRef& operator=(const Matrix<T, BR, BC, O2>& v) {
+  GF_HD BlockRef& operator=(const Matrix<T, BR, BC, O2>& v) {
     for (int i = 0; i < BR; i++)
       for (int j = 0; j < BC; j++) m(r0 + i, c0 + j) = v(i, j);
     return *this;
@@ -54,39 +76,39 @@ struct Matrix {
 
   Matrix() = default;
   template <int O2>
-  Matrix(const Matrix<T, R, C, O2>& o) {
+  GF_HD Matrix(const Matrix<T, R, C, O2>& o) {
     for (int i = 0; i < R; i++)
       for (int j = 0; j < C; j++) (*this)(i, j) = o(i, j);
   }
   template <int O2>
-  Matrix& operator=(const Matrix<T, R, C, O2>& o) {
+  GF_HD Matrix& operator=(const Matrix<T, R, C, O2>& o) {
     for (int i = 0; i < R; i++)
       for (int j = 0; j < C; j++) (*this)(i, j) = o(i, j);
     return *this;
   }
 
-  static Matrix Zero() {
+  GF_HD static Matrix Zero() {
     Matrix m;
     for (int i = 0; i < R * C; i++) m.d[i] = T(0);
     return m;
   }
 
-  T& operator()(int i, int j) { return d[Opt == RowMajor ? i * C + j : j * R + i]; }
-  const T& operator()(int i, int j) const { return d[Opt == RowMajor ? i * C + j : j * R + i]; }
-  T& operator()(int i) { return d[i]; }
-  const T& operator()(int i) const { return d[i]; }
-  T& operator[](int i) { return d[i]; }
-  const T& operator[](int i) const { return d[i]; }
-  const T& x() const { return d[0]; }
-  const T& y() const { return d[1]; }
-  const T& z() const { return d[2]; }
+  GF_HD T& operator()(int i, int j) { return d[Opt == RowMajor ? i * C + j : j * R + i]; }
+  GF_HD const T& operator()(int i, int j) const { return d[Opt == RowMajor ? i * C + j : j * R + i]; }
+  GF_HD T& operator()(int i) { return d[i]; }
+  GF_HD const T& operator()(int i) const { return d[i]; }
+  GF_HD T& operator[](int i) { return d[i]; }
+  GF_HD const T& operator[](int i) const { return d[i]; }
+  GF_HD const T& x() const { return d[0]; }
+  GF_HD const T& y() const { return d[1]; }
+  GF_HD const T& z() const { return d[2]; }
 
-  Matrix& operator*=(T s) {
+  GF_HD Matrix& operator*=(T s) {
     for (int i = 0; i < R * C; i++) d[i] = d[i] * s;
     return *this;
   }
 
-  Matrix<T, R + 1, 1, ColMajor> homogeneous() const {
+  GF_HD Matrix<T, R + 1, 1, ColMajor> homogeneous() const {
     static_assert(C == 1, "homogeneous(): vectors only");
     Matrix<T, R + 1, 1, ColMajor> h;
     for (int i = 0; i < R; i++) h.d[i] = d[i];
@@ -94,33 +116,33 @@ struct Matrix {
     return h;
   }
 
-  T squaredNorm() const {
-    return tree_sum<T, 0, R * C>([&](int k) { return d[k] * d[k]; });
+  GF_HD T squaredNorm() const {
+    return tree_sum<T, 0, R * C>(SquareTerm<T>{d});
   }
-  T norm() const { return std::sqrt(squaredNorm()); }
+  GF_HD T norm() const { return sqrt_of(squaredNorm()); }
 
   template <int BR, int BC>
-  Matrix<T, BR, BC, RowMajor> block(int r0, int c0) const {
+  GF_HD Matrix<T, BR, BC, RowMajor> block(int r0, int c0) const {
     Matrix<T, BR, BC, RowMajor> b;
     for (int i = 0; i < BR; i++)
       for (int j = 0; j < BC; j++) b(i, j) = (*this)(r0 + i, c0 + j);
     return b;
   }
   template <int BR, int BC>
-  BlockRef<T, BR, BC, Matrix> block(int r0, int c0) {
+  GF_HD BlockRef<T, BR, BC, Matrix> block(int r0, int c0) {
     return BlockRef<T, BR, BC, Matrix>{*this, r0, c0};
   }
 };
 
 template <typename T, int R, int C, int O1, int O2>
-inline Matrix<T, R, C, O1> operator+(const Matrix<T, R, C, O1>& a, const Matrix<T, R, C, O2>& b) {
+GF_HD inline Matrix<T, R, C, O1> operator+(const Matrix<T, R, C, O1>& a, const Matrix<T, R, C, O2>& b) {
   Matrix<T, R, C, O1> r;
   for (int i = 0; i < R; i++)
     for (int j = 0; j < C; j++) r(i, j) = a(i, j) + b(i, j);
   return r;
 }
 template <typename T, int R, int C, int O1, int O2>
-inline Matrix<T, R, C, O1> operator-(const Matrix<T, R, C, O1>& a, const Matrix<T, R, C, O2>& b) {
+GF_HD inline Matrix<T, R, C, O1> operator-(const Matrix<T, R, C, O1>& a, const Matrix<T, R, C, O2>& b) {
   Matrix<T, R, C, O1> r;
   for (int i = 0; i < R; i++)
     for (int j = 0; j < C; j++) r(i, j) = a(i, j) - b(i, j);
@@ -128,18 +150,18 @@ inline Matrix<T, R, C, O1> operator-(const Matrix<T, R, C, O1>& a, const Matrix<
 }
 /* matrix (op) scalar: a scalar of another arithmetic type is converted to T first (Eigen's promote_scalar_arg) */
 template <typename T, int R, int C, int O, typename U, typename = std::enable_if_t<std::is_arithmetic<U>::value>>
-inline Matrix<T, R, C, O> operator*(const Matrix<T, R, C, O>& a, U s_) {
+GF_HD inline Matrix<T, R, C, O> operator*(const Matrix<T, R, C, O>& a, U s_) {
   const T s = (T)s_;
   Matrix<T, R, C, O> r;
   for (int i = 0; i < R * C; i++) r.d[i] = a.d[i] * s;
   return r;
 }
 template <typename T, int R, int C, int O, typename U, typename = std::enable_if_t<std::is_arithmetic<U>::value>>
-inline Matrix<T, R, C, O> operator*(U s, const Matrix<T, R, C, O>& a) {
+GF_HD inline Matrix<T, R, C, O> operator*(U s, const Matrix<T, R, C, O>& a) {
   return a * s;
 }
 template <typename T, int R, int C, int O, typename U, typename = std::enable_if_t<std::is_arithmetic<U>::value>>
-inline Matrix<T, R, C, O> operator/(const Matrix<T, R, C, O>& a, U s_) {
+GF_HD inline Matrix<T, R, C, O> operator/(const Matrix<T, R, C, O>& a, U s_) {
   const T s = (T)s_;
   Matrix<T, R, C, O> r;
   for (int i = 0; i < R * C; i++) r.d[i] = a.d[i] / s;
@@ -148,7 +170,7 @@ inline Matrix<T, R, C, O> operator/(const Matrix<T, R, C, O>& a, U s_) {
 
 /* [R x K] * [K x C] */
 template <typename T, int R, int K, int C, int O1, int O2>
-inline Matrix<T, R, C, (C == 1 ? ColMajor : RowMajor)> operator*(const Matrix<T, R, K, O1>& a,
+GF_HD inline Matrix<T, R, C, (C == 1 ? ColMajor : RowMajor)> operator*(const Matrix<T, R, K, O1>& a,
                                                                  const Matrix<T, K, C, O2>& b) {
   Matrix<T, R, C, (C == 1 ? ColMajor : RowMajor)> r;
   for (int i = 0; i < R; i++)
@@ -158,7 +180,7 @@ inline Matrix<T, R, C, (C == 1 ? ColMajor : RowMajor)> operator*(const Matrix<T,
         for (int k = 1; k < K; k++) acc = acc + a(i, k) * b(k, j);
         r(i, j) = acc;
       } else {
-        r(i, j) = tree_sum<T, 0, K>([&](int k) { return a(i, k) * b(k, j); });
+        r(i, j) = tree_sum<T, 0, K>(ProductTerm<T, Matrix<T, R, K, O1>, Matrix<T, K, C, O2>>{a, b, i, j});
       }
     }
   return r;

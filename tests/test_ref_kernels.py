@@ -256,3 +256,64 @@ def test_cuda_sampler_counts_and_anchors_are_the_reference_kernels(fx, rig, mode
     rel_close(dists.cpu().numpy()[m], fx[f"s_{mode}_dists"], 1e-4, "dist")
     assert np.abs(warp.cpu().numpy()[m] - fx[f"s_{mode}_warp_pts"]).max() <= 2e-4
     assert np.array_equal(first.cpu().numpy().reshape(-1), fx[f"s_{mode}_first_oct_dis"])
+
+
+# ------------------------------------------------------------------ GPU, opt-in: beside the reference's kernels built by nvcc
+# `make -C oracle ref_cuda` (build container) + GF_REF_CUDA=1 on the GPU box.  Opt-in because it was written when no
+# GPU minutes were left to run it once; it reports bit-equality fractions rather than asserting them where nvcc's
+# contraction inside the Eigen subset is the open question.
+ref_cuda = pytest.mark.skipif(not (os.environ.get("GF_REF_CUDA") and rh.cuda_available()),
+                              reason="opt-in: GF_REF_CUDA=1 and oracle/_ref/libgf_ref_cuda.so")
+
+
+@pytest.mark.gpu
+@ref_cuda
+def test_cuda_beside_the_reference_kernels_built_by_nvcc(rig):
+    import torch
+    from gfnerf_b200 import _lib
+    from gfnerf_b200.persoctree import rig_rays
+    from tests.helpers import make_sampler
+    dev = "cuda"
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    # hash forward: same table, points, primes -> bit-identical encodings
+    feat, prim, bias, pts, anchors = hash_inputs(200000, 7, 16, seed=3, along_rays=True)
+    L = feat.shape[0] // 16
+    ref = rh.cuda_hash_forward(T(feat), T(prim.astype(np.int32)), T(bias), T(pts), T(anchors))
+    scales_d, scales_h = torch.empty(16, device=dev), np.zeros(16, np.float32)
+    _lib.check(_lib.lib().gf_hash_level_scales(_lib.ptr(scales_d), scales_h.ctypes.data, _lib.cur_stream()))
+    f16 = T(feat).half().contiguous()
+    tp, ta, tprim, tbias = T(pts), T(anchors), T(prim.astype(np.int32)), T(bias)
+    out = torch.empty((pts.shape[0], 32), device=dev)
+    _lib.check(_lib.lib().gf_hash_forward(pts.shape[0], None, 7, L, _lib.ptr(f16), _lib.ptr(tprim), _lib.ptr(tbias),
+                                          _lib.ptr(scales_d), _lib.ptr(tp), _lib.ptr(ta), 1, None, _lib.ptr(out),
+                                          _lib.cur_stream()))
+    torch.cuda.synchronize()
+    print("hash forward bit-equal fraction vs nvcc-built reference:", float((out == ref).float().mean()))
+    assert torch.equal(out, ref)
+    # sampler: leaf ranges, counts and anchors identical; positions reported
+    s = make_sampler(rig, mode=1)
+    R = 4096
+    o, d, _ = rig_rays(rig["c2w"], rig["intri"], R, seed=77)
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    noise = T(np.random.RandomState(5).uniform(0.5, 1.5, S + R + 10).astype(np.float32))
+    r = rh.cuda_get_samples(T(o), T(d), noise, s.tree_nodes_gpu_, s.pers_trans_gpu_, T(orc.search_order()))
+    z = lambda *sh, dt=torch.float32: torch.zeros(sh, dtype=dt, device=dev)
+    world, warp, dirs, anc = z(R, S, 3), z(R, S, 3), z(R, S, 3), z(R, S, 3, dt=torch.int64)
+    dists, ts, se, first, cnt = z(R, S), z(R, S), z(R, 2, dt=torch.int64), z(R, 1), z(R, dt=torch.int32)
+    so = _lib.SamplerOut(world_pts=_lib.ptr(world), warp_pts=_lib.ptr(warp), dirs=_lib.ptr(dirs),
+                         dists=_lib.ptr(dists), ts=_lib.ptr(ts), anchors_i64=_lib.ptr(anc), anchors_i32=None,
+                         pts_idx_start_end=_lib.ptr(se), counts=_lib.ptr(cnt), first_oct_dis=_lib.ptr(first),
+                         n_oct=None, packed=None)
+    s._launch(T(o), T(d), noise, so)
+    torch.cuda.synchronize()
+    same = (cnt == r["counts"])
+    print("sampler: rays with identical sample counts:", float(same.float().mean()), "of", R)
+    m = (torch.arange(S, device=dev)[None, :] < cnt[:, None]) & same[:, None]
+    for name, a, b in (("t", ts, r["ts"]), ("dist", dists, r["dists"]), ("warp", warp, r["warp_pts"]),
+                       ("world", world, r["world_pts"])):
+        mm = m if a.dim() == 2 else m[..., None].expand_as(a)
+        print(f"  {name}: bit-equal fraction {float((a[mm] == b[mm]).float().mean()):.6f}, "
+              f"max abs diff {float((a[mm] - b[mm]).abs().max()):.3e}")
+    assert float(same.float().mean()) > 0.999
+    assert torch.equal(anc[m], r["anchors"][m])
+    assert torch.equal(first.view(-1), r["first_oct_dis"])
