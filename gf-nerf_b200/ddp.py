@@ -33,6 +33,29 @@ def shard_slice(n_items: int, rank: int, world: int) -> slice:
     return slice(lo, lo + base + (1 if rank < rem else 0))
 
 
+def table_level_rows(local_size: int, level: int, n_levels: int = 16):
+    """Rows [lo, hi) of the hash table that level `level` reads and scatters into.  The reference adds the per-level
+    offset level * local_size to a pointer to SCALARS (Hash3DAnchored_cuda.cu:38,105), so the window starts at row
+    level * local_size / 2 and consecutive levels overlap by half (csrc/hash_common.cuh level_base_row)."""
+    lo = (int(level) * int(local_size)) // 2
+    return lo, lo + int(local_size)
+
+
+def table_reduce_ranges(local_size: int, level_group: int, n_levels: int = 16):
+    """Row ranges to all-reduce after each group of `level_group` levels has been scattered, levels ascending:
+    [(l0, l1, row_lo, row_hi)].  A row is handed over once no later level can still add to it: after levels < l1
+    that is every row below level l1's window; the last group takes what is left of the reachable rows.  The ranges
+    are disjoint and cover exactly [0, (n_levels - 1) * local_size / 2 + local_size) -- the rows beyond are never
+    touched on any rank and need no exchange."""
+    out = []
+    for l0 in range(0, n_levels, level_group):
+        l1 = min(l0 + level_group, n_levels)
+        lo = table_level_rows(local_size, l0)[0]
+        hi = table_level_rows(local_size, l1)[0] if l1 < n_levels else table_level_rows(local_size, n_levels - 1)[1]
+        out.append((l0, l1, lo, hi))
+    return out
+
+
 class FlatBucket:
     """Several small tensors carved out of ONE flat buffer, so that one collective covers all of them
     (MLP + appearance-embedding gradients: ~100 KB, latency-bound as separate messages)."""

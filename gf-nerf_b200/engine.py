@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ddp import FlatBucket, GradSync
+from .ddp import FlatBucket, GradSync, table_reduce_ranges
 from .hash_3d_anchored import Hash3DAnchoredCore
 from .perssampler import CompactSamples, PersSamplerCore
 
@@ -416,14 +416,11 @@ class GFNeRFEngine:
                     # (level_base_row: windows overlap by half), so once levels < l1 are scattered the rows below
                     # l1*T/2 are final; the last group takes the rest of the reachable rows.
                     self.sync.start_sum([self._small_grads])
-                    half = self.enc.local_size_ // 2
                     with self._stage("hash_bwd"):
-                        for l0 in range(0, 16, self.LEVEL_GROUP):
-                            l1 = min(l0 + self.LEVEL_GROUP, 16)
+                        for l0, l1, r0, r1 in table_reduce_ranges(self.enc.local_size_, self.LEVEL_GROUP):
                             self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, g_table, d_n_ptr=cs.total,
                                                      keep_x128=True, levels=(l0, l1))
-                            r1 = l1 * half if l1 < 16 else self.enc.used_rows_
-                            self.sync.start_sum([g_table[l0 * half:r1]])
+                            self.sync.start_sum([g_table[r0:r1]])
                     self._deferred = lr_scale
                 else:
                     with self._stage("hash_bwd"):

@@ -96,3 +96,60 @@ def test_single_process_is_a_no_op():
     assert shard_slice(10, 0, 1) == slice(0, 10)
     covered = sum((list(range(*shard_slice(10, k, 4).indices(10))) for k in range(4)), [])
     assert covered == list(range(10))
+
+
+def test_table_reduce_ranges_cover_the_reachable_rows_once():
+    from gfnerf_b200.ddp import table_level_rows, table_reduce_ranges
+    T = 1 << 10
+    assert table_level_rows(T, 0) == (0, T) and table_level_rows(T, 1) == (T // 2, T // 2 + T)   # half-overlapping
+    for group in (1, 2, 4, 8, 16):
+        rr = table_reduce_ranges(T, group)
+        assert rr[0][2] == 0 and rr[-1][3] == 15 * T // 2 + T == 17 * T // 2
+        assert all(a[3] == b[2] and a[1] == b[0] for a, b in zip(rr, rr[1:]))                    # contiguous, disjoint
+        for l0, l1, lo, hi in rr:
+            # nothing a LATER level can still write lies inside a range that is handed over
+            assert all(table_level_rows(T, l)[0] >= hi for l in range(l1, 16))
+            # and everything levels < l1 wrote that was not handed over earlier is inside or comes later
+            assert lo == table_level_rows(T, l0)[0]
+    assert table_reduce_ranges(48 * 16, 16) == [(0, 16, 0, 17 * 48 * 8)]
+
+
+def _worker_groups(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gfnerf_b200.ddp import GradSync, table_level_rows, table_reduce_ranges
+        sync = GradSync(dist.group.WORLD, torch.device("cpu"))
+        T = 256
+        rng = np.random.RandomState(7 + rank)
+        contrib = []                                   # per level: (rows, values) this rank scatters
+        for l in range(16):
+            lo, hi = table_level_rows(T, l)
+            contrib.append((torch.from_numpy(rng.randint(lo, hi, size=300)), torch.from_numpy(rng.normal(size=(300, 2)))))
+        results = {}
+        for group in (16, 4, 1):
+            g = torch.zeros(16 * T, 2, dtype=torch.float64)
+            for l0, l1, r0, r1 in table_reduce_ranges(T, group):
+                for l in range(l0, l1):                # the scatter of this level group
+                    g.index_add_(0, contrib[l][0], contrib[l][1])
+                sync.start_sum([g[r0:r1]])             # exactly what GFNeRFEngine.train_step hands over
+            sync.wait()
+            results[group] = g
+        torch.save(results, os.path.join(out_dir, f"groups{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_level_group_exchange_equals_one_shot_exchange(tmp_path):
+    """With the reference's half-overlapping level windows a level group is no longer a private row range; the ranges
+    of table_reduce_ranges still give every rank the same total as one all-reduce after the whole scatter."""
+    world = 2
+    mp.spawn(_worker_groups, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"groups{k}.pt")) for k in range(world)]
+    assert torch.equal(r[0][16], r[1][16]) and float(r[0][16].abs().sum()) > 0
+    assert not r[0][16][17 * 256 // 2:].any()                       # rows past 8.5 T: never touched
+    for group in (4, 1):
+        for k in range(world):
+            assert torch.allclose(r[k][group], r[0][16], rtol=0, atol=1e-12)
