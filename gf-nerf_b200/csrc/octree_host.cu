@@ -168,9 +168,20 @@ extern "C" int gf_octree_proc(const void* nodes_in, int64_t n_in, const int64_t*
   std::vector<int64_t> nw(inv_idx.size()), na(inv_idx.size());
   for (size_t i = 0; i < inv_idx.size(); i++) {
     nn[i] = nb[(size_t)inv_idx[i]];  // byte copy: padding travels with the node
-    if (nn[i].parent >= 0) nn[i].parent = new_idx[(size_t)nn[i].parent];
+    // CHECK_GE(node.parent, 0) / CHECK_GE(node.childs[st], 0), PersSampler.cpp:307,315: the reference aborts when a
+    // removed node is still linked, which is what ProcOctree without `compact` does on a tree with pruned leaves
+    if (nn[i].parent >= 0) {
+      nn[i].parent = new_idx[(size_t)nn[i].parent];
+      GF_REQUIRE(nn[i].parent >= 0, "gf_octree_proc: the parent of node %lld was removed (compact = 0 on a pruned tree?)",
+                 (long long)inv_idx[i]);
+    }
     for (int k = 0; k < 8; k++)
-      if (nn[i].childs[k] >= 0) nn[i].childs[k] = new_idx[(size_t)nn[i].childs[k]];
+      if (nn[i].childs[k] >= 0) {
+        nn[i].childs[k] = new_idx[(size_t)nn[i].childs[k]];
+        GF_REQUIRE(nn[i].childs[k] >= 0,
+                   "gf_octree_proc: a removed node is still linked from node %lld (compact = 0 on a pruned tree?)",
+                   (long long)inv_idx[i]);
+      }
     nw[i] = weight_stats_in[inv_idx[i]];
     na[i] = alpha_stats_in[inv_idx[i]];
   }

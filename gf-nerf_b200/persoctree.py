@@ -351,6 +351,10 @@ class PersOctree:
         nn["parent"][pm] = new_idx[nn["parent"][pm]]
         cm = nn["childs"] >= 0
         nn["childs"][cm] = new_idx[nn["childs"][cm]]
+        if (nn["parent"][pm] < 0).any() or (nn["childs"][cm] < 0).any():
+            # the reference's CHECK_GE(node.parent, 0) / CHECK_GE(node.childs[st], 0), PersSampler.cpp:307,315: a
+            # pruned leaf still linked from its parent, i.e. ProcOctree without `compact` on a tree with pruned leaves
+            raise RuntimeError("ProcOctree: a removed node is still linked (call it with compact=True)")
         nw, na = w_before[keep].copy(), a_before[keep].copy()
         if subdivide:
             out_nodes, out_w, out_a = [], [], []

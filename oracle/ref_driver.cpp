@@ -215,3 +215,62 @@ void ref_set_block_idxs(int64_t n_nodes, int64_t n_blocks, void* tree_nodes, flo
 int64_t ref_sizeof_edge_pool(void) { return (int64_t)sizeof(EdgePool); }
 
 } /* extern "C" */
+
+/* ---- host member functions of PersOctree, PtsSampler/PersSampler.cpp:154-417, 833-895 ----------------------------
+ * The class below declares only the members those two bodies touch (PtsSampler/PersSampler.h:51-95); the bodies
+ * themselves are the reference's text (ref_host_fns.inc), compiled against ref_shim/torch_stub.h. */
+#include "ref_shim/torch_stub.h"
+
+class PersOctree {
+  using Tensor = torch::Tensor;
+
+ public:
+  void ProcOctree(bool compact, bool subdivide, bool brute_force);
+  void ConstructEdgePool();
+  std::vector<TreeNode> tree_nodes_;
+  std::vector<EdgePool> edge_pool_;
+  Tensor tree_nodes_gpu_, tree_weight_stats_, tree_alpha_stats_, tree_visit_cnt_;
+};
+
+#include "_ref/ref_host_fns.inc"
+
+extern "C" {
+
+/* PersOctree::ProcOctree on blobs.  Call with nodes_out == NULL to learn the node count, then again with buffers of
+ * that size (the function is deterministic).  Returns the new node count, or -(line) of a failed reference CHECK. */
+int64_t ref_proc_octree(const void* nodes_in, int64_t n_in, const int64_t* weight_stats, const int64_t* alpha_stats,
+                        const int64_t* visit_cnt, int compact, int subdivide, int brute_force, void* nodes_out,
+                        int64_t* weight_out, int64_t* alpha_out, int64_t capacity) {
+  PersOctree oc;
+  oc.tree_nodes_.resize((size_t)n_in);
+  std::memcpy((void*)oc.tree_nodes_.data(), nodes_in, (size_t)n_in * sizeof(TreeNode));
+  oc.tree_nodes_gpu_ = torch::from_blob((void*)nodes_in, {n_in * (int64_t)sizeof(TreeNode)}, CPUUInt8);
+  oc.tree_weight_stats_ = torch::from_blob((void*)weight_stats, {n_in}, CPUInt64);
+  oc.tree_alpha_stats_ = torch::from_blob((void*)alpha_stats, {n_in}, CPUInt64);
+  oc.tree_visit_cnt_ = torch::from_blob((void*)visit_cnt, {n_in}, CPUInt64);
+  try {
+    oc.ProcOctree(compact != 0, subdivide != 0, brute_force != 0);
+  } catch (const RefCheckFailure& f) {
+    return -(int64_t)f.line;
+  }
+  const int64_t n = (int64_t)oc.tree_nodes_.size();
+  if (nodes_out && n <= capacity) {
+    std::memcpy(nodes_out, oc.tree_nodes_gpu_.data_ptr(), (size_t)n * sizeof(TreeNode));
+    std::memcpy(weight_out, oc.tree_weight_stats_.data_ptr(), (size_t)n * 8);
+    std::memcpy(alpha_out, oc.tree_alpha_stats_.data_ptr(), (size_t)n * 8);
+  }
+  return n;
+}
+
+/* PersOctree::ConstructEdgePool on a node blob; same two-call protocol.  Returns the number of 64-byte entries. */
+int64_t ref_construct_edge_pool(const void* nodes_in, int64_t n_in, void* pool_out, int64_t capacity) {
+  PersOctree oc;
+  oc.tree_nodes_.resize((size_t)n_in);
+  std::memcpy((void*)oc.tree_nodes_.data(), nodes_in, (size_t)n_in * sizeof(TreeNode));
+  oc.ConstructEdgePool();
+  const int64_t n = (int64_t)oc.edge_pool_.size();
+  if (pool_out && n <= capacity) std::memcpy(pool_out, oc.edge_pool_.data(), (size_t)n * sizeof(EdgePool));
+  return n;
+}
+
+} /* extern "C" */

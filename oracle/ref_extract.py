@@ -15,8 +15,12 @@ What is extracted, verbatim and in file order:
                                                         CheckVisible, MarkInvisibleNodesKernel
   * the `#define` constants those bodies use (the two .cu files, PersSampler.h, Hash3DAnchored.h, Utils/Common.h)
   * `struct alignas(32) TransInfo / TreeNode / EdgePool` of PtsSampler/PersSampler.h.
-The host functions of those files (torch tensors, `<<< >>>` launches) are NOT extracted: the launch sequence of
-PersSampler::GetSamples (PersSampler_cuda.cu:321-477) is restated in ref_driver.cpp.
+  * two HOST member functions of PtsSampler/PersSampler.cpp, into a second include (ref_host_fns.inc):
+      PersOctree::ProcOctree (:154-417, compaction / path compression / subdivision of the node array) and
+      PersOctree::ConstructEdgePool (:833-895) -- plain C++ over std::vector<TreeNode> apart from a torch
+      prologue / epilogue, which compiles against the stand-in Tensor of ref_shim/torch_stub.h.
+The other host functions of those files (torch tensor code, `<<< >>>` launches) are NOT extracted: the launch
+sequence of PersSampler::GetSamples (PersSampler_cuda.cu:321-477) is restated in ref_driver.cpp.
 
 Why the reference's own build cannot be used: it needs un-vendored External/tiny-cuda-nn and a
 locally patched External/eigen-3.4.0.  The device code itself needs neither tcnn nor torch, only a handful of
@@ -93,6 +97,23 @@ def device_functions(path):
     return found
 
 
+def host_function(path, signature_start):
+    """(first_line, last_line, text) of the top-level definition that starts with `signature_start`."""
+    src = open(path, encoding="utf-8", errors="replace").read()
+    clean = strip_comments_keep_lines(src)
+    start = clean.index(signature_start)
+    j, depth = clean.index("{", start), 0
+    while True:
+        if clean[j] == "{":
+            depth += 1
+        elif clean[j] == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    return src.count("\n", 0, start) + 1, src.count("\n", 0, j) + 1, src[start:j + 1]
+
+
 def defines(path):
     return [l.rstrip() for l in open(path, encoding="utf-8", errors="replace") if DEFINE_OK.match(l)]
 
@@ -129,6 +150,17 @@ def main():
             manifest.append(f"{os.path.relpath(p, REF)}:{first}-{last} {name}")
     with open(os.path.join(OUT_DIR, "ref_kernels.inc"), "w") as f:
         f.write("\n".join(parts) + "\n")
+    # host member functions of PersOctree that are plain C++ over std::vector<TreeNode> between a torch prologue and
+    # epilogue (PtsSampler/PersSampler.cpp): compiled by ref_driver.cpp against a stand-in Tensor (ref_shim/torch_stub.h)
+    samp_cpp = os.path.join(BIND, "PtsSampler", "PersSampler.cpp")
+    hparts = ["// GENERATED by oracle/ref_extract.py from the reference tree -- build output, never committed.\n"]
+    for sig in ("void PersOctree::ProcOctree(", "void PersOctree::ConstructEdgePool("):
+        first, last, text = host_function(samp_cpp, sig)
+        hparts.append(f"// ---- {os.path.relpath(samp_cpp, REF)}:{first}-{last}")
+        hparts.append(text)
+        manifest.append(f"{os.path.relpath(samp_cpp, REF)}:{first}-{last} {sig[5:-1]}")
+    with open(os.path.join(OUT_DIR, "ref_host_fns.inc"), "w") as f:
+        f.write("\n".join(hparts) + "\n")
     with open(os.path.join(OUT_DIR, "ref_manifest.txt"), "w") as f:
         f.write("\n".join(manifest) + "\n")
     print("\n".join(manifest))

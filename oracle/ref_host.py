@@ -215,3 +215,32 @@ def cuda_get_samples(rays_o, rays_d_unit, noise, tree_nodes, pers_trans, search_
     se = out["pts_idx_start_end"]
     out["counts"] = (se[:, 1] - se[:, 0]).to(torch.int32)
     return out
+
+
+# ---------------------------------------------------------------- host member functions of PersOctree
+def proc_octree(tree_nodes, weight_stats, alpha_stats, visit_cnt, compact, subdivide, brute_force, flavour="off"):
+    """PersOctree::ProcOctree (PtsSampler/PersSampler.cpp:154-417), the reference's own body.  -> (nodes blob uint8,
+    weight_stats, alpha_stats) of the processed tree."""
+    L = lib(flavour)
+    L.ref_proc_octree.restype = C.c_int64
+    nodes = _c(tree_nodes, np.uint8)
+    n_in = nodes.size // 128
+    w, a, v = _c(weight_stats, np.int64), _c(alpha_stats, np.int64), _c(visit_cnt, np.int64)
+    args = (_p(nodes), _i64(n_in), _p(w), _p(a), _p(v), _int(int(compact)), _int(int(subdivide)), _int(int(brute_force)))
+    n = L.ref_proc_octree(*args, None, None, None, _i64(0))
+    if n < 0:
+        raise RuntimeError(f"a CHECK of the reference's ProcOctree failed (ref_host_fns.inc line {-n})")
+    out, wo, ao = np.zeros(n * 128, np.uint8), np.zeros(n, np.int64), np.zeros(n, np.int64)
+    assert L.ref_proc_octree(*args, _p(out), _p(wo), _p(ao), _i64(n)) == n
+    return out, wo, ao
+
+
+def construct_edge_pool(tree_nodes, flavour="off"):
+    """PersOctree::ConstructEdgePool (PersSampler.cpp:833-895).  -> uint8 blob of 64-byte EdgePool entries."""
+    L = lib(flavour)
+    L.ref_construct_edge_pool.restype = C.c_int64
+    nodes = _c(tree_nodes, np.uint8)
+    n = L.ref_construct_edge_pool(_p(nodes), _i64(nodes.size // 128), None, _i64(0))
+    pool = np.zeros(max(n, 1) * 64, np.uint8)
+    assert L.ref_construct_edge_pool(_p(nodes), _i64(nodes.size // 128), _p(pool), _i64(n)) == n
+    return pool[:n * 64]

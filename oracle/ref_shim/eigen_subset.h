@@ -75,6 +75,7 @@ struct Matrix {
   T d[R * C];
 
   Matrix() = default;
+  GF_HD Matrix(T a, T b, T c) : d{a, b, c} { static_assert(R * C == 3, "three-coefficient constructor"); }
   template <int O2>
   GF_HD Matrix(const Matrix<T, R, C, O2>& o) {
     for (int i = 0; i < R; i++)
@@ -120,6 +121,17 @@ struct Matrix {
     return tree_sum<T, 0, R * C>(SquareTerm<T>{d});
   }
   GF_HD T norm() const { return sqrt_of(squaredNorm()); }
+
+  GF_HD Matrix cwiseAbs() const {
+    Matrix r;
+    for (int i = 0; i < R * C; i++) r.d[i] = d[i] < T(0) ? -d[i] : d[i];
+    return r;
+  }
+  GF_HD T maxCoeff() const {
+    T m = d[0];
+    for (int i = 1; i < R * C; i++) m = d[i] > m ? d[i] : m;
+    return m;
+  }
 
   template <int BR, int BC>
   GF_HD Matrix<T, BR, BC, RowMajor> block(int r0, int c0) const {

@@ -115,6 +115,19 @@ def main(flavour="fma"):
     ecoord = rng.uniform(-1, 1, size=(300, 2)).astype(np.float32)
     epts, eids = rh.edge_samples(pool, rig["pers_trans"], eidx, ecoord, flavour)
     fx.update({"e_idx": eidx, "e_coord": ecoord, "e_pts": epts, "e_ids": eids})
+    # ---- PersOctree::ProcOctree / ConstructEdgePool (host functions): digests of the reference's outputs
+    import hashlib
+    from tests.test_ref_kernels import _history
+    hrng = np.random.RandomState(5)
+    for trial in range(3):
+        nodes, w, a, v = _history(rig, trial, hrng)
+        for tag, flags in (("c", (True, False, False)), ("cs", (True, True, False)), ("csb", (True, True, True))):
+            out = rh.proc_octree(nodes, w, a, v, *flags, flavour=flavour)
+            fx[f"o_{trial}_{tag}"] = np.array([out[0].size // 128] + [int(hashlib.sha256(x.tobytes()).hexdigest()[:15], 16)
+                                                                      for x in out], np.int64)
+    ep = rh.construct_edge_pool(rig["tree_nodes"], flavour)
+    used = np.arange(ep.size) % 64 < 52
+    fx["o_edge_pool"] = np.array([ep.size // 64, int(hashlib.sha256(ep[used].tobytes()).hexdigest()[:15], 16)], np.int64)
     path = os.path.join(HERE, "ref_kernels.npz")
     np.savez_compressed(path, **fx)
     print("wrote", path, os.path.getsize(path) >> 10, "KiB;", rh.lib(flavour).ref_build_flavour().decode())

@@ -51,6 +51,16 @@ def test_matches_numpy_restatement(compact, subdivide, brute):
         oc.weight_stats = rng.randint(-100, 5000, size=n).astype(np.int64)
         oc.alpha_stats = rng.randint(-100, 5000, size=n).astype(np.int64)
         oc.visit_cnt = rng.randint(0, 12, size=n).astype(np.int64)
+        if not compact:
+            # pruned leaves stay linked from their parents without the compaction pass: the reference's
+            # CHECK_GE(node.childs[st], 0) (PersSampler.cpp:315) aborts, and so do both implementations here
+            with pytest.raises(RuntimeError):
+                _cxx(oc, compact, subdivide, brute)
+            with pytest.raises(RuntimeError):
+                oc.proc_octree(compact, subdivide, brute)
+            oc.proc_octree(True, False, False)     # a compacted tree (no pruned leaf left) goes through
+            n = oc.nodes.shape[0]
+            oc.visit_cnt = rng.randint(0, 12, size=n).astype(np.int64)
         got_nodes, got_w, got_a = _cxx(oc, compact, subdivide, brute)
         oc.proc_octree(compact, subdivide, brute)
         ref_nodes = np.ascontiguousarray(oc.nodes).view(np.uint8).reshape(-1)

@@ -206,6 +206,92 @@ def test_live_block_index_and_visibility_kernels(rig):
     assert (got == want).mean() > 0.999                                      # ties / fp32-vs-fp64 norm aside
 
 
+def _history(rig, trial, rng):
+    """A training history on the rig's tree: some leaves voted empty, random statistics and visit counts."""
+    nodes = rig["tree_nodes"].copy()
+    tidx = nodes.view(np.int64).reshape(-1, 16)[:, 12]
+    n = tidx.shape[0]
+    leaves = np.nonzero(tidx >= 0)[0]
+    tidx[rng.choice(leaves, size=int(len(leaves) * (0.2 + 0.3 * trial)), replace=False)] = -1
+    return (nodes, rng.randint(-100, 5000, size=n).astype(np.int64), rng.randint(-100, 5000, size=n).astype(np.int64),
+            rng.randint(0, 12, size=n).astype(np.int64))
+
+
+def _our_proc_octree(nodes, w, a, v, compact, subdivide, brute):
+    import ctypes as C
+    from gfnerf_b200 import _lib
+    L, n_out = _lib.lib(), C.c_int64(0)
+    args = (nodes.ctypes.data, nodes.size // 128, w.ctypes.data, a.ctypes.data, v.ctypes.data, int(compact),
+            int(subdivide), int(brute))
+    _lib.check(L.gf_octree_proc(*args, None, None, None, 0, C.byref(n_out)))
+    n = n_out.value
+    o_nodes, o_w, o_a = np.empty(n * 128, np.uint8), np.empty(n, np.int64), np.empty(n, np.int64)
+    _lib.check(L.gf_octree_proc(*args, o_nodes.ctypes.data, o_w.ctypes.data, o_a.ctypes.data, n, C.byref(n_out)))
+    return o_nodes, o_w, o_a
+
+
+def test_proc_octree_and_edge_pool_match_the_reference_digests(fx, rig):
+    """gf_octree_proc / gf_octree_edge_pool against digests of what the reference's own PersOctree::ProcOctree and
+    ConstructEdgePool bodies produced on the same inputs (node count + sha256 of node blob / weight / alpha stats)."""
+    import hashlib
+    from tests.golden.make_golden_ref_kernels import edge_pool_of
+    dig = lambda x: int(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()[:15], 16)
+    rng = np.random.RandomState(5)
+    for trial in range(3):
+        nodes, w, a, v = _history(rig, trial, rng)
+        for tag, flags in (("c", (True, False, False)), ("cs", (True, True, False)), ("csb", (True, True, True))):
+            out = _our_proc_octree(nodes, w, a, v, *flags)
+            assert [out[0].size // 128] + [dig(x) for x in out] == fx[f"o_{trial}_{tag}"].tolist(), (trial, tag)
+    ep = edge_pool_of(rig["tree_nodes"])
+    used = np.arange(ep.size) % 64 < 52
+    assert [ep.size // 64, dig(ep[used])] == fx["o_edge_pool"].tolist()
+
+
+@live
+@pytest.mark.parametrize("compact,subdivide,brute", [(True, False, False), (True, True, False), (True, True, True),
+                                                      (False, True, False), (False, False, False)])
+def test_live_proc_octree_is_the_reference_function(rig, compact, subdivide, brute):
+    """gf_octree_proc (csrc/octree_host.cu) against the reference's own PersOctree::ProcOctree body
+    (PtsSampler/PersSampler.cpp:154-417) on the same blobs: node array byte for byte, statistics identical; and the
+    milestone sequence of UpdateOctNodes (:662-667): ProcOctree(true, true, .) then ProcOctree(true, false, false)."""
+    rng = np.random.RandomState(5)
+    for trial in range(3):
+        nodes, w, a, v = _history(rig, trial, rng)
+        if not compact:
+            # without the compaction pass pruned leaves stay linked: the reference's CHECK_GE (PersSampler.cpp:315)
+            # aborts -- and so does ours; a compacted tree goes through both
+            with pytest.raises(RuntimeError, match="CHECK"):
+                rh.proc_octree(nodes, w, a, v, compact, subdivide, brute)
+            with pytest.raises(RuntimeError, match="removed"):
+                _our_proc_octree(nodes, w, a, v, compact, subdivide, brute)
+            nodes, w, a = rh.proc_octree(nodes, w, a, v, True, False, False)
+            v = rng.randint(0, 12, size=w.shape[0]).astype(np.int64)
+        ref = rh.proc_octree(nodes, w, a, v, compact, subdivide, brute)
+        got = _our_proc_octree(nodes, w, a, v, compact, subdivide, brute)
+        assert got[0].size == ref[0].size
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        if subdivide:   # the second call of a milestone, on the first call's output (visit counts restart at 0)
+            z = np.zeros(ref[1].shape[0], np.int64)
+            ref2 = rh.proc_octree(ref[0], ref[1], ref[2], z, True, False, False)
+            got2 = _our_proc_octree(got[0], got[1], got[2], z, True, False, False)
+            assert all(np.array_equal(x, y) for x, y in zip(got2, ref2))
+
+
+@live
+def test_live_edge_pool_is_the_reference_function(rig):
+    """gf_octree_edge_pool against the reference's own PersOctree::ConstructEdgePool body (:833-895)."""
+    from tests.golden.make_golden_ref_kernels import edge_pool_of
+    rng = np.random.RandomState(2)
+    for trial in range(2):
+        nodes = _history(rig, trial, rng)[0] if trial else rig["tree_nodes"].copy()
+        ref = rh.construct_edge_pool(nodes)
+        got = edge_pool_of(nodes)
+        assert ref.size > 0 and ref.size % 64 == 0
+        # the 12 padding bytes of each 64-byte record (52 used) are indeterminate in the reference's push_back
+        used = np.arange(ref.size) % 64 < 52
+        assert got.size == ref.size and np.array_equal(got[used], ref[used])
+
+
 # ------------------------------------------------------------------ GPU: the CUDA kernels against the same fixture
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["h0", "h1"])
