@@ -161,6 +161,36 @@ def main():
         manifest.append(f"{os.path.relpath(samp_cpp, REF)}:{first}-{last} {sig[5:-1]}")
     with open(os.path.join(OUT_DIR, "ref_host_fns.inc"), "w") as f:
         f.write("\n".join(hparts) + "\n")
+    # PersOctree CONSTRUCTION (PersSampler.cpp:7-417 and 516-895: DistanceSummary, GetVisiCams, the constructor,
+    # ProcOctree, ConstructTreeNode, PCA, ConstructTrans, ConstructEdgePool) is torch tensor code through and through:
+    # it is compiled against the REAL libtorch of this image, on the CPU device (ref_driver_torch.cpp), with the
+    # reference's own macros (Utils/Common.h) and class declaration (PersSampler.h).
+    src = open(samp_cpp, encoding="utf-8", errors="replace").read()
+    clean = strip_comments_keep_lines(src)
+    a0 = clean.index("using Tensor = torch::Tensor;")
+    a1 = clean.index("void PersSampler::VisWarpedPoints(")
+    b0 = clean.index("void PersOctree::ConstructTreeNode(")
+    b1 = clean.index("PersSampler::PersSampler(")
+    b1 = clean.rfind("}", 0, b1) + 1
+    hdr = open(os.path.join(BIND, "PtsSampler", "PersSampler.h"), encoding="utf-8", errors="replace").read()
+    c0 = hdr.index("class PersOctree {")
+    c1 = hdr.index("};", c0) + 2
+    common = [l.rstrip() for l in open(os.path.join(BIND, "Utils", "Common.h"), encoding="utf-8", errors="replace")
+              if l.startswith("#define") and not l.startswith("#define PRINT_VAL")]
+    oparts = ["// GENERATED by oracle/ref_extract.py from the reference tree -- build output, never committed.\n",
+              "// ---- gfnerf/bindings/Utils/Common.h #defines"] + common + [
+              "// ---- gfnerf/bindings/PtsSampler/PersSampler.h #defines, structs, class PersOctree"] + \
+        defines(os.path.join(BIND, "PtsSampler", "PersSampler.h")) + \
+        structs(os.path.join(BIND, "PtsSampler", "PersSampler.h"), ["TransInfo", "TreeNode", "EdgePool"]) + [
+              hdr[c0:c1],
+              f"// ---- gfnerf/bindings/PtsSampler/PersSampler.cpp:{src.count(chr(10), 0, a0) + 1}-{src.count(chr(10), 0, a1)}",
+              src[a0:a1],
+              f"// ---- gfnerf/bindings/PtsSampler/PersSampler.cpp:{src.count(chr(10), 0, b0) + 1}-{src.count(chr(10), 0, b1) + 1}",
+              src[b0:b1]]
+    with open(os.path.join(OUT_DIR, "ref_octree_src.inc"), "w") as f:
+        f.write("\n".join(oparts) + "\n")
+    manifest.append(f"{os.path.relpath(samp_cpp, REF)}:{src.count(chr(10), 0, a0) + 1}-{src.count(chr(10), 0, a1)},"
+                    f"{src.count(chr(10), 0, b0) + 1}-{src.count(chr(10), 0, b1) + 1} PersOctree construction (libtorch build)")
     with open(os.path.join(OUT_DIR, "ref_manifest.txt"), "w") as f:
         f.write("\n".join(manifest) + "\n")
     print("\n".join(manifest))

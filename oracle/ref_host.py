@@ -244,3 +244,50 @@ def construct_edge_pool(tree_nodes, flavour="off"):
     pool = np.zeros(max(n, 1) * 64, np.uint8)
     assert L.ref_construct_edge_pool(_p(nodes), _i64(nodes.size // 128), _p(pool), _i64(n)) == n
     return pool[:n * 64]
+
+
+# ---------------------------------------------------------------- PersOctree construction against real libtorch (CPU)
+OCTREE_LIB = os.path.join(REF_DIR, "libgf_ref_octree.so")
+_octree_lib = None
+
+
+def octree_available():
+    return os.path.exists(OCTREE_LIB)
+
+
+def octree_lib():
+    """oracle/_ref/libgf_ref_octree.so (`make -C oracle ref_octree`): PtsSampler/PersSampler.cpp:9-417, 516-895 compiled
+    against this image's libtorch with kCUDA -> kCPU (oracle/ref_driver_torch.cpp)."""
+    global _octree_lib
+    if _octree_lib is None:
+        import torch  # noqa: F401  (loads libtorch / libc10 into the process first)
+        _octree_lib = C.CDLL(OCTREE_LIB)
+        _octree_lib.refoct_build.restype = C.c_int64
+    return _octree_lib
+
+
+def build_octree(max_depth, bbox_side_len, split_dist_thres, c2w, w2c, intri, bound, seed=0):
+    """The reference's PersOctree constructor.  -> (tree_nodes uint8 blob, pers_trans uint8 blob, search_order u8[64])"""
+    L = octree_lib()
+    c2w, w2c, intri, bound = (_c(x, np.float32) for x in (c2w, w2c, intri, bound))
+    n_trans = C.c_int64(0)
+    args = (_i64(max_depth), _f32(bbox_side_len), _f32(split_dist_thres), _p(c2w), _p(w2c), _p(intri), _p(bound),
+            _i64(c2w.shape[0]), C.c_uint64(seed))
+    n = L.refoct_build(*args, None, None, None, C.byref(n_trans))
+    if n < 0:
+        raise RuntimeError("the reference's PersOctree constructor failed (see stderr)")
+    nodes, trans, so = np.zeros(n * 128, np.uint8), np.zeros(n_trans.value * 576, np.uint8), np.zeros(64, np.uint8)
+    assert L.refoct_build(*args, _p(nodes), _p(trans), _p(so), C.byref(n_trans)) == n
+    return nodes, trans, so
+
+
+def construct_trans(rand_pts, c2w, intri0, center, seed=0):
+    """The reference's PersOctree::ConstructTrans.  -> 576-byte TransInfo blob (side_len = 0)."""
+    rand_pts, c2w = _c(rand_pts, np.float32), _c(c2w, np.float32)
+    out = np.zeros(576, np.uint8)
+    rc = octree_lib().refoct_construct_trans(_p(rand_pts), _i64(rand_pts.shape[0]), _p(c2w), _i64(c2w.shape[0]),
+                                             _p(_c(intri0, np.float32)), _p(_c(center, np.float32)), C.c_uint64(seed),
+                                             _p(out))
+    if rc != 0:
+        raise RuntimeError("the reference's ConstructTrans failed (see stderr)")
+    return out

@@ -88,6 +88,11 @@ struct Matrix {
     return *this;
   }
 
+  template <typename AA, typename = decltype(&AA::angle)>
+  Matrix& operator=(const AA& aa) { /* rot_mat = Eigen::AngleAxisf(angle, axis) */
+    *this = static_cast<Matrix>(aa);
+    return *this;
+  }
   GF_HD static Matrix Zero() {
     Matrix m;
     for (int i = 0; i < R * C; i++) m.d[i] = T(0);
@@ -122,6 +127,32 @@ struct Matrix {
   }
   GF_HD T norm() const { return sqrt_of(squaredNorm()); }
 
+  GF_HD T* data() { return d; }
+  GF_HD const T* data() const { return d; }
+  template <int O2>
+  GF_HD T dot(const Matrix<T, R, C, O2>& o) const {
+    const T* od = o.d;
+    const T* md = d;
+    struct Term {
+      const T *a, *b;
+      GF_HD T operator()(int k) const { return a[k] * b[k]; }
+    };
+    return tree_sum<T, 0, R * C>(Term{md, od});
+  }
+  template <int O2>
+  GF_HD Matrix cross(const Matrix<T, R, C, O2>& o) const { /* Eigen: a.y*b.z - a.z*b.y, ... */
+    static_assert(R * C == 3, "cross(): 3-vectors");
+    Matrix r;
+    r.d[0] = d[1] * o.d[2] - d[2] * o.d[1];
+    r.d[1] = d[2] * o.d[0] - d[0] * o.d[2];
+    r.d[2] = d[0] * o.d[1] - d[1] * o.d[0];
+    return r;
+  }
+  GF_HD Matrix normalized() const { /* Eigen: divide by sqrt(squaredNorm()) if that is > 0 */
+    const T n2 = squaredNorm();
+    if (n2 > T(0)) return *this / sqrt_of(n2);
+    return *this;
+  }
   GF_HD Matrix cwiseAbs() const {
     Matrix r;
     for (int i = 0; i < R * C; i++) r.d[i] = d[i] < T(0) ? -d[i] : d[i];
@@ -197,6 +228,30 @@ GF_HD inline Matrix<T, R, C, (C == 1 ? ColMajor : RowMajor)> operator*(const Mat
     }
   return r;
 }
+
+/* Eigen::AngleAxis<float>: only construction and conversion to a rotation matrix (AngleAxis::toRotationMatrix) */
+struct AngleAxisf {
+  float angle;
+  Matrix<float, 3, 1> axis;
+  AngleAxisf(float a, const Matrix<float, 3, 1>& ax) : angle(a), axis(ax) {}
+  template <int Opt>
+  operator Matrix<float, 3, 3, Opt>() const {
+    Matrix<float, 3, 3, Opt> res;
+    const float s = sinf(angle), c = cosf(angle);
+    const Matrix<float, 3, 1> sin_axis = axis * s, cos1_axis = axis * (1.f - c);
+    float tmp = cos1_axis.x() * axis.y();
+    res(0, 1) = tmp - sin_axis.z();
+    res(1, 0) = tmp + sin_axis.z();
+    tmp = cos1_axis.x() * axis.z();
+    res(0, 2) = tmp + sin_axis.y();
+    res(2, 0) = tmp - sin_axis.y();
+    tmp = cos1_axis.y() * axis.z();
+    res(1, 2) = tmp - sin_axis.x();
+    res(2, 1) = tmp + sin_axis.x();
+    for (int i = 0; i < 3; i++) res(i, i) = cos1_axis[i] * axis[i] + c;
+    return res;
+  }
+};
 
 typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<float, 3, 1> Vector3f;

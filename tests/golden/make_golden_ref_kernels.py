@@ -128,6 +128,15 @@ def main(flavour="fma"):
     ep = rh.construct_edge_pool(rig["tree_nodes"], flavour)
     used = np.arange(ep.size) % 64 < 52
     fx["o_edge_pool"] = np.array([ep.size // 64, int(hashlib.sha256(ep[used].tobytes()).hexdigest()[:15], 16)], np.int64)
+    # ---- PersOctree construction by the reference's own constructor (real libtorch on the CPU; ~40 s)
+    if rh.octree_available():
+        from gfnerf_b200.persoctree import TRANS_INFO_DTYPE
+        from tests.test_ref_octree import _w2c, node_digest
+        nodes, trans, so = rh.build_octree(16, 512.0, 1.5, rig["c2w"], _w2c(rig["c2w"]), rig["intri"], rig["bounds"], seed=0)
+        t = trans.view(TRANS_INFO_DTYPE)
+        fx.update({"t_nodes": np.array([nodes.size // 128, node_digest(nodes)], np.int64), "t_search_order": so,
+                   "t_center": t["center"].copy(), "t_side_len": t["side_len"].copy(),
+                   "t_dis_summary": t["dis_summary"].copy()})
     path = os.path.join(HERE, "ref_kernels.npz")
     np.savez_compressed(path, **fx)
     print("wrote", path, os.path.getsize(path) >> 10, "KiB;", rh.lib(flavour).ref_build_flavour().decode())
