@@ -450,6 +450,8 @@ def main():
                        "samples_per_step_per_gpu": round(v_mean), "slots_per_step_per_gpu": RAYS_PER_GPU * 1024,
                        "l2_policy": "inputs larger than L2 (0.3 GB table+optimizer state, ~1 GB sample buffers, "
                                     f"{N_BATCHES} ray batches cycled)",
+                       "level_addressing": "reference (level l = table rows [l*T/2, l*T/2 + T): windows overlap by half, "
+                                           "8.5*T of the 16*T rows reachable; DESIGN.md section 5)",
                        "sample_ahead": bool(ahead),
                        "parallelism": f"dp{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "rays/s",
