@@ -21,6 +21,12 @@
  * results are identical; the hash blend is identical bit for bit; the march
  * agrees to 1e-4 (fp contraction is the compiler's choice: nvcc's for the
  * reference binary, g++'s for the host build, spelled out here for nvcc).
+ * The host side is held to the reference too: PersOctree::ProcOctree and
+ * ConstructEdgePool run from the same extraction (stand-in Tensor), and the
+ * whole PersOctree constructor (GetVisiCams, DistanceSummary, ConstructTreeNode,
+ * PCA, ConstructTrans) compiled against this image's real libtorch on the CPU
+ * (oracle/ref_driver_torch.cpp, tests/test_ref_octree.py): same tree, field for
+ * field.
  * What stays UNPINNED: the last bit of fp32 results that depend on nvcc's
  * contraction and on Eigen's evaluation order inside the shim (our reading of
  * Eigen 3.4), and the tcnn SH-4 encoding (un-vendored third party).
