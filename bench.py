@@ -389,7 +389,8 @@ def main():
         "composite_fwd": ("hbm", (28.0 + 12.0) * v_mean + 20.0 * RAYS_PER_GPU),
         "composite_bwd": ("hbm", 44.0 * v_mean + 20.0 * RAYS_PER_GPU),
         "mlp_fwd": ("tensor", 2.0 * 11392.0 * v_mean), "mlp_bwd": ("tensor", 2.0 * 2.0 * 11392.0 * v_mean),
-        "adam_table": ("hbm", 30.0 * 16 * (1 << log2t) * 2),
+        # the 8.5 * T rows the levels can reach (the rest never gets a gradient: dense Adam leaves it untouched)
+        "adam_table": ("hbm", 30.0 * 17 * (1 << log2t)),
     }
     kernels = []
     for name, ms in sorted(stage_ms.items(), key=lambda kv: -kv[1]):

@@ -50,8 +50,12 @@ class _Adam:
     """State of gf_adam_step for one flat fp32 tensor."""
 
     def __init__(self, param: torch.Tensor, lr: float, eps: float = 1e-15, betas=(0.9, 0.999), grad=None,
-                 grad_scale: float = 1.0):
+                 grad_scale: float = 1.0, n_active: Optional[int] = None):
         self.param, self.lr, self.eps, self.betas = param, lr, eps, betas
+        # n_active: the leading elements the step sweeps.  For a hash table that is the 8.5 * T rows its levels can
+        # reach (level_base_row): the rows beyond never receive a gradient, so their moments stay 0 and dense Adam
+        # leaves them where they are (update = lr * 0 / (sqrt(0) + eps)) -- skipping them is exact, not an approximation
+        self.n_active = int(param.numel() if n_active is None else n_active)
         # `grad` holds grad_scale x the gradient (a power of two: the hash tables stay at the reference's x128 scale,
         # Hash3DAnchored_cuda.cu:209, and the division rides along with the optimizer's 1 / world)
         self.grad_scale = float(grad_scale)
@@ -69,7 +73,7 @@ class _Adam:
         NaN guard, trainer.py:416-426; the host-side step counter is not rewound)"""
         self.t += 1
         _lib.check(_lib.lib().gf_adam_step_guarded(
-            self.param.numel(), _lib.ptr(self.param), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
+            self.n_active, _lib.ptr(self.param), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
             _lib.ptr(shadow), float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.t,
             float(grad_div) * self.grad_scale, 1, _lib.ptr(skip_flag), _lib.cur_stream()), "gf_adam_step_guarded")
 
@@ -116,7 +120,8 @@ class GFNeRFEngine:
         self.mlp = init_mlp_params(hidden, gen, self.device)
         self.emb = (torch.randn(num_images, APPEARANCE_DIM, generator=gen).to(self.device)
                     if use_appearance_embedding else None)
-        self.opt_table = _Adam(self.enc.feat_pool_.detach().view(-1), lr_table, grad_scale=GRAD_SCALE)
+        self.opt_table = _Adam(self.enc.feat_pool_.detach().view(-1), lr_table, grad_scale=GRAD_SCALE,
+                               n_active=self.enc.used_rows_ * 2)
         # MLP + embedding gradients live in one flat bucket: one collective for both
         small = FlatBucket([self.mlp.shape] + ([self.emb.shape] if self.emb is not None else []), device=self.device)
         self.opt_mlp = _Adam(self.mlp, lr_mlp, grad=small.views[0])
@@ -146,7 +151,8 @@ class GFNeRFEngine:
         self.res.feat_pool_.requires_grad_(False)
         self.res.Zero()
         self.res.shadow(force=True)
-        self.opt_res = _Adam(self.res.feat_pool_.detach().view(-1), lr, grad_scale=GRAD_SCALE)   # sub-encoder lr, gfnerf/nerfacto.py:483
+        self.opt_res = _Adam(self.res.feat_pool_.detach().view(-1), lr, grad_scale=GRAD_SCALE,   # sub-encoder lr, gfnerf/nerfacto.py:483
+                             n_active=self.res.used_rows_ * 2)
         self.stage = "block_stage"
         self.sampler.UpdateMode(1)                                        # nerfacto.py:614-616
 
@@ -396,7 +402,7 @@ class GFNeRFEngine:
                 if optimizer_step:
                     with self._stage("adam_table"):
                         self.opt_res.step(shadow=self.res._shadow, lr=self.opt_res.lr * lr_scale,
-                                          skip_flag=self._nan_flag([self.opt_res.grad]))
+                                          skip_flag=self._nan_flag([self.opt_res.grad[:self.opt_res.n_active]]))
                     self.res.mark_shadow_fresh()
             else:
                 d_ray_emb = (self._buf("d_ray_emb", (R, APPEARANCE_DIM), torch.float32, zero=True)
@@ -542,7 +548,7 @@ class GFNeRFEngine:
     def _apply_adam(self, lr_scale: float):
         div = float(self.world)
         with self._stage("adam_small"):
-            flag = self._nan_flag([self._small_grads, self.opt_table.grad])
+            flag = self._nan_flag([self._small_grads, self.opt_table.grad[:self.opt_table.n_active]])
             self.opt_mlp.step(grad_div=div, lr=self.opt_mlp.lr * lr_scale, skip_flag=flag)
             if self.opt_emb is not None:
                 self.opt_emb.step(grad_div=div, lr=self.opt_emb.lr * lr_scale, skip_flag=flag)
