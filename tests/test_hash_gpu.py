@@ -151,7 +151,13 @@ def test_full_size_properties():
     t16 = core.feat_pool_.detach().half().double()
     lhs = float((core.feat_pool_.grad.double() * t16).sum())
     rhs = float((g.double() * y.detach().double()).sum())
-    assert abs(lhs - rhs) <= 2e-3 * abs(rhs) + 1e-9
+    # Both sides are sums of ~3e7 random-sign terms g_i * y_i, so |rhs| itself is only ~ the L2 norm of the terms and
+    # a tolerance relative to |rhs| is a ratio of two Gaussians (it failed one time in six by chance).  The honest
+    # scale is that L2 norm: the fp16 quantisations (gradient x128 -> fp16, every w * g product -> fp16, y -> fp16)
+    # put ~1e-3 of it between the two sides; a backward that scattered into other rows than the forward read would put
+    # ~1.4 x of it there.
+    l2 = float((g.double() * y.detach().double()).pow(2).sum().sqrt())
+    assert abs(lhs - rhs) <= 0.02 * l2, (lhs, rhs, l2)
     # scaling the table by 2 (exact in fp16) scales the encoding by 2 exactly
     core.feat_pool_.data.mul_(2)
     y2 = core.AnchoredQuery(pts, anc)

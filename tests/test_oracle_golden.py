@@ -97,3 +97,34 @@ def test_s3im_matches_reference():
     l2, g2 = orc.s3im(g["src"], g["tar"], g["index"], mult=0.25)
     assert abs(l2 - 0.25 * loss) < 1e-12 and np.allclose(g2, 0.25 * grad, rtol=1e-6, atol=1e-12)
     assert orc.s3im(g["src"], g["tar"], g["index"], want_grad=False)[0] == loss
+
+
+def test_field_wiring_matches_the_reference_field_class():
+    """The oracle chain hash -> MLPs against the reference's own GFNeRFField.get_density / get_outputs
+    (gfnerf/nerfacto_field.py:412-591) run on the CPU with stand-ins only for its native extension (whose AnchoredQuery
+    ran the reference's own forward kernel on the host) and for tinycudann (tests/golden/make_golden_field.py)."""
+    g = load("ref_field")
+    R, S = g["warp_pts"].shape[:2]
+    n_vol = g["prim"].shape[1]
+    # nerfacto_field.py:431,437: the field queries EVERY slot -- the padding anchor 0 passes `anchors > -1` -- at
+    # (warp + 1.5) / 3 with anchor column 0
+    assert g["query_pts"].shape[0] == R * S
+    assert np.array_equal(g["query_anchors"], g["anchors"][..., 0].reshape(-1))
+    pts01 = ((g["warp_pts"].reshape(-1, 3) + np.float32(1.5)) * (np.float32(1.0) / np.float32(3.0))).astype(np.float32)
+    # torch's CPU true division vs the multiply-by-reciprocal of its CUDA kernels (what the GPU path reproduces)
+    assert np.abs(pts01 - g["query_pts"]).max() <= 2 ** -23
+    bias = np.zeros((16 * n_vol, 3), np.float32)
+    feat = orc.hash_forward(g["table"], g["prim"], bias, g["query_pts"], g["query_anchors"])
+    assert np.array_equal(feat, g["hash_feats"].astype(np.float32))             # the reference's forward kernel
+    ray_id = np.repeat(np.arange(R), S).astype(np.int32)
+    ray_emb = g["emb"][g["cam"]]                                                # Embedding(rel_camera_indices), :529-531
+    sigma, rgb = orc.mlp_forward(g["params"], feat, ray_id, g["dirs"], ray_emb, 64)
+    # padding is not masked out by the field (the mask is all true): density = trunc_exp(h0 + 1) everywhere, :499-505
+    close(sigma, g["density"].reshape(-1), what="density")
+    close(rgb, g["rgb"].reshape(-1, 3), what="rgb")
+    d_feat, d_params, d_emb = orc.mlp_backward(g["params"], feat, ray_id, g["dirs"], ray_emb, g["g_sigma"].reshape(-1),
+                                               g["g_rgb"].reshape(-1, 3), 64)
+    close(d_params, g["d_params"], rtol=5e-5, what="d_params")
+    d_emb_cam = np.zeros_like(g["d_emb"], dtype=np.float64)
+    np.add.at(d_emb_cam, g["cam"], d_emb)
+    close(d_emb_cam, g["d_emb"], rtol=5e-5, what="d_embedding")
