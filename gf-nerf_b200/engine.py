@@ -215,7 +215,7 @@ class GFNeRFEngine:
             if self.res is not None:
                 self.res.launch_forward_residual(cs.pts01, cs.anchor, feat, d_n_ptr=cs.total, recast=False)
         with self._stage("ray_bias"):
-            _lib.check(L.gf_mlp_ray_bias(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
+            _lib.check(L.gf_mlp_ray_bias(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d),
                                          _lib.ptr(ray_emb), _lib.ptr(ray_bias), st), "gf_mlp_ray_bias")
         with self._stage("mlp_fwd"):
             _lib.check(L.gf_mlp_forward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
@@ -408,7 +408,7 @@ class GFNeRFEngine:
                 d_ray_emb = (self._buf("d_ray_emb", (R, APPEARANCE_DIM), torch.float32, zero=True)
                              if ray_emb is not None else None)
                 with self._stage("ray_bias_bwd"):
-                    _lib.check(L.gf_mlp_ray_bias_backward(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d_unit),
+                    _lib.check(L.gf_mlp_ray_bias_backward(R, self.hidden, _lib.ptr(self.mlp), _lib.ptr(cs.rays_d),
                                                           _lib.ptr(ray_emb), _lib.ptr(d_ray_bias),
                                                           _lib.ptr(self.opt_mlp.grad), _lib.ptr(d_ray_emb), st),
                                "gf_mlp_ray_bias_backward")

@@ -39,7 +39,10 @@ class CompactSamples:
     delta: torch.Tensor         # f32 [cap]
     ray_id: torch.Tensor        # int32 [cap]
     first_oct_dis: torch.Tensor  # f32 [R]
-    rays_d_unit: torch.Tensor   # f32 [R,3]
+    rays_d_unit: torch.Tensor   # f32 [R,3]  normalised (what the march uses, PersSampler_cuda.cu:323)
+    rays_d: torch.Tensor        # f32 [R,3]  the bundle's directions AS GIVEN: what the field's SH encodes -- the reference
+                                # normalises only inside GetSamples; frustums.directions stay the bundle's
+                                # (perssampler.py:414-418, nerfacto_field.py:518-521; pinned by tests/golden/ref_model.npz)
 
 
 def build_octree(max_depth: int, bbox_side_len: float, split_dist_thres: float, c2w, intri, bounds, seed: int = 0,
@@ -225,7 +228,7 @@ class PersSamplerCore:
             node=self._buf("node" + sfx, (cap,), torch.int32), t=self._buf("t" + sfx, (cap,), torch.float32),
             delta=self._buf("delta" + sfx, (cap,), torch.float32),
             ray_id=self._buf("ray_id" + sfx, (cap,), torch.int32),
-            first_oct_dis=first, rays_d_unit=rays_d)
+            first_oct_dis=first, rays_d_unit=rays_d, rays_d=rays_d_raw.contiguous().float())
         if R == 0:
             offsets.zero_()
             total.zero_()

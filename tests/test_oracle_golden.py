@@ -128,3 +128,64 @@ def test_field_wiring_matches_the_reference_field_class():
     d_emb_cam = np.zeros_like(g["d_emb"], dtype=np.float64)
     np.add.at(d_emb_cam, g["cam"], d_emb)
     close(d_emb_cam, g["d_emb"], rtol=5e-5, what="d_embedding")
+
+
+def test_whole_path_matches_the_reference_model_code():
+    """The oracle chain sampler -> hash -> MLPs -> composite -> octree vote against the reference's own Python model
+    path -- PersSampler.generate_ray_samples, GFNeRFField, get_weights_f2nerf, the renderers, GFNeRFModel.get_outputs --
+    run on the CPU over the reference's kernels compiled for the host (tests/golden/make_golden_model.py)."""
+    from tests.helpers import load_rig
+    g = load("ref_model")
+    rig = load_rig("rig8")
+    R, S = g["rays_o"].shape[0], 1024
+    assert bool(g["deltas_are_dists"]) and bool(g["starts_are_t"])        # perssampler.py:411-412, 429
+    assert list(g["calls"]) == [f"UpdateRayMarch:{int(g['step'])}", "UpdateMode:0", f"UpdateOctNodes:{int(g['step'])}"]
+    # GetSamples normalises the directions (PersSampler_cuda.cu:323)
+    d_unit = g["rays_d_raw"] / np.linalg.norm(g["rays_d_raw"], axis=1, keepdims=True)
+    assert np.abs(d_unit - g["rays_d_unit"]).max() < 2e-7
+    smp = orc.sampler_get_samples(g["rays_o"], g["rays_d_unit"], g["noise"], rig["tree_nodes"], rig["pers_trans"])
+    counts = smp["counts"]
+    assert np.array_equal(counts, g["counts"]) and counts[-1] == 0
+    m = counts[:, None] > np.arange(S)[None]
+    pts01 = ((smp["warp_pts"][m] + np.float32(1.5)) * (np.float32(1.0) / np.float32(3.0))).astype(np.float32)
+    n_vol = g["prim"].shape[1]
+    feat = orc.hash_forward(g["table"], g["prim"], np.zeros((16 * n_vol, 3), np.float32), pts01, smp["anchors"][m][:, 0])
+    ray_id = np.repeat(np.arange(R), counts).astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    ray_emb = g["emb"][g["cam"]]
+    # The field encodes the bundle's directions AS GIVEN: generate_ray_samples puts ray_bundle.directions into the
+    # frustums (perssampler.py:414-418) and get_outputs feeds (directions + 1) / 2 to the SH (nerfacto_field.py:518-521);
+    # only GetSamples normalises, for the march.  The fixture's bundle is deliberately not normalised.
+    sigma, rgb = orc.mlp_forward(g["params"], feat, ray_id, g["rays_d_raw"], ray_emb, 64)
+    sigma_u, rgb_u = orc.mlp_forward(g["params"], feat, ray_id, g["rays_d_unit"], ray_emb, 64)
+    assert np.array_equal(sigma, sigma_u) and np.abs(rgb - rgb_u).max() > 1e-3      # (so the distinction is visible)
+    comp = orc.composite_forward(offsets, sigma, smp["dists"][m], rgb, smp["ts"][m])
+    # 1e-4: the reference's sample positions come from the host build of its march kernel (g++'s contraction), the
+    # oracle's follow nvcc's; see tests/test_ref_kernels.py
+    close(comp["rgb"], g["out_rgb"], rtol=1e-4, what="rgb")
+    close(comp["acc"], g["out_acc"][:, 0], rtol=1e-4, what="accumulation")
+    # DepthRenderer('expected') clips to the dense tensor's [min, max] of t (min = the padding's 0), then / scale_factor
+    depth = np.clip(comp["depth"], 0.0, smp["ts"].max()) / g["scale_factor"]
+    close(depth, g["out_depth"][:, 0], rtol=1e-4, what="depth")
+    close(smp["first_oct_dis"] / g["scale_factor"], g["out_oct_depth"][:, 0], what="oct_depth")
+    # backward of mean((rgb - target)^2) through composite and both MLPs
+    g_rgb = (2.0 * (comp["rgb"] - g["target"]) / np.float32(R * 3)).astype(np.float32)
+    assert abs(float(((comp["rgb"] - g["target"]) ** 2).mean()) - float(g["loss"])) <= 1e-4 * float(g["loss"])
+    d_sigma, d_rgb = orc.composite_backward(offsets, sigma, smp["dists"][m], rgb, g_rgb)
+    _, d_params, d_emb = orc.mlp_backward(g["params"], feat, ray_id, g["rays_d_raw"], ray_emb, d_sigma, d_rgb, 64)
+    close(d_params, g["d_params"], rtol=2e-3, what="d_params")
+    d_emb_cam = np.zeros_like(g["d_emb"], dtype=np.float64)
+    np.add.at(d_emb_cam, g["cam"], d_emb)
+    close(d_emb_cam, g["d_emb"], rtol=2e-3, what="d_embedding")
+    # the octree vote with the arguments get_outputs passes (nerfacto.py:603-611)
+    w_dense, a_dense = np.zeros((R, S), np.float32), np.zeros((R, S), np.float32)
+    w_dense[m], a_dense[m] = comp["weights"], comp["alphas"]
+    nodes = rig["tree_nodes"].copy()
+    n = nodes.size // 128
+    ws, as_, vc = np.full(n, 1000, np.int64), np.full(n, 1000, np.int64), np.zeros(n, np.int64)
+    orc.update_oct_nodes(counts, smp["anchors"][..., 1].reshape(-1), w_dense.reshape(-1), a_dense.reshape(-1), nodes, ws,
+                         as_, vc)
+    assert np.array_equal(vc, g["visit"])
+    # a vote flips when a leaf's max weight sits within 1e-4 of its threshold: allow none here, report if it happens
+    assert np.array_equal(ws, g["w_stats"]) and np.array_equal(as_, g["a_stats"])
+    assert np.array_equal(nodes.view(np.int64).reshape(-1, 16)[:, 12], g["trans_idx"])
