@@ -319,24 +319,30 @@ class PersSamplerCore:
         oc.visit_cnt = np.zeros(n, np.int64)
         self._upload_octree(stats=True)
 
-    def MarkInvisibleNodes(self):
-        """MarkInvisibleNodesKernel + CheckVisible (PersSampler_cuda.cu:680-742); cold (milestones only), so it
-        is a handful of torch ops over [n_nodes, n_cams] instead of a kernel of its own."""
-        nodes = self.tree_nodes_gpu_.view(-1, 128)
+    @staticmethod
+    def invisible_nodes(nodes: torch.Tensor, w2c: torch.Tensor, intri: torch.Tensor, bound: torch.Tensor) -> torch.Tensor:
+        """CheckVisible over all (node, camera) pairs (PersSampler_cuda.cu:680-723) as torch ops on whatever device the
+        tensors live on: bool [n_nodes], True = seen by no camera.  nodes: uint8 [n,128] TreeNode blobs."""
         cs = nodes[:, :16].contiguous().view(torch.float32)                    # center xyz, side_len
         center, side = cs[:, :3], cs[:, 3]
-        cam = torch.einsum("cij,nj->nci", self.w2c_[:, :, :3], center) + self.w2c_[None, :, :, 3]   # [n,c,3]
+        cam = torch.einsum("cij,nj->nci", w2c[:, :, :3], center) + w2c[None, :, :, 3]   # [n,c,3]
         radius = (side * 0.707)[:, None]
         z = -cam[..., 2]
-        out_z = (z < self.bound_[None, :, 0] - radius) | (z > self.bound_[None, :, 1] + radius)
+        out_z = (z < bound[None, :, 0] - radius) | (z > bound[None, :, 1] + radius)
         inside = torch.linalg.norm(cam, dim=-1) < radius
-        cx, cy = self.intri_[None, :, 0, 2], self.intri_[None, :, 1, 2]
-        fx, fy = self.intri_[None, :, 0, 0], self.intri_[None, :, 1, 1]
+        cx, cy = intri[None, :, 0, 2], intri[None, :, 1, 2]
+        fx, fy = intri[None, :, 0, 0], intri[None, :, 1, 1]
         bx, by = radius / z * fx, radius / z * fy
         ix, iy = cam[..., 0] / z * fx, cam[..., 1] / z * fy
         out_img = (ix + bx < -cx) | (ix > cx + bx) | (iy + by < -cy) | (iy > cy + by)
         visible = (~out_z) & (inside | ~out_img)
-        invisible = visible.sum(-1) < 1
+        return visible.sum(-1) < 1
+
+    def MarkInvisibleNodes(self):
+        """MarkInvisibleNodesKernel + CheckVisible (PersSampler_cuda.cu:680-742); cold (milestones only), so it
+        is a handful of torch ops over [n_nodes, n_cams] instead of a kernel of its own."""
+        nodes = self.tree_nodes_gpu_.view(-1, 128)
+        invisible = self.invisible_nodes(nodes, self.w2c_, self.intri_, self.bound_)
         tidx = nodes[:, 96:104].contiguous().view(torch.int64).view(-1)
         tidx[invisible] = -1
         nodes[:, 96:104] = tidx.view(-1, 1).view(torch.uint8)

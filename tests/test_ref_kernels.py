@@ -194,6 +194,30 @@ def test_live_sampler_2000_rays(rig, flavour):
 
 
 @live
+def test_live_mark_invisible_nodes_is_the_reference_kernel(rig):
+    """PersSamplerCore.invisible_nodes (the torch ops MarkInvisibleNodes runs at milestones) against the reference's
+    MarkInvisibleNodesKernel / CheckVisible (PersSampler_cuda.cu:680-723) on the rig's tree, with a camera subset so
+    that a good part of the nodes really is out of sight."""
+    import torch
+    from gfnerf_b200.perssampler import PersSamplerCore
+    c2w = rig["c2w"][:6]
+    m = np.tile(np.eye(4, dtype=np.float32)[None], (c2w.shape[0], 1, 1))
+    m[:, :3, :] = c2w
+    w2c = np.ascontiguousarray(np.linalg.inv(m)[:, :3, :].astype(np.float32))
+    intri, bound = np.ascontiguousarray(rig["intri"][:6]), np.ascontiguousarray(rig["bounds"][:6])
+    nodes_ref = rig["tree_nodes"].copy()
+    tidx0 = nodes_ref.view(np.int64).reshape(-1, 16)[:, 12].copy()
+    rh.mark_invisible_nodes(nodes_ref, intri, w2c, bound)
+    ref_invisible = (nodes_ref.view(np.int64).reshape(-1, 16)[:, 12] == -1) & (tidx0 != -1)
+    T = torch.from_numpy
+    mine = PersSamplerCore.invisible_nodes(T(rig["tree_nodes"].copy()).view(-1, 128), T(w2c), T(intri), T(bound)).numpy()
+    mine_marks = mine & (tidx0 != -1)
+    assert 0 < ref_invisible.sum() < (tidx0 != -1).sum()
+    # borderline nodes (a frustum edge within fp rounding of the node's bounding sphere) may fall either way
+    assert (mine_marks != ref_invisible).sum() <= 2, ((mine_marks != ref_invisible).sum(), ref_invisible.sum())
+
+
+@live
 def test_live_block_index_and_visibility_kernels(rig):
     """SetBlockIdxsNearestKernel / MarkInvisibleNodesKernel (PersSampler_cuda.cu:680-766) against the host mirror."""
     from gfnerf_b200 import persoctree as po
