@@ -5,6 +5,8 @@ import os
 import re
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -85,3 +87,54 @@ int main(void) {
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "sm_100a" in r.stdout
+
+
+# Method surface of the reference's TorchScript classes, TORCH_LIBRARY(my_classes, m) of hashanchored/bindings.cpp:343-401
+# (uncommented .def lines), as parsed from the reference tree by the live test below.
+REFERENCE_SURFACE = {
+    "Hash3DAnchored": ["AnchoredQuery", "GetParams", "LoadStates", "ReleaseResources", "Reset", "SetFeatPoolRequireGrad",
+                       "States", "Zero", "to"],
+    "PersSampler": ["GetEdgeSamples", "GetSamples", "InitSampler", "LoadStates", "States", "UpdateBlockIdxs", "UpdateMode",
+                    "UpdateOctNodes", "UpdateRayMarch", "VisOctree", "get_compact_freq_", "get_global_near_",
+                    "get_max_oct_intersect_per_ray_", "get_mode_", "get_n_volumes_", "get_pers_trans_info",
+                    "get_points_anchors", "get_ray_march_fineness_", "get_sample_l_", "get_sampled_oct_per_ray_",
+                    "get_scale_by_dis_", "get_sub_div_milestones_", "get_tree_nodes_block_idx_", "get_tree_nodes_center_",
+                    "get_tree_nodes_is_leaf_node_", "get_tree_nodes_side_len_", "get_tree_nodes_trans_idx_",
+                    "qurey_tree_nodes_centers", "trans_query_frame"],
+}
+
+
+def _defs(path, strip_commented=True):
+    """{class: sorted method names} of the torch::class_ registrations in a bindings source."""
+    import re
+    out, cur = {}, None
+    for line in open(path, encoding="utf-8", errors="replace"):
+        s = line.strip()
+        if strip_commented and s.startswith("//"):
+            continue
+        m = re.search(r'class_<[^>]*>\s*\(\s*"(\w+)"\s*\)', s)          # m.class_<Impl>("Name")
+        if m:
+            cur = m.group(1)
+            out.setdefault(cur, [])
+        for name in re.findall(r'\.def\(\s*"(\w+)"', s):
+            if cur is not None:
+                out[cur].append(name)
+    return {k: sorted(set(v)) for k, v in out.items()}
+
+
+def test_torchscript_classes_register_every_method_of_the_reference():
+    """csrc/torch_bindings.cpp (-> f2nerf_bindings_b200.so) registers my_classes.Hash3DAnchored / PersSampler with
+    every method name the reference's bindings register, so gfnerf/hash_3d_anchored.py and gfnerf/perssampler.py find
+    what they call."""
+    ours = _defs(os.path.join(ROOT, "gf-nerf_b200", "csrc", "torch_bindings.cpp"))
+    for cls, methods in REFERENCE_SURFACE.items():
+        assert cls in ours, (cls, list(ours))
+        missing = [m for m in methods if m not in ours[cls]]
+        assert not missing, (cls, missing)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/gfnerf/bindings"), reason="reference tree only in the build container")
+def test_reference_surface_list_is_current():
+    ref = _defs("/root/reference/gfnerf/bindings/hashanchored/bindings.cpp")
+    for cls, methods in REFERENCE_SURFACE.items():
+        assert ref.get(cls) == methods, (cls, ref.get(cls))
