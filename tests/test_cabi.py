@@ -138,3 +138,21 @@ def test_reference_surface_list_is_current():
     ref = _defs("/root/reference/gfnerf/bindings/hashanchored/bindings.cpp")
     for cls, methods in REFERENCE_SURFACE.items():
         assert ref.get(cls) == methods, (cls, ref.get(cls))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/gfnerf"), reason="reference tree only in the build container")
+def test_every_native_call_of_the_reference_python_is_registered():
+    """Every method the reference's Python invokes on its native objects -- `self.sampler.X(` in gfnerf/perssampler.py,
+    `self.hash_3d.X(` in gfnerf/hash_3d_anchored.py -- exists on the classes f2nerf_bindings_b200.so registers."""
+    ours = _defs(os.path.join(ROOT, "gf-nerf_b200", "csrc", "torch_bindings.cpp"))
+    for cls, attr, path in (("PersSampler", "sampler", "/root/reference/gfnerf/perssampler.py"),
+                            ("Hash3DAnchored", "hash_3d", "/root/reference/gfnerf/hash_3d_anchored.py")):
+        src = "\n".join(l for l in open(path, encoding="utf-8", errors="replace") if not l.strip().startswith("#"))
+        called = sorted(set(re.findall(r"self\.%s\.(\w+)\(" % attr, src)))
+        assert len(called) >= 5, called
+        ref = _defs("/root/reference/gfnerf/bindings/hashanchored/bindings.cpp")[cls]
+        missing = [m for m in called if m in ref and m not in ours[cls]]
+        assert not missing, (cls, missing)
+        # (the reference's own Python also calls one name its bindings never register -- perssampler.py:623
+        # `self.sampler.sampled_oct_per_ray_()`, registered as get_sampled_oct_per_ray_: an AttributeError there too)
+        assert [m for m in called if m not in ref] == (["sampled_oct_per_ray_"] if cls == "PersSampler" else [])
