@@ -185,7 +185,7 @@ struct PersSamplerImpl : torch::CustomClassHolder {
   void InitSampler(double split_dist_thres, std::vector<int64_t> sub_div_milestones, int64_t compact_freq,
                    int64_t max_oct_intersect_per_ray, double global_near, bool scale_by_dis, int64_t bbox_levels,
                    double sample_l, int64_t max_level, Tensor c2w, Tensor w2c, Tensor intri, Tensor bounds, int64_t mode,
-                   int64_t sampled_oct_per_ray, double ray_march_fineness, double ray_march_init_fineness,
+                   double sampled_oct_per_ray, double ray_march_fineness, double ray_march_init_fineness,
                    int64_t ray_march_fineness_decay_end_iter) {
     TORCH_CHECK(torch::cuda::is_available(), "PersSampler needs a CUDA device: the B200 kernels have no CPU fallback");
     Configure(compact_freq, max_oct_intersect_per_ray, global_near, scale_by_dis, sample_l, mode, ray_march_fineness,
@@ -514,7 +514,7 @@ struct PersSamplerImpl : torch::CustomClassHolder {
   int64_t get_max_oct_intersect_per_ray_() { return max_oct_; }
   double get_global_near_() { return global_near_; }
   double get_sample_l_() { return sample_l_; }
-  bool get_scale_by_dis_() { return scale_by_dis_; }
+  double get_scale_by_dis_() { return scale_by_dis_ ? 1.0 : 0.0; }   // double_t in the reference (bindings.cpp:272-275)
   int64_t get_mode_() { return mode_; }
   int64_t get_n_volumes_() { return n_trans(); }
   double get_sampled_oct_per_ray_() { return sampled_oct_per_ray_; }

@@ -156,3 +156,45 @@ def test_every_native_call_of_the_reference_python_is_registered():
         # (the reference's own Python also calls one name its bindings never register -- perssampler.py:623
         # `self.sampler.sampled_oct_per_ray_()`, registered as get_sampled_oct_per_ray_: an AttributeError there too)
         assert [m for m in called if m not in ref] == (["sampled_oct_per_ray_"] if cls == "PersSampler" else [])
+
+
+def _method_signature(text, cls, func):
+    """(argument types, return type) of `func` as declared inside class / struct `cls`, normalised to schema words."""
+    i = text.index("class " + cls) if ("class " + cls) in text else text.index("struct " + cls)
+    body = re.sub(r"/\*.*?\*/", "", text[i:], flags=re.S)
+    m = next(x for x in re.finditer(r"[\s>]%s\s*\(([^(){}]*)\)\s*(?:const\s*)?[{;]" % re.escape(func), body)
+             if not body[:x.start() + 1].rstrip().endswith(("return", "=", ",", "(", "->", ".")))
+    head = body[:m.start() + 1]
+    ret = head[max(head.rfind(c) for c in (";", "}", "{", "public:", "private:")) + 1:]
+    ret = ret.split("public:")[-1].split("private:")[-1]
+
+    def norm(t):
+        t = "".join(t.split())
+        for a, b in (("const", ""), ("&", ""), ("double_t", "float"), ("double", "float"), ("int64_t", "int"),
+                     ("torch::Tensor", "Tensor"), ("std::", "")):
+            t = t.replace(a, b)
+        return t
+
+    args = [norm(re.sub(r"\s*\w+\s*$", "", a.strip())) for a in re.split(r",(?![^<]*>)", m.group(1)) if a.strip()]
+    return args, norm(ret)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/gfnerf/bindings"), reason="reference tree only in the build container")
+def test_torchscript_method_signatures_match_the_reference():
+    """Argument and return types of every registered method, ours against hashanchored/bindings.cpp (TorchScript
+    checks them at call time: an int64_t where the reference takes a double_t would reject a Python float)."""
+    strip = lambda p: "\n".join("" if l.lstrip().startswith("#") else l.split("//")[0]
+                                for l in open(p, encoding="utf-8", errors="replace"))
+    ref_src = strip("/root/reference/gfnerf/bindings/hashanchored/bindings.cpp")
+    our_src = strip(os.path.join(ROOT, "gf-nerf_b200", "csrc", "torch_bindings.cpp"))
+    regs = lambda s: {name: (impl, dict(re.findall(r'\.def\(\s*"(\w+)"\s*,\s*&\w+::(\w+)\)', body)))
+                      for impl, name, body in re.findall(r'm\.class_<(\w+)>\("(\w+)"\)(.*?);', s, flags=re.S)}
+    ref, ours = regs(ref_src), regs(our_src)
+    n = 0
+    for cls, (r_impl, r_map) in ref.items():
+        o_impl, o_map = ours[cls]
+        for meth, r_func in r_map.items():
+            r_sig, o_sig = _method_signature(ref_src, r_impl, r_func), _method_signature(our_src, o_impl, o_map[meth])
+            assert o_sig == r_sig, (cls, meth, o_sig, r_sig)
+            n += 1
+    assert n >= 38
