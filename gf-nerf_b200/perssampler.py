@@ -528,9 +528,33 @@ class PersSampler(nn.Module):
         return destination
 
     def load_states(self, state_dict, prefix=""):
+        """`state_dict` may also be the reference's positional form: a list of the four state tensors with `prefix`
+        the start index (perssampler.py:579-580 `load_states(states, idx)`)."""
+        if isinstance(state_dict, (list, tuple)):
+            return self.sampler.LoadStates(list(state_dict), int(prefix or 0))
         pre = "" if prefix == "" else f"{prefix}."
-        self.sampler.LoadStates([state_dict[pre + k] for k in
-                                 ("tree_nodes_gpu", "pers_trans_gpu", "tree_visit_cnt", "milestones_ts")], 0)
+        return self.sampler.LoadStates([state_dict[pre + k] for k in
+                                        ("tree_nodes_gpu", "pers_trans_gpu", "tree_visit_cnt", "milestones_ts")], 0)
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """perssampler.py:517-547: takes its four entries (and the cameras) out of the model's state dict."""
+        self.load_states([state_dict.pop("persampler." + k) for k in
+                          ("tree_nodes_gpu", "pers_trans_gpu", "tree_visit_cnt", "milestones_ts")], 0)
+        if "field.persampler.c2w" in state_dict:
+            self.c2w = state_dict.pop("field.persampler.c2w").to(self.sampler.device)
+        return None
+
+    # read-only views of the native sampler's configuration, under the reference's names (perssampler.py:583-623)
+    sub_div_milestones_ = property(lambda self: list(self.sampler.sub_div_milestones_))
+    compact_freq_ = property(lambda self: self.sampler.compact_freq_)
+    max_oct_intersect_per_ray_ = property(lambda self: self.sampler.max_oct_intersect_per_ray_)
+    global_near_ = property(lambda self: self.sampler.global_near_)
+    sample_l_ = property(lambda self: self.sampler.sample_l_)
+    scale_by_dis_ = property(lambda self: self.sampler.scale_by_dis_)
+    mode_ = property(lambda self: self.sampler.mode_)
+    n_volumes_ = property(lambda self: self.sampler.n_volumes_)
+    sampled_oct_per_ray_ = property(lambda self: self.sampler.sampled_oct_per_ray_)
+    ray_march_fineness_ = property(lambda self: self.sampler.ray_march_fineness_)
 
     # ---- eval-mode block routing (perssampler.py:138-165, 244-260): the block / appearance embedding of a render
     # chunk is the one of the training camera nearest to the chunk's first ray origin
