@@ -157,28 +157,75 @@ class GFNeRFField(nn.Module):
         self.persampler = None
 
     # ---- focal-stage tables (nerfacto_field.py:248-403) ------------------------------------------
-    def add_table(self, i: int, generator: torch.Generator = None) -> None:
-        """zero-initialised residual encoder `base_encoding_{i}`"""
+    def add_table(self, table_idx: int, generator: torch.Generator = None) -> None:
+        """zero-initialised residual encoder `base_encoding_{table_idx}` (nerfacto_field.py:336-347)"""
         enc = Hash3DAnchored(self.log2_table_size, self.n_volumes, generator=generator)
         enc.zero()
-        setattr(self, f"base_encoding_{i}", enc)
+        setattr(self, f"base_encoding_{table_idx}", enc)
 
-    def del_table(self, i: int) -> None:
-        enc = getattr(self, f"base_encoding_{i}")
+    def del_table(self, table_idx: int) -> None:
+        enc = getattr(self, f"base_encoding_{table_idx}")
+        enc.unregister_hooks()
         enc.release_resources()
-        delattr(self, f"base_encoding_{i}")
+        delattr(self, f"base_encoding_{table_idx}")
 
-    def save_table(self, i: int) -> str:
+    def save_table(self, table_idx: int) -> str:
+        """nerfacto_field.py:368-383: the encoder's state dict (feat_pool / prime_pool / bias_pool / n_volumes, no
+        prefix) under encodings_ckpt/base_encoding_{idx}.ckpt -- the reference's file format, so swapped-out tables
+        travel between the two implementations."""
         os.makedirs(self.encodings_ckpt_dir, exist_ok=True)
-        path = str(self.encodings_ckpt_dir / f"base_encoding_{i}.ckpt")
-        torch.save([s.cpu() for s in getattr(self, f"base_encoding_{i}").states()], path)
+        path = str(self.encodings_ckpt_dir / f"base_encoding_{table_idx}.ckpt")
+        enc = getattr(self, f"base_encoding_{table_idx}")
+        torch.save({k: v.detach().cpu() for k, v in enc.state_dict().items()}, path)
         return path
 
-    def load_table(self, i: int) -> None:
-        states = torch.load(str(self.encodings_ckpt_dir / f"base_encoding_{i}.ckpt"))
-        if not hasattr(self, f"base_encoding_{i}"):
-            self.add_table(i)
-        getattr(self, f"base_encoding_{i}").load_states(states, 0)
+    def load_table(self, table_idx: int, strict: bool = False) -> None:
+        """nerfacto_field.py:386-403; a missing file is an error only if `strict`.  Unlike the reference the table is
+        created if it is not there yet (the reference asserts it is)."""
+        path = str(self.encodings_ckpt_dir / f"base_encoding_{table_idx}.ckpt")
+        if not os.path.exists(path):
+            if strict:
+                raise FileNotFoundError(path)
+            return
+        if not hasattr(self, f"base_encoding_{table_idx}"):
+            self.add_table(table_idx)
+        states = torch.load(path, map_location="cpu")
+        enc = getattr(self, f"base_encoding_{table_idx}")
+        if isinstance(states, (list, tuple)):      # files written before the format followed the reference's
+            enc.load_states(list(states), 0)
+        else:
+            enc.load_state_dict(dict(states))
+
+    def update_active_blocks(self, cur_split_data_idx: int, ray_samples=None) -> None:
+        """nerfacto_field.py:248-330: make block `cur_split_data_idx` the active one for the current mode (train /
+        eval): bring its table in (from disk if it was swapped out), freeze the eval-side tables, and swap every table
+        that is neither active in training nor in eval out to disk.  -1 = no active block."""
+        active = [] if cur_split_data_idx == -1 else [int(cur_split_data_idx)]
+        in_train, in_test = (active, self.active_block_idxs_test) if self.training else (self.active_block_idxs, active)
+        for i in in_test:
+            if not hasattr(self, f"base_encoding_{i}"):
+                self.add_table(i)
+                self.load_table(i, strict=True)
+            getattr(self, f"base_encoding_{i}").set_require_grad(False)
+        for i in in_train:
+            if not hasattr(self, f"base_encoding_{i}"):
+                self.add_table(i)
+                self.load_table(i, strict=False)
+            enc = getattr(self, f"base_encoding_{i}")
+            enc.set_require_grad(True)
+            enc.train()
+        for i in sorted(set(range(self.n_blocks)) - set(in_train) - set(in_test)):
+            if hasattr(self, f"base_encoding_{i}"):
+                self.save_table(i)
+                self.del_table(i)
+        if self.training:
+            self.active_block_idxs = active
+        else:
+            self.active_block_idxs_test = active
+
+    def memory_stats(self):
+        print(f"Allocated Memory: {torch.cuda.memory_allocated() / 1024 ** 3:.2f} GB")
+        print(f"Cached Memory: {torch.cuda.memory_reserved() / 1024 ** 3:.2f} GB")
 
     def set_stage(self, stage: str, active_block: Optional[int] = None) -> None:
         """'init_stage' (global table + MLPs + embedding train) or 'block_stage' (they are frozen, the active
