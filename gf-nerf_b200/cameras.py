@@ -34,6 +34,12 @@ class Cameras:
     def __len__(self):
         return int(self.camera_to_worlds.shape[0])
 
+    def get_intrinsics_matrices(self) -> torch.Tensor:
+        """K [n,3,3] (nerfstudio/cameras/cameras.py get_intrinsics_matrices)"""
+        K = torch.zeros((len(self), 3, 3), dtype=torch.float32, device=self.device)
+        K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = self.fx, self.fy, self.cx, self.cy, 1.0
+        return K
+
     @torch.no_grad()
     def generate_rays(self, camera_indices: torch.Tensor, coords: torch.Tensor) -> RayBundle:
         _lib.require_cuda(camera_indices, coords)

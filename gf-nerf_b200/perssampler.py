@@ -489,15 +489,25 @@ class PersSampler(nn.Module):
     """Drop-in for reference gfnerf/perssampler.py:47-447 (`generate_ray_samples` returns the same dense
     RaySamples structure; see rays.py)."""
 
-    def __init__(self, c2w, intri, bounds, n_split_dataset=10, steps_per_split_dataset=10000,
+    def __init__(self, c2w=None, intri=None, bounds=None, n_split_dataset=10, steps_per_split_dataset=10000,
                  steps_perssampler_init=30000, split_dist_thres: float = 1.5,
                  sub_div_milestones=(2000, 4000, 6000, 8000, 10000), compact_freq: int = 1000,
                  max_oct_intersect_per_ray: int = 1024, global_near: float = 0.01, scale_by_dis: bool = True,
                  bbox_levels: int = 8, sample_l: float = 1.0 / 256, max_level: int = 16, mode: int = 0,
                  sampled_oct_per_ray: int = 512, ray_march_fineness: float = 1.0, ray_march_init_fineness=16.0,
-                 ray_march_fineness_decay_end_iter=10000, device=None, seed: int = 0, octree: PersOctree = None):
+                 ray_march_fineness_decay_end_iter=10000, device=None, seed: int = 0, octree: PersOctree = None,
+                 cameras=None):
+        """Either (c2w [n,3,4], intri [n,3,3], bounds [n,2]) or, as the reference's call site does
+        (gfnerf/nerfacto.py:223-227), `cameras=` an object with `camera_to_worlds` and `get_intrinsics_matrices()`
+        (nerfstudio's Cameras / gfnerf_b200.Cameras) plus `bounds=` (perssampler.py:78-86)."""
         super().__init__()
-        c2w = torch.as_tensor(c2w, dtype=torch.float32)
+        if cameras is not None:
+            self.cameras = cameras
+            c2w, intri = cameras.camera_to_worlds, cameras.get_intrinsics_matrices()
+        if c2w is None or intri is None or bounds is None:
+            raise TypeError("PersSampler: pass cameras= and bounds=, or c2w, intri and bounds")
+        c2w = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()
+        intri = torch.as_tensor(intri, dtype=torch.float32).detach().cpu()
         n = c2w.shape[0]
         w2c = torch.eye(4).unsqueeze(0).repeat(n, 1, 1)
         w2c[:, :3, :] = c2w
