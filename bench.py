@@ -412,7 +412,9 @@ def main():
     tp = tps[-1] if tps else ""
     if tp:
         with open(tp) as f:
-            traffic = {k: v["dram_bytes_per_launch"] for k, v in json.load(f)["kernels"].items()}
+            cap = json.load(f)
+            # kernels whose memory behaviour changed after the capture are listed as stale there: null, not a stale number
+            traffic = {k: v["dram_bytes_per_launch"] for k, v in cap["kernels"].items() if k not in cap.get("stale", [])}
     for k in kernels:
         if k["kernel"] in traffic:
             k["traffic"] = traffic[k["kernel"]]
