@@ -215,6 +215,12 @@ def test_live_mark_invisible_nodes_is_the_reference_kernel(rig):
     assert 0 < ref_invisible.sum() < (tidx0 != -1).sum()
     # borderline nodes (a frustum edge within fp rounding of the node's bounding sphere) may fall either way
     assert (mine_marks != ref_invisible).sum() <= 2, ((mine_marks != ref_invisible).sum(), ref_invisible.sum())
+    # the whole method on host tensors: the node blob it leaves is the blob the reference kernel leaves
+    core = PersSamplerCore.__new__(PersSamplerCore)
+    core.tree_nodes_gpu_ = T(rig["tree_nodes"].copy())
+    core.w2c_, core.intri_, core.bound_ = T(w2c), T(intri), T(bound)
+    core.MarkInvisibleNodes()
+    assert (core.tree_nodes_gpu_.numpy() != nodes_ref).sum() <= 2 * 8
 
 
 @live
