@@ -350,10 +350,19 @@ class PersSamplerCore:
     def UpdateBlockIdxs(self, centers: torch.Tensor):
         """SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-798): nearest block centre per node, then compact."""
         nodes = self.tree_nodes_gpu_.view(-1, 128)
-        center = nodes[:, :12].contiguous().view(torch.float32)
-        d = torch.linalg.norm(center.double()[:, None] - centers.to(self.device).double()[None], dim=-1)
-        nodes[:, 104:112] = torch.argmin(d, dim=-1).to(torch.int64).view(-1, 1).view(torch.uint8)
+        nodes[:, 104:112] = self.nearest_block(nodes, centers.to(nodes.device)).view(-1, 1).view(torch.uint8)
         self.ProcOctree(True, False, False)
+
+    @staticmethod
+    def nearest_block(nodes: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+        """int64 [n_nodes]: index of the block centre nearest to each node centre (SetBlockIdxsNearestKernel,
+        PersSampler_cuda.cu:746-766: fp32 norm, strict `<`, so the first of equal minima)."""
+        center = nodes[:, :12].contiguous().view(torch.float32)
+        d = torch.linalg.norm(center[:, None] - centers.float()[None], dim=-1)
+        # first minimum explicitly (torch.argmin does not promise which of equal minima it returns)
+        is_min = d == d.min(dim=-1, keepdim=True).values
+        idx = torch.arange(d.shape[1], device=d.device).expand_as(d)
+        return torch.where(is_min, idx, torch.full_like(idx, d.shape[1])).min(dim=-1).values.to(torch.int64)
 
     def UpdateMode(self, mode: int):
         self.mode_ = int(mode)

@@ -224,16 +224,19 @@ def test_live_mark_invisible_nodes_is_the_reference_kernel(rig):
 
 
 @live
-def test_live_block_index_and_visibility_kernels(rig):
-    """SetBlockIdxsNearestKernel / MarkInvisibleNodesKernel (PersSampler_cuda.cu:680-766) against the host mirror."""
-    from gfnerf_b200 import persoctree as po
-    nodes_ref = rig["tree_nodes"].copy()
+def test_live_nearest_block_is_the_reference_kernel(rig):
+    """PersSamplerCore.nearest_block (what UpdateBlockIdxs writes into the nodes) against SetBlockIdxsNearestKernel
+    (PersSampler_cuda.cu:746-766), incl. exact ties (duplicated centres: the first wins, strict `<`)."""
+    import torch
+    from gfnerf_b200.perssampler import PersSamplerCore
     centers = np.random.RandomState(0).uniform(-4, 4, size=(5, 3)).astype(np.float32)
+    centers = np.concatenate([centers, centers[1:3]], 0)                      # blocks 5, 6 duplicate 1, 2
+    nodes_ref = rig["tree_nodes"].copy()
     rh.set_block_idxs(nodes_ref, centers)
-    nc = nodes_ref.view(np.float32).reshape(-1, 32)[:, :3]
-    want = np.linalg.norm(nc[:, None, :].astype(np.float32) - centers[None], axis=-1).argmin(1)
-    got = nodes_ref.view(np.int64).reshape(-1, 16)[:, 13]
-    assert (got == want).mean() > 0.999                                      # ties / fp32-vs-fp64 norm aside
+    want = nodes_ref.view(np.int64).reshape(-1, 16)[:, 13]
+    got = PersSamplerCore.nearest_block(torch.from_numpy(rig["tree_nodes"].copy()).view(-1, 128),
+                                        torch.from_numpy(centers)).numpy()
+    assert want.max() <= 4 and (got != want).sum() <= 2, (got != want).sum()  # (fp32 norm rounding at near-ties)
 
 
 def _history(rig, trial, rng):
