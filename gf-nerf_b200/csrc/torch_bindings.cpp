@@ -425,8 +425,9 @@ struct PersSamplerImpl : torch::CustomClassHolder {
   void UpdateBlockIdxs(const Tensor& centers) {
     c10::cuda::CUDAGuard guard(tree_nodes_.device());
     auto nodes = tree_nodes_.view({-1, GF_TREE_NODE_BYTES});
-    auto center = nodes.slice(1, 0, 12).contiguous().view(torch::kFloat32).to(torch::kFloat64);
-    auto c = centers.to(tree_nodes_.device()).to(torch::kFloat64);
+    // fp32 norm like the kernel (:758), first of equal minima like its strict `<` (torch::argmin returns the first)
+    auto center = nodes.slice(1, 0, 12).contiguous().view(torch::kFloat32);
+    auto c = centers.to(tree_nodes_.device()).to(torch::kFloat32);
     auto d = torch::linalg_norm(center.unsqueeze(1) - c.unsqueeze(0), 2, {-1}, false);
     auto best = torch::argmin(d, -1).to(torch::kInt64).contiguous();
     nodes.slice(1, 104, 112).copy_(best.view({-1, 1}).view(torch::kUInt8));

@@ -359,10 +359,7 @@ class PersSamplerCore:
         PersSampler_cuda.cu:746-766: fp32 norm, strict `<`, so the first of equal minima)."""
         center = nodes[:, :12].contiguous().view(torch.float32)
         d = torch.linalg.norm(center[:, None] - centers.float()[None], dim=-1)
-        # first minimum explicitly (torch.argmin does not promise which of equal minima it returns)
-        is_min = d == d.min(dim=-1, keepdim=True).values
-        idx = torch.arange(d.shape[1], device=d.device).expand_as(d)
-        return torch.where(is_min, idx, torch.full_like(idx, d.shape[1])).min(dim=-1).values.to(torch.int64)
+        return torch.argmin(d, dim=-1).to(torch.int64)      # torch returns the first of equal minima, like the strict `<`
 
     def UpdateMode(self, mode: int):
         self.mode_ = int(mode)
