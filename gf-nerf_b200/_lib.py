@@ -57,6 +57,7 @@ _SIGS = {
     "gf_charbonnier": [_i64, _vp, _vp, _f32, _vp, _vp, _vp],
     "gf_grad_nan_scan": [_i64, _vp, _vp, _vp],
     "gf_adam_step_guarded": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _int, _vp, _vp],
+    "gf_adam_step_counted": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _int, _vp, _vp],
     "gf_adam_step": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _int, _vp],
 }
 

@@ -62,7 +62,14 @@ class _Adam:
         self.grad = torch.zeros_like(param) if grad is None else grad
         self.m = torch.zeros_like(param)
         self.v = torch.zeros_like(param)
-        self.t = 0
+        # the step count lives on the device: a step skipped by the NaN guard must not advance the bias correction
+        # (the reference skips optimizer.step() altogether, trainer.py:416-426)
+        self.d_step = torch.zeros(1, dtype=torch.int64, device=param.device)
+
+    @property
+    def t(self) -> int:
+        """steps applied so far (host sync; for tests / checkpoints)"""
+        return int(self.d_step.item())
 
     def unscaled_grad(self) -> torch.Tensor:
         """The gradient in units of dL/dparam (a copy when grad_scale != 1; exact, the scale is a power of two)."""
@@ -70,12 +77,12 @@ class _Adam:
 
     def step(self, shadow=None, grad_div=1.0, lr=None, skip_flag=None):
         """skip_flag: device int32 set by gf_grad_nan_scan -- non-zero leaves the parameters untouched (the trainer's
-        NaN guard, trainer.py:416-426; the host-side step counter is not rewound)"""
-        self.t += 1
-        _lib.check(_lib.lib().gf_adam_step_guarded(
+        NaN guard, trainer.py:416-426) and does not count as a step"""
+        _lib.check(_lib.lib().gf_adam_step_counted(
             self.n_active, _lib.ptr(self.param), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v),
-            _lib.ptr(shadow), float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.t,
-            float(grad_div) * self.grad_scale, 1, _lib.ptr(skip_flag), _lib.cur_stream()), "gf_adam_step_guarded")
+            _lib.ptr(shadow), float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
+            _lib.ptr(self.d_step), float(grad_div) * self.grad_scale, 1, _lib.ptr(skip_flag), _lib.cur_stream()),
+            "gf_adam_step_counted")
 
 
 @dataclass
@@ -116,7 +123,7 @@ class GFNeRFEngine:
         self.n_volumes = max(int(sampler.n_volumes_), 1)
         self.enc = Hash3DAnchoredCore(log2_table_size, self.n_volumes, device=self.device, generator=gen)
         self.enc.feat_pool_.requires_grad_(False)
-        self.enc.Reset()   # U(-0.01, 0.01), gfnerf/nerfacto_field.py:200
+        self.enc.Reset(generator=gen)   # U(-0.01, 0.01), gfnerf/nerfacto_field.py:200; reproducible from `seed`
         self.mlp = init_mlp_params(hidden, gen, self.device)
         self.emb = (torch.randn(num_images, APPEARANCE_DIM, generator=gen).to(self.device)
                     if use_appearance_embedding else None)
@@ -127,11 +134,16 @@ class GFNeRFEngine:
         self.opt_mlp = _Adam(self.mlp, lr_mlp, grad=small.views[0])
         self.opt_emb = _Adam(self.emb.view(-1), lr_mlp, grad=small.views[1].view(-1)) if self.emb is not None else None
         self._small_grads = small.flat
-        self.enc.shadow(force=True)
         self.sync = GradSync(dist_group, self.device)
         self.world = self.sync.world
         if self.world > 1:
+            # identical initial parameters on every replica, whatever seed each rank was built with (what DDP's
+            # constructor does; ranks seeded seed + rank -- ddp.rank_seed -- would otherwise average gradients of
+            # different tables forever)
+            self.sync.broadcast_([self.enc.feat_pool_.data, self.enc.prim_pool_, self.enc.bias_pool_, self.mlp]
+                                 + ([self.emb] if self.emb is not None else []))
             sampler.vote_reduce = self.sync.max_
+        self.enc.shadow(force=True)
         self._ws = {}
         self.step_count = 0
         self._deferred = None   # lr_scale of an optimizer step whose gradient reduce is still in flight

@@ -4,7 +4,7 @@ Mirrors reference gfnerf/nerfacto_field.py: constructor arguments and sub-module
 + `get_outputs` as one `forward` (:412-591; `Field.forward`, nerfstudio/fields/base_field.py:108-129, is the only
 caller, gfnerf/nerfacto.py:535), the per-block residual tables of the focal stage (`add_table / del_table /
 save_table / load_table`, :248-403; residual added to the hash features before the frozen MLP, :458-489), and
-`parameters()` (:593-603).  State-dict keys match the reference (`base_network.model.N.*`, `mlp_head.model.N.*`,
+`parameters()` (:593-603).  State-dict keys match the reference (`base_network.layers.N.*`, `mlp_head.layers.N.*`,
 `embedding_appearance.embedding.weight`, `base_encoding_init.{feat_pool,prime_pool,bias_pool,n_volumes}`).
 
 What differs, by design: the field evaluates only the VALID samples of the dense `[R,1024]` layout (the reference

@@ -213,14 +213,25 @@ class Hash3DAnchoredCore:
         self.n_volumes_ = int(states[idx].item()); idx += 1
         if self.bias_pool_.shape[0] != N_LEVELS * self.n_volumes_:
             self.bias_pool_ = torch.zeros((N_LEVELS * self.n_volumes_, 3), dtype=torch.float32, device=self.device)
+        # `.data.copy_()` does not bump `_version`: drop both cached decisions (fp16 shadow, all-zero bias) by hand
         self._shadow_key = None
+        self._bias_key = None
         return idx
 
-    def Reset(self) -> None:
-        self.feat_pool_.data.uniform_(-1e-2, 1e-2)
+    def Reset(self, generator: torch.Generator = None) -> None:
+        """U(-0.01, 0.01) (Hash3DAnchored.cpp Reset).  `generator` (a CPU generator) makes the table reproducible
+        from a seed -- the draw then happens on the host and is copied; without it the device's global RNG is used
+        like the reference does."""
+        if generator is None:
+            self.feat_pool_.data.uniform_(-1e-2, 1e-2)
+        else:
+            host = torch.empty(self.feat_pool_.shape, dtype=torch.float32).uniform_(-1e-2, 1e-2, generator=generator)
+            self.feat_pool_.data.copy_(host)
+        self._shadow_key = None
 
     def Zero(self) -> None:
         self.feat_pool_.data.zero_()
+        self._shadow_key = None
 
     def SetFeatPoolRequireGrad(self, require_grad: bool) -> None:
         self.feat_pool_.requires_grad_(require_grad)

@@ -1,6 +1,8 @@
 """`MLPNetwork` with the constructor and parameter naming of the reference (gfnerf/mlp.py:3-57): a stack of
-`nn.Linear` (+bias) with ReLU between layers, configured by a tiny-cuda-nn style dict.  State dicts are
-interchangeable with the reference's (`model.<i>.weight / .bias`).
+`nn.Linear` (+bias) with ReLU between layers, configured by a tiny-cuda-nn style dict.  The Linears live in
+`self.layers = nn.ModuleList()` with contiguous indices exactly like the reference (gfnerf/mlp.py:35-43), so state
+dicts are interchangeable with the reference's (`layers.<i>.weight / .bias`; tests/test_field_tables.py loads one
+produced by the reference's own class).
 
 On its own it is a parameter container: GF-NeRF never runs one of these stacks alone -- the density net and the
 colour head are evaluated together by the fused tensor-core kernels (csrc/mlp.cu) through
@@ -21,17 +23,15 @@ class MLPNetwork(nn.Module):
         self.output_activation = network_config.get("output_activation", "None")
         if self.activation != "ReLU":
             raise ValueError("gfnerf_b200 MLPNetwork: only ReLU hidden activations are built")
-        layers, d = [], self.n_input_dims
+        self.layers = nn.ModuleList()
+        d = self.n_input_dims
         for _ in range(self.n_hidden_layers):
-            layers += [nn.Linear(d, self.n_neurons), nn.ReLU()]
+            self.layers.append(nn.Linear(d, self.n_neurons))
             d = self.n_neurons
-        layers.append(nn.Linear(d, self.n_output_dims))
-        if self.output_activation == "Sigmoid":
-            layers.append(nn.Sigmoid())
-        self.model = nn.Sequential(*layers)
+        self.layers.append(nn.Linear(d, self.n_output_dims))
 
     def linears(self):
-        return [m for m in self.model if isinstance(m, nn.Linear)]
+        return list(self.layers)
 
     def flat_params(self) -> torch.Tensor:
         """weights then bias of every layer, nn.Linear layout -- the blob order of include/gfnerf_b200.h"""

@@ -350,6 +350,12 @@ int gf_grad_nan_scan(int64_t n, const float* grad, int32_t* flag, void* stream);
 int gf_adam_step_guarded(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                          void* shadow_f16, float lr, float beta1, float beta2, float eps,
                          int64_t step, float grad_div, int zero_grad, const int32_t* skip_flag, void* stream);
+/* gf_adam_step_guarded whose step count lives on the device: the bias corrections use *d_step + 1 and *d_step is
+ * advanced only when the step was applied -- a step skipped by the NaN guard does not exist for the optimizer, as in
+ * the reference, which skips optimizer.step() altogether (trainer.py:416-426).  d_step: device int64, starts at 0. */
+int gf_adam_step_counted(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                         void* shadow_f16, float lr, float beta1, float beta2, float eps,
+                         int64_t* d_step, float grad_div, int zero_grad, const int32_t* skip_flag, void* stream);
 
 /* ---- ray generation (the step before the path) --------
  * Cameras.generate_rays for PERSPECTIVE cameras without distortion (nerfstudio/cameras/cameras.py:583-727, with

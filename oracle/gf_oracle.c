@@ -381,8 +381,12 @@ static inline void query_frame_transform(const trans_info* tr, const float* p, f
     v[i] = xz[0] / xz[1];
   }
   for (int r = 0; r < 3; r++) {
-    float acc = tr->weight[r][0] * v[0];
-    for (int k = 1; k < N_PROS; k++) acc = fmaf(tr->weight[r][k], v[k], acc);
+    /* w0 v0 + w1 v1 + w2 v2 + ... under nvcc's contraction: the SECOND product is the rounded one,
+     * t = w1 v1; t = fma(w0, v0, t); t = fma(w2, v2, t); ...  (read off the SASS of the reference's RayMarchKernel
+     * built by nvcc for sm_100a, profiles/r02a_ref_march_sass_notes.md; ours beside it on the B200 is bit-equal) */
+    float acc = tr->weight[r][1] * v[1];
+    acc = fmaf(tr->weight[r][0], v[0], acc);
+    for (int k = 2; k < N_PROS; k++) acc = fmaf(tr->weight[r][k], v[k], acc);
     out[r] = acc;
   }
 }
@@ -487,7 +491,11 @@ void orc_sampler_get_samples(int64_t n_rays, const float* rays_o, const float* r
             }
             pts_ptr += 1;
           }
-          while (cur_t + cur_march_step > cur_far) {
+          /* nvcc fuses `cur_march_step = exp_march_step * float(ex_march_steps)` into both of its consumers, the loop
+           * condition and `cur_t += cur_march_step` (SASS of the reference kernel: FFMA R3 = exp * ex + cur_t;
+           * FSETP.GT R3, cur_far; ... MOV cur_t, R3): the position after a crossing is rounded once */
+          float next_t = cur_t + cur_march_step;
+          while (next_t > cur_far) {
             oct_ptr++;
             if (oct_ptr >= n_oct_nodes) break;
             cur_oct_idx = oct_idx[oct_ptr];
@@ -495,8 +503,9 @@ void orc_sampler_get_samples(int64_t n_rays, const float* rays_o, const float* r
             cur_far = oct_nf[2 * oct_ptr + 1];
             int64_t ex_march_steps = (int64_t)ceilf(fmaxf((cur_near - cur_t) / exp_march_step, 1.f));
             cur_march_step = exp_march_step * (float)ex_march_steps;
+            next_t = fmaf(exp_march_step, (float)ex_march_steps, cur_t);
           }
-          cur_t += cur_march_step;
+          cur_t = next_t;
           for (int c = 0; c < 3; c++) cur_xyz[c] = fmaf(d[c], cur_t, o[c]);
           the_first_pts = 0;
         }

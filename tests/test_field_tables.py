@@ -103,3 +103,45 @@ def test_update_active_blocks_keeps_only_the_active_tables_resident(tmp_path, mo
     assert hasattr(f, "base_encoding_2")                         # the training block stays resident
     f.update_active_blocks(-1)                                   # no eval block any more
     assert f.active_block_idxs_test == [] and not hasattr(f, "base_encoding_1") and hasattr(f, "base_encoding_2")
+
+
+# ---- MLPNetwork: parameter names of the reference's own class (gfnerf/mlp.py:35-43) ---------------------------------
+
+REF_MLP_KEYS = {  # what `MLPNetwork(...).state_dict()` of the reference yields for the two stacks of the field
+    "base": ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias"],
+    "head": ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias", "layers.2.weight",
+             "layers.2.bias"],
+}
+
+
+def _stacks(cls, hidden=64):
+    cfg = lambda act, n: {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": act,
+                          "n_neurons": hidden, "n_hidden_layers": n}
+    return cls(32, 16, cfg("None", 1)), cls(63, 3, cfg("Sigmoid", 2))
+
+
+def test_mlpnetwork_state_dict_keys_are_the_references():
+    from gfnerf_b200.mlp import MLPNetwork
+    base, head = _stacks(MLPNetwork)
+    assert list(base.state_dict().keys()) == REF_MLP_KEYS["base"]
+    assert list(head.state_dict().keys()) == REF_MLP_KEYS["head"]
+
+
+def test_mlpnetwork_loads_a_state_dict_of_the_references_class():
+    """strict load of a state dict produced by the reference's own MLPNetwork (where the reference tree exists)"""
+    import importlib.util
+    import pytest
+    path = "/root/reference/gfnerf/mlp.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    spec = importlib.util.spec_from_file_location("ref_gfnerf_mlp", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from gfnerf_b200.mlp import MLPNetwork
+    for H in (64, 128):
+        for mine, theirs in zip(_stacks(MLPNetwork, H), _stacks(ref.MLPNetwork, H)):
+            assert list(theirs.state_dict().keys()) == list(mine.state_dict().keys())
+            mine.load_state_dict(theirs.state_dict(), strict=True)
+            theirs.load_state_dict(mine.state_dict(), strict=True)
+            ref_flat = torch.cat([torch.cat([l.weight.reshape(-1), l.bias.reshape(-1)]) for l in theirs.layers])
+            assert torch.equal(mine.flat_params(), ref_flat)

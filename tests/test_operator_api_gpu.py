@@ -157,7 +157,7 @@ def test_state_dict_keys_match_reference_names():
     rig = load_rig("rig8")
     _, model = build(rig)
     keys = set(model.state_dict().keys())
-    for k in ("field.base_network.model.0.weight", "field.base_network.model.2.bias", "field.mlp_head.model.4.weight",
+    for k in ("field.base_network.layers.0.weight", "field.base_network.layers.1.bias", "field.mlp_head.layers.2.weight",
               "field.embedding_appearance.embedding.weight", "field.base_encoding_init.feat_pool",
               "field.base_encoding_init.prime_pool", "field.base_encoding_init.bias_pool",
               "field.base_encoding_init.n_volumes", "persampler.tree_nodes_gpu", "persampler.pers_trans_gpu",
