@@ -530,7 +530,7 @@ class PersSampler(nn.Module):
         self.n_split_dataset = n_split_dataset
         self.steps_per_split_dataset = steps_per_split_dataset
         self.steps_perssampler_init = steps_perssampler_init
-        self.register_buffer("c2w", c2w.to(self.sampler.device), persistent=False)      # perssampler.py:130
+        self.register_buffer("c2w", c2w.to(self.sampler.device))      # persistent, like perssampler.py:130
         self.cameras_labels = None    # int64 [n_cams,1] block label of every camera, set by the clustering (:236-237)
         self._register_state_dict_hook(self.state_dict_hook)
 
@@ -556,8 +556,11 @@ class PersSampler(nn.Module):
         """perssampler.py:517-547: takes its four entries (and the cameras) out of the model's state dict."""
         self.load_states([state_dict.pop("persampler." + k) for k in
                           ("tree_nodes_gpu", "pers_trans_gpu", "tree_visit_cnt", "milestones_ts")], 0)
-        if "field.persampler.c2w" in state_dict:
-            self.c2w = state_dict.pop("field.persampler.c2w").to(self.sampler.device)
+        # the reference reads `field.persampler.c2w` (:531); the same module is also reachable as `persampler`, so a
+        # checkpoint carries the buffer under both names -- consume both, so that a strict load of the rest succeeds
+        for key in ("persampler.c2w", "field.persampler.c2w"):
+            if key in state_dict:
+                self.c2w = state_dict.pop(key).to(self.sampler.device)
         return None
 
     # read-only views of the native sampler's configuration, under the reference's names (perssampler.py:583-623)
