@@ -50,8 +50,8 @@ _SIGS = {
     "gf_composite_forward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_composite_backward": [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_mlp_ray_bias": [_i64, _int, _vp, _vp, _vp, _vp, _vp],
-    "gf_mlp_forward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "gf_mlp_backward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp],
+    "gf_mlp_forward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gf_mlp_backward": [_i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp],
     "gf_mlp_ray_bias_backward": [_i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gf_s3im": [_i64, _i64, _vp, _vp, _vp, _int, _int, _int, _f32, _vp, _vp, _vp],
     "gf_charbonnier": [_i64, _vp, _vp, _f32, _vp, _vp, _vp],
@@ -65,8 +65,10 @@ EXPORTS = ["gf_last_error", "gf_version", "gf_launch_count", "gf_mlp_param_count
 
 
 def lib():
-    global _lib
+    global _lib, LIB_PATH
     if _lib is None:
+        # development only (tools/mlp_variants.py A/B builds): another build of the SAME library
+        LIB_PATH = os.environ.get("GF_LIB_OVERRIDE", LIB_PATH)
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python gf-nerf_b200/build.py` "

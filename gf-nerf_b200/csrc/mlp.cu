@@ -153,11 +153,13 @@ ray_bias_bwd_kernel(int64_t n_rays, const float* __restrict__ params, const floa
 using namespace gf;
 
 int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
-                         const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, cudaStream_t st);
+                         const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, void* relu_masks,
+                         cudaStream_t st);
 
 int gf_launch_mlp_bwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
-                         const int32_t* ray_id, const float* ray_bias, const float* d_sigma, const float* d_rgb,
-                         void* d_feat, float* d_params, float* d_ray_bias, float gscale, cudaStream_t st);
+                         const int32_t* ray_id, const float* ray_bias, const void* relu_masks, const float* d_sigma,
+                         const float* d_rgb, void* d_feat, float* d_params, float* d_ray_bias, float gscale,
+                         cudaStream_t st);
 
 extern "C" {
 
@@ -188,25 +190,30 @@ int gf_mlp_ray_bias_backward(int64_t n_rays, int hidden, const float* params, co
 }
 
 int gf_mlp_forward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params, const void* feat_f16,
-                   const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, void* stream) {
+                   const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, void* relu_masks,
+                   void* stream) {
   GF_REQUIRE(hidden == kH, "gf_mlp_forward: hidden width %d is not built (64 only)", hidden);
   GF_REQUIRE(n >= 0, "gf_mlp_forward: bad sizes");
   if (n == 0) return GF_OK;
   GF_REQUIRE(params && feat_f16 && ray_id && ray_bias && sigma && rgb, "gf_mlp_forward: null pointer");
-  return gf_launch_mlp_fwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, sigma, rgb, (cudaStream_t)stream);
+  GF_REQUIRE((reinterpret_cast<uintptr_t>(relu_masks) & 15) == 0, "gf_mlp_forward: relu_masks must be 16-byte aligned");
+  return gf_launch_mlp_fwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, sigma, rgb, relu_masks,
+                              (cudaStream_t)stream);
 }
 
 int gf_mlp_backward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params, const void* feat_f16,
-                    const int32_t* ray_id, const float* ray_bias, const float* d_sigma, const float* d_rgb,
+                    const int32_t* ray_id, const float* ray_bias, const void* relu_masks, const float* d_sigma,
+                    const float* d_rgb,
                     void* d_feat_scaled_f16, float* d_params, float* d_ray_bias, float grad_scale, void* stream) {
   GF_REQUIRE(hidden == kH, "gf_mlp_backward: hidden width %d is not built (64 only)", hidden);
   GF_REQUIRE(n >= 0 && grad_scale > 0.f, "gf_mlp_backward: bad sizes");
   if (n == 0) return GF_OK;
-  GF_REQUIRE(params && feat_f16 && ray_id && ray_bias && d_sigma && d_rgb && d_feat_scaled_f16,
+  GF_REQUIRE(params && feat_f16 && ray_id && ray_bias && relu_masks && d_sigma && d_rgb && d_feat_scaled_f16,
              "gf_mlp_backward: null pointer");
+  GF_REQUIRE((reinterpret_cast<uintptr_t>(relu_masks) & 15) == 0, "gf_mlp_backward: relu_masks must be 16-byte aligned");
   GF_REQUIRE((d_params == nullptr) == (d_ray_bias == nullptr),
              "gf_mlp_backward: d_params and d_ray_bias go together (both NULL = frozen MLP)");
-  return gf_launch_mlp_bwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, d_sigma, d_rgb, d_feat_scaled_f16,
+  return gf_launch_mlp_bwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, relu_masks, d_sigma, d_rgb, d_feat_scaled_f16,
                               d_params, d_ray_bias, grad_scale, (cudaStream_t)stream);
 }
 

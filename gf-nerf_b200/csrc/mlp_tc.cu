@@ -54,7 +54,9 @@ constexpr int kW0 = 0, kB0 = kW0 + kH * 32, kW1 = kB0 + kH, kB1 = kW1 + 16 * kH,
 constexpr int kTile = 128;  // samples per CTA tile = MMA M
 constexpr int kThreads = 256;
 
-enum Mode { kFwd = 0, kBwdFrozen = 1, kBwdFull = 2 };
+// kFwd: plain fp16 forward (inference: no gradients, no masks).  kFwdSplit: the split-precision training forward that
+// also writes the ReLU masks the backward modes consume.
+enum Mode { kFwd = 0, kBwdFrozen = 1, kBwdFull = 2, kFwdSplit = 3 };
 
 #ifdef GF_MLP_TRACE
 // profiling build only (tools/mlp_trace.py): clock64() of thread 0 / thread 128 of CTA 0 at the phase boundaries of
@@ -263,29 +265,59 @@ __device__ __forceinline__ void bias_relu_pack32(const uint32_t (&v)[32], const 
     out[2 * q + 1] = relu_h2(pack_h2(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w));
   }
 }
-// split-precision epilogue: accumulator row (+ optional fp32 bias row) -> ReLU -> fp16 hi / lo pairs + the mask word
+// split-precision epilogue of a 64-wide layer for this thread's 32 columns: accumulator (+ optional fp32 bias row)
+// -> ReLU -> fp16 hi (and lo) pairs written straight back to TMEM as the next layer's A operand(s); returns the
+// ReLU-mask word.  Works in two 16-column parts to stay inside the forward's 64-register budget.
 template <bool WITH_BIAS, bool WITH_LO>
-__device__ __forceinline__ void split_relu_pack32(const uint32_t (&v)[32], const float* bias, uint32_t (&hi)[16],
-                                                  uint32_t (&lo)[16], uint32_t& mask) {
+__device__ __forceinline__ uint32_t split_epilogue(uint32_t lane_addr, int hf, const float* bias) {
   const __half2 zero = __float2half2_rn(0.f);
   uint32_t m = 0u;
+#ifdef GF_MLP_SPLIT_LD32
+  uint32_t vv[2][16];   // both halves in flight before the first wait (needs the registers: GF_MLP_SPLIT_CTAS <= 3)
+  tmem_ld16(lane_addr + kColD + 32 * hf, vv[0]);
+  tmem_ld16(lane_addr + kColD + 32 * hf + 16, vv[1]);
+  tmem_wait_ld();
+#endif
 #pragma unroll
-  for (int q4 = 0; q4 < 8; q4++) {
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (WITH_BIAS) b = __ldg(reinterpret_cast<const float4*>(bias) + q4);
-    const float x[4] = {__uint_as_float(v[4 * q4]) + b.x, __uint_as_float(v[4 * q4 + 1]) + b.y,
-                        __uint_as_float(v[4 * q4 + 2]) + b.z, __uint_as_float(v[4 * q4 + 3]) + b.w};
+  for (int part = 0; part < 2; part++) {
+    uint32_t hi[8], lo[8];
+#ifdef GF_MLP_SPLIT_LD32
+    const uint32_t (&v)[16] = vv[part];
+#else
+    uint32_t v[16];
+    tmem_ld16(lane_addr + kColD + 32 * hf + 16 * part, v);
+    tmem_wait_ld();
+#endif
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const int q = 2 * q4 + e;
-      const float a = x[2 * e], c = x[2 * e + 1];
-      const float ah = trunc11(a), ch = trunc11(c);
-      hi[q] = pack_relu_h2(ah, ch);
-      if (WITH_LO) lo[q] = pack_relu_h2(a - ah, c - ch);   // same sign as the value: ReLU zeroes it with the hi part
-      m |= __hgt2_mask(*reinterpret_cast<const __half2*>(&hi[q]), zero) & mask_bits_of_pair(q);
+    for (int q4 = 0; q4 < 4; q4++) {
+      float x[4] = {__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
+                    __uint_as_float(v[4 * q4 + 3])};
+      if (WITH_BIAS) {   // (an unconditional "+ 0.f" would not fold: -0.f + 0.f)
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + 4 * part + q4);
+        x[0] += b.x;
+        x[1] += b.y;
+        x[2] += b.z;
+        x[3] += b.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float a = x[2 * e], c = x[2 * e + 1];
+        if (WITH_LO) {
+          const float ah = trunc11(a), ch = trunc11(c);
+          hi[2 * q4 + e] = pack_relu_h2(ah, ch);
+          // the remainder has the sign of the value: the conversion's ReLU zeroes it together with the hi part
+          lo[2 * q4 + e] = pack_relu_h2(a - ah, c - ch);
+        } else {
+          hi[2 * q4 + e] = pack_relu_h2(a, c);   // no lo part wanted: plain round-to-nearest fp16
+        }
+        m |= __hgt2_mask(*reinterpret_cast<const __half2*>(&hi[2 * q4 + e]), zero) &
+             mask_bits_of_pair(8 * part + 2 * q4 + e);
+      }
     }
+    tmem_st8(lane_addr + kColA + 16 * hf + 8 * part, hi);
+    if (WITH_LO) tmem_st8(lane_addr + kColAlo + 16 * hf + 8 * part, lo);
   }
-  mask = m;
+  return m;
 }
 // gradient row masked by the forward's ReLU-mask word -> 16 packed pairs.  Pair q < 8: its two bits sit at 7 - q and
 // 23 - q, so after a left shift by q they are the sign bits of bytes 0 and 2, which PRMT (selector nibble | 8 =
@@ -293,7 +325,8 @@ __device__ __forceinline__ void split_relu_pack32(const uint32_t (&v)[32], const
 __device__ __forceinline__ void mask_bits_pack32(const uint32_t (&v)[32], uint32_t mask, uint32_t (&out)[16]) {
 #pragma unroll
   for (int q = 0; q < 16; q++) {
-    const uint32_t sel = __byte_perm(mask << (q & 7), 0u, q < 8 ? 0xAA88u : 0xBB99u);
+    uint32_t sel;   // (__byte_perm only takes 3-bit selectors; the sign-replicate bit needs the PTX form)
+    asm("prmt.b32 %0, %1, %2, %3;\n" : "=r"(sel) : "r"(mask << (q & 7)), "r"(0u), "r"(q < 8 ? 0xAA88u : 0xBB99u));
     out[q] = pack_h2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])) & sel;
   }
 }
@@ -358,22 +391,43 @@ __device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const uint3
   }                            \
   GF_TR()
 
+// relu_masks: uint4 per (sample, column half): {mask h1, mask h2, mask h3, 0} -- written by the forward (may be
+// NULL: render), read by the backward
+// Registers (measured with tools/mlp_variants.py on the bench's sample count, r02e): the plain forward runs 4 CTAs per
+// SM at 64 registers; the split forward 3 per SM at 80 with both accumulator halves in flight (0.497 ms; 4 per SM
+// with 36 bytes of spills: 0.511); the backward modes 2 per SM uncapped (126 registers, 1.08 ms; capped at 112 -- what
+// would leave room for a sampler CTA underneath -- 16-36 bytes of spills cost 0.11 ms, more than the overlap gives).
+#ifndef GF_MLP_BWD_REGS
+#define GF_MLP_BWD_REGS 128
+#endif
+#ifndef GF_MLP_SPLIT_CTAS
+#define GF_MLP_SPLIT_CTAS 3   // resident CTAs per SM of the split forward (4 -> 64 registers, 3 -> 80, 2 -> 128)
+#endif
+#if GF_MLP_SPLIT_CTAS <= 3 && !defined(GF_MLP_SPLIT_LD16)
+#define GF_MLP_SPLIT_LD32 1
+#endif
+constexpr int min_ctas(int mode) { return mode == kFwd ? 4 : mode == kFwdSplit ? GF_MLP_SPLIT_CTAS : 2; }
+constexpr int max_regs(int mode) {
+  return mode == kFwd ? 64 : mode == kFwdSplit ? (GF_MLP_SPLIT_CTAS == 4 ? 64 : GF_MLP_SPLIT_CTAS == 3 ? 80 : 128)
+                                               : GF_MLP_BWD_REGS;
+}
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, MODE == kFwd ? 4 : 2)
+__global__ void __launch_bounds__(kThreads, min_ctas(MODE)) __maxnreg__(max_regs(MODE))
 mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __restrict__ params,
               const __half* __restrict__ feat, const int32_t* __restrict__ ray_id,
               const float* __restrict__ ray_bias, float* __restrict__ sigma, float* __restrict__ rgb,
-              const float* __restrict__ d_sigma, const float* __restrict__ d_rgb, __half* __restrict__ d_feat,
-              float* __restrict__ d_params, float* __restrict__ d_ray_bias, float gscale) {
+              uint4* __restrict__ relu_masks, const float* __restrict__ d_sigma, const float* __restrict__ d_rgb,
+              __half* __restrict__ d_feat, float* __restrict__ d_params, float* __restrict__ d_ray_bias, float gscale) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr bool WGRAD = MODE == kBwdFull;
-  constexpr bool BWD = MODE != kFwd;
+  constexpr bool BWD = MODE == kBwdFull || MODE == kBwdFrozen;
+  constexpr bool SPLIT = MODE == kFwdSplit;   // split-precision forward (see the header)
   constexpr uint32_t kCols = WGRAD ? 256u : 128u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = 32 * (warp & 3) + lane;  // row of the tile = TMEM lane
   const int hf = warp >> 2;              // column half
   const float inv_gscale = BWD ? 1.f / gscale : 1.f;
-  stage_weights(params, smem);
+  stage_weights<SPLIT>(params, smem);
   const uint32_t bar = smem_u32(smem + kOffBar), bar_w = smem_u32(smem + kOffBarW);
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -424,6 +478,9 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
 #endif
     int ray = rayn;
     uint4 x0 = xn0, x1 = xn1;
+    // backward: the forward's ReLU masks of this thread's 32 columns (h1, h2, h3); first used half a tile from here
+    uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+    if (BWD && valid) mk = __ldg(relu_masks + 2 * row + hf);
     if (!kRegAhead) {
       ray = -1;
       x0 = x1 = make_uint4(0u, 0u, 0u, 0u);
@@ -445,7 +502,8 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       }
     }
     const int64_t nrow = row + (int64_t)gridDim.x * kTile;
-    uint32_t h1p[16], h2p[16], h3p[16];  // post-ReLU activations of this thread's column half (the ReLU masks)
+    uint32_t h1p[16], h2p[16], h3p[16];  // post-ReLU activations of this thread's column half
+    uint32_t m1 = 0u, m2 = 0u, m3 = 0u;  // forward: their ReLU masks
     float pre = 0.f;                      // density logit + 1 (hf == 0)
     // ---- input: features 16 hf .. 16 hf + 15 of this row -> A columns [8 hf, 8 hf + 8) (+ X tile) -------------
     {
@@ -478,11 +536,18 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
         if (hf == 0) prefetch_l2(d_rgb + 3 * nrow);
         else prefetch_l2(d_sigma + nrow);
       }
+      if (BWD && (lane & 3) == 0) prefetch_l2(relu_masks + 2 * nrow + hf);
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 32, true>(tmem, sBe, kOffB0, kOffBb0)))
+    if (SPLIT) {   // the input features ARE fp16 (the hash encoder's output): only the weights carry a lo part
+      GF_TC_SYNC_ISSUE((issue_fwd_split<64, 32, true, false>(tmem, sBe, kOffB0, kOffB0L, kOffBb0)))
+    } else {
+      GF_TC_SYNC_ISSUE((issue_fwd<64, 32, true>(tmem, sBe, kOffB0, kOffBb0)))
+    }
     GF_TC_WAIT()
     // ---- h1 = relu(acc) ----------------------------------------------------------------------------------
-    {
+    if (SPLIT) {
+      m1 = split_epilogue<false, true>(lane_addr, hf, nullptr);
+    } else {
       uint32_t v[32];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
@@ -513,7 +578,11 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
         }
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sBe, kOffB1, kOffBb1)))
+    if (SPLIT) {
+      GF_TC_SYNC_ISSUE((issue_fwd_split<16, 64, true, true>(tmem, sBe, kOffB1, kOffB1L, kOffBb1)))
+    } else {
+      GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sBe, kOffB1, kOffBb1)))
+    }
     GF_TC_WAIT()
     // ---- h = acc; density = exp(h0 + 1); geo features -> A (16 fp16) ------------------------------------------
     if (hf == 0) {
@@ -521,17 +590,41 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       tmem_ld16(lane_addr + kColD, v);
       tmem_wait_ld();
       pre = __uint_as_float(v[0]) + 1.f;
-      if (MODE == kFwd && valid) sigma[row] = expf(pre);  // trunc_exp(h0 + 1), nerfacto_field.py:499
-      a[0] = pack_h2(0.f, __uint_as_float(v[1]));          // column 0 of the geo tile has zero weights
+      if (!BWD && valid) sigma[row] = expf(pre);  // trunc_exp(h0 + 1), nerfacto_field.py:499
+      if (SPLIT) {
+        uint32_t al[8];
+        float hh[16], hl[16];
 #pragma unroll
-      for (int j = 1; j < 8; j++) a[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        for (int j = 0; j < 16; j++) {
+          const float x = __uint_as_float(v[j]);
+          hh[j] = trunc11(x);
+          hl[j] = x - hh[j];
+        }
+        hh[0] = hl[0] = 0.f;                                // column 0 of the geo tile has zero weights
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          a[j] = pack_h2(hh[2 * j], hh[2 * j + 1]);
+          al[j] = pack_h2(hl[2 * j], hl[2 * j + 1]);
+        }
+        tmem_st8(lane_addr + kColAlo, al);
+      } else {
+        a[0] = pack_h2(0.f, __uint_as_float(v[1]));          // column 0 of the geo tile has zero weights
+#pragma unroll
+        for (int j = 1; j < 8; j++) a[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      }
       tmem_st8(lane_addr + kColA, a);
       if (WGRAD) store_chunks<2>(smem + kOffHh, kSboS, r, 0, a);
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 16, false>(tmem, sBe, kOffB2, 0u)))
+    if (SPLIT) {
+      GF_TC_SYNC_ISSUE((issue_fwd_split<64, 16, false, true>(tmem, sBe, kOffB2, kOffB2L, 0u)))
+    } else {
+      GF_TC_SYNC_ISSUE((issue_fwd<64, 16, false>(tmem, sBe, kOffB2, 0u)))
+    }
     GF_TC_WAIT()
     // ---- h2 = relu(acc + ray_bias[ray]) ----------------------------------------------------------------------
-    {
+    if (SPLIT) {
+      m2 = split_epilogue<true, true>(lane_addr, hf, rb);
+    } else {
       uint32_t v[32];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
@@ -542,10 +635,18 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
         if (hf == 0) store_ones(smem + kOffH2, kSboH, r, 8);
       }
     }
-    GF_TC_SYNC_ISSUE((issue_fwd<64, 64, true>(tmem, sBe, kOffB3, kOffBb3)))
+    if (SPLIT) {
+      GF_TC_SYNC_ISSUE((issue_fwd_split<64, 64, true, true>(tmem, sBe, kOffB3, kOffB3L, kOffBb3)))
+    } else {
+      GF_TC_SYNC_ISSUE((issue_fwd<64, 64, true>(tmem, sBe, kOffB3, kOffBb3)))
+    }
     GF_TC_WAIT()
     // ---- h3 = relu(acc) ----------------------------------------------------------------------------------
-    {
+    if (SPLIT) {
+      // (no lo part: the output layer takes h3 as plain fp16 -- no ReLU follows it)
+      m3 = split_epilogue<false, false>(lane_addr, hf, nullptr);
+      if (relu_masks && valid) relu_masks[2 * row + hf] = make_uint4(m1, m2, m3, 0u);
+    } else {
       uint32_t v[32];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
@@ -558,7 +659,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
     }
     GF_TC_SYNC_ISSUE((issue_fwd<16, 64, true>(tmem, sBe, kOffB4, kOffBb4)))
     GF_TC_WAIT()
-    if (MODE == kFwd) {
+    if (!BWD) {
       // ---- rgb = sigmoid(acc) --------------------------------------------------------------------------------
       if (hf == 0) {
         uint32_t v[4];
@@ -601,7 +702,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       uint32_t v[32], g[16];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
-      mask_pack32(v, h3p, g);
+      mask_bits_pack32(v, mk.z, g);
       tmem_st16(lane_addr + kColA + 16 * hf, g);
       GF_TC_WAIT_W()
       if (WGRAD) store_chunks<4>(smem + kOffH3, kSboG, r, 4 * hf, g);  // G3 over H3 (its readers have completed)
@@ -614,7 +715,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       uint32_t v[32], g[16];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
-      mask_pack32(v, h2p, g);
+      mask_bits_pack32(v, mk.y, g);
       tmem_st16(lane_addr + kColA + 16 * hf, g);
       GF_TC_WAIT_W()
       if (WGRAD) store_chunks<4>(smem + kOffH2, kSboG, r, 4 * hf, g);  // G2 over H2
@@ -729,7 +830,7 @@ mlp_tc_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __res
       uint32_t v[32], g[16];
       tmem_ld32(lane_addr + kColD + 32 * hf, v);
       tmem_wait_ld();
-      mask_pack32(v, h1p, g);
+      mask_bits_pack32(v, mk.x, g);
       tmem_st16(lane_addr + kColA + 16 * hf, g);
       GF_TC_WAIT_W()
       if (WGRAD) store_chunks<4>(smem + kOffH1, kSboG, r, 4 * hf, g);  // G1 over H1
@@ -858,7 +959,7 @@ using namespace gf;
 // 512 TMEM columns (a CTA beyond that would sit in tcgen05.alloc until another one exits):
 // 128-column modes: 52 KB -> at most 4 CTAs per SM; full backward: ~102 KB (its tiles) -> 2 CTAs per SM.
 static constexpr int kSmemSmall = 52 * 1024;
-static_assert(tc::kSmemBase <= kSmemSmall, "forward smem");
+static_assert(tc::kSmemFwd <= kSmemSmall, "forward smem");
 
 // the opt-in is per device (context), and one process may drive several: remember it per device ordinal
 static int set_attrs() {
@@ -868,6 +969,8 @@ static int set_attrs() {
   const bool track = dev >= 0 && dev < 64;
   if (!track || !done_dev[dev].load(std::memory_order_acquire)) {
     GF_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<tc::kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSmall));
+    GF_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<tc::kFwdSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemSmall));
     GF_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<tc::kBwdFrozen>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmemSmall));
     GF_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<tc::kBwdFull>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -879,33 +982,42 @@ static int set_attrs() {
 
 // launched by gf_mlp_forward / gf_mlp_backward (mlp.cu)
 int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
-                         const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, cudaStream_t st) {
+                         const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, void* relu_masks,
+                         cudaStream_t st) {
   int rc = set_attrs();
   if (rc) return rc;
   const int64_t tiles = div_up(n, tc::kTile);
+  if (relu_masks) {   // training: split precision + the ReLU masks for gf_mlp_backward
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * GF_MLP_SPLIT_CTAS);
+    tc::mlp_tc_kernel<tc::kFwdSplit><<<grid, tc::kThreads, kSmemSmall, st>>>(
+        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, sigma, rgb, (uint4*)relu_masks, nullptr, nullptr,
+        nullptr, nullptr, nullptr, 1.f);
+    return check_launch("mlp_tc_kernel<fwd split>");
+  }
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 4);
   tc::mlp_tc_kernel<tc::kFwd><<<grid, tc::kThreads, kSmemSmall, st>>>(
       n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, sigma, rgb, nullptr, nullptr, nullptr, nullptr,
-      nullptr, 1.f);
+      nullptr, nullptr, 1.f);
   return check_launch("mlp_tc_kernel<fwd>");
 }
 
 int gf_launch_mlp_bwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
-                         const int32_t* ray_id, const float* ray_bias, const float* d_sigma, const float* d_rgb,
-                         void* d_feat, float* d_params, float* d_ray_bias, float gscale, cudaStream_t st) {
+                         const int32_t* ray_id, const float* ray_bias, const void* relu_masks, const float* d_sigma,
+                         const float* d_rgb, void* d_feat, float* d_params, float* d_ray_bias, float gscale,
+                         cudaStream_t st) {
   int rc = set_attrs();
   if (rc) return rc;
   const int64_t tiles = div_up(n, tc::kTile);
   if (d_params) {
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
     tc::mlp_tc_kernel<tc::kBwdFull><<<grid, tc::kThreads, tc::kSmemFull, st>>>(
-        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, nullptr, nullptr, d_sigma, d_rgb,
-        (__half*)d_feat, d_params, d_ray_bias, gscale);
+        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, nullptr, nullptr, (uint4*)relu_masks, d_sigma,
+        d_rgb, (__half*)d_feat, d_params, d_ray_bias, gscale);
   } else {  // frozen MLP (focal stage): dgrad only
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
     tc::mlp_tc_kernel<tc::kBwdFrozen><<<grid, tc::kThreads, kSmemSmall, st>>>(
-        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, nullptr, nullptr, d_sigma, d_rgb,
-        (__half*)d_feat, nullptr, nullptr, gscale);
+        n, d_n_ptr, params, (const __half*)feat_f16, ray_id, ray_bias, nullptr, nullptr, (uint4*)relu_masks, d_sigma,
+        d_rgb, (__half*)d_feat, nullptr, nullptr, gscale);
   }
   return check_launch("mlp_tc_kernel<bwd>");
 }

@@ -215,13 +215,15 @@ class GFNeRFEngine:
         return t
 
     # ---- forward pieces --------------------------------------------------------------------
-    def _field_forward(self, cs: CompactSamples, ray_emb):
+    def _field_forward(self, cs: CompactSamples, ray_emb, train: bool = False):
+        """train: also keep the forward's ReLU masks (`relu_masks` workspace) for gf_mlp_backward"""
         L, st = _lib.lib(), _lib.cur_stream()
         cap, R = cs.pts01.shape[0], cs.n_rays
         feat = self._buf("feat", (cap, 32), torch.float16)
         sigma = self._buf("sigma", (cap,), torch.float32)
         rgb = self._buf("rgb", (cap, 3), torch.float32)
         ray_bias = self._buf("ray_bias", (R, self.hidden), torch.float32)
+        masks = self._buf("relu_masks", (cap, 2, 4), torch.int32) if train else None
         with self._stage("hash_fwd"):
             self.enc.launch_forward(cs.pts01, cs.anchor, out_f16=feat, d_n_ptr=cs.total, recast=False)
             if self.res is not None:
@@ -231,8 +233,8 @@ class GFNeRFEngine:
                                          _lib.ptr(ray_emb), _lib.ptr(ray_bias), st), "gf_mlp_ray_bias")
         with self._stage("mlp_fwd"):
             _lib.check(L.gf_mlp_forward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
-                                        _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(sigma), _lib.ptr(rgb), st),
-                       "gf_mlp_forward")
+                                        _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(sigma), _lib.ptr(rgb),
+                                        _lib.ptr(masks), st), "gf_mlp_forward")
         return feat, sigma, rgb, ray_bias
 
     def _composite(self, cs: CompactSamples, sigma, rgb, keep: bool):
@@ -355,7 +357,7 @@ class GFNeRFEngine:
             self.flush()   # a deferred optimizer step of the previous iteration lands here
             cap, R = cs.pts01.shape[0], cs.n_rays
             ray_emb = self._ray_emb(rel_camera_indices)
-            feat, sigma, rgb, ray_bias = self._field_forward(cs, ray_emb)
+            feat, sigma, rgb, ray_bias = self._field_forward(cs, ray_emb, train=True)
             out_rgb, depth, acc, weights, alphas, trans = self._composite(cs, sigma, rgb, keep=True)
             # loss (CharbonnierLoss, nerfstudio/model_components/losses.py:73-84)
             g_rgb = self._buf("g_rgb", (R, 3), torch.float32)
@@ -399,8 +401,9 @@ class GFNeRFEngine:
             d_ray_bias = None if block else self._buf("d_ray_bias", (R, self.hidden), torch.float32, zero=True)
             with self._stage("mlp_bwd"):   # block stage: frozen MLP, only d_feat
                 _lib.check(L.gf_mlp_backward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
-                                             _lib.ptr(cs.ray_id), _lib.ptr(ray_bias), _lib.ptr(d_sigma),
-                                             _lib.ptr(d_rgb), _lib.ptr(d_feat),
+                                             _lib.ptr(cs.ray_id), _lib.ptr(ray_bias),
+                                             _lib.ptr(self._buf("relu_masks", (cap, 2, 4), torch.int32)),
+                                             _lib.ptr(d_sigma), _lib.ptr(d_rgb), _lib.ptr(d_feat),
                                              None if block else _lib.ptr(self.opt_mlp.grad),
                                              _lib.ptr(d_ray_bias), grad_scale, st), "gf_mlp_backward")
             if presample_late:

@@ -73,12 +73,16 @@ class _FusedFieldFn(torch.autograd.Function):
         ray_bias = torch.empty((R, hidden), dtype=torch.float32, device=dev)
         sigma = torch.empty(V, dtype=torch.float32, device=dev)
         rgb = torch.empty((V, 3), dtype=torch.float32, device=dev)
+        # the forward's ReLU masks, handed to the backward (include/gfnerf_b200.h gf_mlp_forward)
+        masks = torch.empty((V, 2, 4), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.gf_mlp_ray_bias(R, hidden, _lib.ptr(blob), _lib.ptr(dirs), _lib.ptr(emb), _lib.ptr(ray_bias),
                                          st), "gf_mlp_ray_bias")
             _lib.check(L.gf_mlp_forward(V, None, hidden, _lib.ptr(blob), _lib.ptr(feat), _lib.ptr(ray_id),
-                                        _lib.ptr(ray_bias), _lib.ptr(sigma), _lib.ptr(rgb), st), "gf_mlp_forward")
-        ctx.save_for_backward(pts01, anchors, ray_id, dirs, feat, blob, ray_bias, emb if emb is not None else dirs)
+                                        _lib.ptr(ray_bias), _lib.ptr(sigma), _lib.ptr(rgb), _lib.ptr(masks), st),
+                       "gf_mlp_forward")
+        ctx.save_for_backward(pts01, anchors, ray_id, dirs, feat, blob, ray_bias, emb if emb is not None else dirs,
+                              masks)
         ctx.meta = (enc, res_enc, hidden, bool(train_mlp), emb is not None, feat_pool.shape,
                     None if res_pool is None else res_pool.shape)
         return sigma, rgb
@@ -86,7 +90,7 @@ class _FusedFieldFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_sigma, d_rgb):
         L, st = _lib.lib(), _lib.cur_stream()
-        pts01, anchors, ray_id, dirs, feat, blob, ray_bias, emb = ctx.saved_tensors
+        pts01, anchors, ray_id, dirs, feat, blob, ray_bias, emb, masks = ctx.saved_tensors
         enc, res_enc, hidden, train_mlp, has_emb, pool_shape, res_shape = ctx.meta
         emb = emb if has_emb else None
         V, R, dev = pts01.shape[0], dirs.shape[0], pts01.device
@@ -98,7 +102,8 @@ class _FusedFieldFn(torch.autograd.Function):
         d_emb = torch.zeros((R, 32), dtype=torch.float32, device=dev) if (train_mlp and has_emb) else None
         with torch.cuda.device(dev):
             _lib.check(L.gf_mlp_backward(V, None, hidden, _lib.ptr(blob), _lib.ptr(feat), _lib.ptr(ray_id),
-                                         _lib.ptr(ray_bias), _lib.ptr(d_sigma), _lib.ptr(d_rgb), _lib.ptr(d_feat),
+                                         _lib.ptr(ray_bias), _lib.ptr(masks), _lib.ptr(d_sigma), _lib.ptr(d_rgb),
+                                         _lib.ptr(d_feat),
                                          _lib.ptr(d_blob), _lib.ptr(d_rb), _scale(R), st), "gf_mlp_backward")
             if train_mlp:
                 _lib.check(L.gf_mlp_ray_bias_backward(R, hidden, _lib.ptr(blob), _lib.ptr(dirs), _lib.ptr(emb),

@@ -294,20 +294,29 @@ int gf_mlp_ray_bias(int64_t n_rays, int hidden, const float* params, const float
                     const float* ray_emb, float* ray_bias, void* stream);
 
 /* feat_f16 __half [n,32] (the hash encoding), ray_id int32 [n] -> sigma [n] = exp(h0 + 1),
- * rgb [n,3] = sigmoid(head). */
+ * rgb [n,3] = sigmoid(head).
+ * relu_masks == NULL (inference): plain fp16 weights / activations, fp32 accumulate (outputs within ~1e-3 of the
+ * reference's fp32 nn.Linear stack, gfnerf/mlp.py:45-57).
+ * relu_masks != NULL (training): uint32 [n][2][4], 16-byte aligned.  Split precision: weights and hidden activations
+ * are carried as fp16 pairs hi + lo (three tensor-core products per layer), so pre-activations -- and with them the
+ * ReLU masks -- agree with the fp32 reference far inside fp16 rounding (outputs within ~1e-4).  Written per sample
+ * and per 32-column half of the 64-wide hidden layers: {mask of base.0's ReLU, of head.0's, of head.1's, 0}; bit
+ * layout private to the library (csrc/mlp_tc.cu mask_bits_of_pair).  gf_mlp_backward consumes it. */
 int gf_mlp_forward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params,
                    const void* feat_f16, const int32_t* ray_id, const float* ray_bias,
-                   float* sigma, float* rgb, void* stream);
+                   float* sigma, float* rgb, void* relu_masks, void* stream);
 
 /* d_sigma [n], d_rgb [n,3] -> d_feat_scaled_f16 __half [n,32] (= dL/dfeat * 128, the reference's
  * grad_in, Hash3DAnchored_cuda.cu:209), d_params fp32 [param_count] ACCUMULATED (all of it except
  * the SH / emb columns of W2 and b2), d_ray_bias fp32 [R,H] ACCUMULATED (caller zeroes).
  * d_params == d_ray_bias == NULL: frozen MLP (focal stage), only d_feat is produced.
- * Hidden activations are recomputed.  grad_scale: internal loss scale of the fp16 gradient
+ * Hidden activations are recomputed (plain fp16); the ReLU masks are the forward's (relu_masks, required): a
+ * recomputed fp16 mask flips ~1e-3 of the units near zero, which alone costs 1-2 % of every gradient in L2.
+ * grad_scale: internal loss scale of the fp16 gradient
  * fragments (a power of two near 1/|d_rgb|, e.g. the ray count); results are unscaled. */
 int gf_mlp_backward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params,
                     const void* feat_f16, const int32_t* ray_id, const float* ray_bias,
-                    const float* d_sigma, const float* d_rgb,
+                    const void* relu_masks, const float* d_sigma, const float* d_rgb,
                     void* d_feat_scaled_f16, float* d_params, float* d_ray_bias, float grad_scale,
                     void* stream);
 

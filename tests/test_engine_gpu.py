@@ -60,13 +60,17 @@ def test_one_step_matches_oracle_chain():
     sc = np.abs(g_table).max()
     err = np.abs(got_t - g_table).max() / sc
     print("table grad max err / max", err, "nonzero rows", (g_table != 0).any(-1).sum())
-    assert err < 2e-2
+    assert err < 5e-3                      # north star: 1e-2 (fp16 MLP)
     got_p = eng.opt_mlp.grad.double().cpu().numpy()
-    assert np.abs(got_p - d_params).max() / np.abs(d_params).max() < 2e-2
+    err_p = np.abs(got_p - d_params).max() / np.abs(d_params).max()
+    print("mlp grad max err / max", err_p)
+    assert err_p < 5e-3
     emb_ref = np.zeros_like(emb0, dtype=np.float64)
     np.add.at(emb_ref, cam, d_emb)
     got_e = eng.opt_emb.grad.view(-1, 32).double().cpu().numpy()
-    assert np.abs(got_e - emb_ref).max() / np.abs(emb_ref).max() < 2e-2
+    err_e = np.abs(got_e - emb_ref).max() / np.abs(emb_ref).max()
+    print("embedding grad max err / max", err_e)
+    assert err_e < 5e-3
     # ---- Adam step on exactly these gradients ----
     g_t32, g_p32 = eng.opt_table.unscaled_grad().cpu().numpy().copy(), eng.opt_mlp.grad.cpu().numpy().copy()
     eng._reduce_and_step(1.0)

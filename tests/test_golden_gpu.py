@@ -67,24 +67,26 @@ def test_mlp_matches_reference_mlpnetwork():
     rb = torch.empty((R, H), device="cuda")
     _lib.check(L.gf_mlp_ray_bias(R, H, _lib.ptr(p), _lib.ptr(dirs), _lib.ptr(emb), _lib.ptr(rb), st))
     sigma, rgb = torch.empty(n, device="cuda"), torch.empty((n, 3), device="cuda")
+    masks = torch.zeros((n, 2, 4), dtype=torch.int32, device="cuda")
     _lib.check(L.gf_mlp_forward(n, None, H, _lib.ptr(p), _lib.ptr(feat), _lib.ptr(ray_id), _lib.ptr(rb),
-                                _lib.ptr(sigma), _lib.ptr(rgb), st))
-    close(sigma, g["sigma"], 1e-2, "density")     # north star: 1e-2 for the fp16 MLP
-    close(rgb, g["rgb"], 1e-2, "rgb")
+                                _lib.ptr(sigma), _lib.ptr(rgb), _lib.ptr(masks), st))
+    close(sigma, g["sigma"], 2e-3, "density")     # north star: 1e-2 for the fp16 MLP; split precision does better
+    close(rgb, g["rgb"], 2e-3, "rgb")
     d_feat = torch.empty((n, 32), dtype=torch.float16, device="cuda")
     d_params = torch.zeros(g["params"].size, device="cuda")
     d_rb = torch.zeros((R, H), device="cuda")
     d_emb = torch.zeros((R, 32), device="cuda")
     g_sigma, g_rgb = T(g["g_sigma"]), T(g["g_rgb"])
     _lib.check(L.gf_mlp_backward(n, None, H, _lib.ptr(p), _lib.ptr(feat), _lib.ptr(ray_id), _lib.ptr(rb),
-                                 _lib.ptr(g_sigma), _lib.ptr(g_rgb), _lib.ptr(d_feat), _lib.ptr(d_params),
-                                 _lib.ptr(d_rb), 16.0, st))
+                                 _lib.ptr(masks), _lib.ptr(g_sigma), _lib.ptr(g_rgb), _lib.ptr(d_feat),
+                                 _lib.ptr(d_params), _lib.ptr(d_rb), 16.0, st))
     _lib.check(L.gf_mlp_ray_bias_backward(R, H, _lib.ptr(p), _lib.ptr(dirs), _lib.ptr(emb), _lib.ptr(d_rb),
                                           _lib.ptr(d_params), _lib.ptr(d_emb), st))
     rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
-    assert rel(d_feat.float().cpu().numpy() / 128.0, g["d_feat"]) < 1e-2
-    assert rel(d_params.cpu().numpy(), g["d_params"]) < 1e-2
-    assert rel(d_emb.cpu().numpy(), g["d_emb"]) < 1e-2
+    for name, got, want in (("d_feat", d_feat.float().cpu().numpy() / 128.0, g["d_feat"]),
+                            ("d_params", d_params.cpu().numpy(), g["d_params"]), ("d_emb", d_emb.cpu().numpy(), g["d_emb"])):
+        print(name, "rel L2 vs the reference MLPNetwork's autograd:", rel(got, want))
+        assert rel(got, want) < 3e-3, name        # north star: 1e-2
 
 
 def test_charbonnier_and_adam_match_reference():

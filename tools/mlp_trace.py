@@ -40,19 +40,20 @@ def main():
     d_params = torch.zeros(11603, device="cuda")
     d_rb = torch.zeros(R, 64, device="cuda")
     vp, i64, f32, cint = C.c_void_p, C.c_int64, C.c_float, C.c_int
-    L.gf_mlp_backward.argtypes = [i64, vp, cint, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp]
+    L.gf_mlp_backward.argtypes = [i64, vp, cint, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp]
+    masks = torch.full((n, 2, 4), -1, device="cuda", dtype=torch.int32)   # all units active
     st = torch.cuda.current_stream().cuda_stream
     for full in (1, 0):
         for _ in range(3):
             rc = L.gf_mlp_backward(n, None, 64, params.data_ptr(), feat.data_ptr(), ray_id.data_ptr(), ray_bias.data_ptr(),
-                                   d_sigma.data_ptr(), d_rgb.data_ptr(), d_feat.data_ptr(),
+                                   masks.data_ptr(), d_sigma.data_ptr(), d_rgb.data_ptr(), d_feat.data_ptr(),
                                    d_params.data_ptr() if full else None, d_rb.data_ptr() if full else None, 4096.0, st)
             assert rc == 0, L.gf_last_error()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         L.gf_mlp_backward(n, None, 64, params.data_ptr(), feat.data_ptr(), ray_id.data_ptr(), ray_bias.data_ptr(),
-                          d_sigma.data_ptr(), d_rgb.data_ptr(), d_feat.data_ptr(),
+                          masks.data_ptr(), d_sigma.data_ptr(), d_rgb.data_ptr(), d_feat.data_ptr(),
                           d_params.data_ptr() if full else None, d_rb.data_ptr() if full else None, 4096.0, st)
         e1.record()
         torch.cuda.synchronize()
