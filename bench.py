@@ -301,10 +301,8 @@ def main():
     sampler.ray_march_fineness_decay_end_iter_ = 0.0
     sampler.ray_march_fineness_ = 1.0
     log2t = 21 if args.workload == "focal" else LOG2T
+    # (the engine broadcasts rank 0's initial parameters when it is given a group)
     eng = GFNeRFEngine(sampler, log2_table_size=log2t, num_images=rig["c2w"].shape[0], seed=0, dist_group=group)
-    if world > 1:    # identical parameters on every rank
-        eng.sync.broadcast_([eng.enc.feat_pool_.data, eng.enc.prim_pool_, eng.mlp, eng.emb])
-        eng.enc.shadow(force=True)
     if args.workload == "focal":
         eng.start_block_stage(seed=100 + rank)
 
@@ -456,6 +454,13 @@ def main():
                        "level_addressing": "reference (level l = table rows [l*T/2, l*T/2 + T): windows overlap by half, "
                                            "8.5*T of the 16*T rows reachable; DESIGN.md section 5)",
                        "sample_ahead": bool(ahead),
+                       "march_fineness": "1.0 (the steady state of the schedule: PersSampler.cpp:958-967 decays 16 -> 1 "
+                                         "over the first 10 k of 130 k iterations; the bench pins the other 120 k)",
+                       "exchange": ("none (single GPU)" if world == 1 else
+                                    "peer memory over NVLink: one kernel per rank = reduce-scatter (fp32 gradient rows, "
+                                    "P2P loads) + Adam on the owned 1/N of the rows + all-gather (fp16 gather table, P2P "
+                                    "stores), between two one-CTA cross-GPU barriers; octree votes: NCCL MAX all-reduce"
+                                    if eng.peer is not None else "NCCL all-reduce of the fp32 table gradient + replicated Adam"),
                        "parallelism": f"dp{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "rays/s",
                     "h2d_bytes_per_step": int(sum(a.numel() * a.element_size() for a in pinned[0])) * world,

@@ -63,14 +63,20 @@ class FlatBucket:
     ALIGN = 64   # elements; every view starts 256-byte aligned (the kernels use 16-byte vector accesses)
 
     def __init__(self, shapes: Sequence[Sequence[int]], dtype=torch.float32, device="cpu"):
+        self.shapes = [tuple(int(x) for x in s) for s in shapes]
         sizes = [int(torch.Size(s).numel()) for s in shapes]
-        padded = [(n + self.ALIGN - 1) // self.ALIGN * self.ALIGN for n in sizes]
-        self.flat = torch.zeros(sum(padded), dtype=dtype, device=device)
+        self.padded = [(n + self.ALIGN - 1) // self.ALIGN * self.ALIGN for n in sizes]
+        self.offsets = [sum(self.padded[:i]) for i in range(len(sizes))]     # element offset of each view
+        self.rebind(torch.zeros(sum(self.padded), dtype=dtype, device=device))
+
+    def rebind(self, flat: torch.Tensor) -> None:
+        """Carve the views out of another flat buffer of the same size (peer-mapped memory, peer.PeerExchange)."""
+        assert flat.numel() == sum(self.padded)
+        self.flat = flat
         self.views: List[torch.Tensor] = []
-        o = 0
-        for s, n, p in zip(shapes, sizes, padded):
+        for s, o in zip(self.shapes, self.offsets):
+            n = int(torch.Size(s).numel())
             self.views.append(self.flat[o:o + n].view(*s))
-            o += p
 
 
 class GradSync:
@@ -80,6 +86,7 @@ class GradSync:
     def __init__(self, group=None, device: Optional[torch.device] = None):
         self.group = group
         self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.cuda = self.device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=self.device) if (self.cuda and self.world > 1) else None

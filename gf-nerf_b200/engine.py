@@ -60,8 +60,10 @@ class _Adam:
         # Hash3DAnchored_cuda.cu:209, and the division rides along with the optimizer's 1 / world)
         self.grad_scale = float(grad_scale)
         self.grad = torch.zeros_like(param) if grad is None else grad
-        self.m = torch.zeros_like(param)
-        self.v = torch.zeros_like(param)
+        # (moments with room for a vector tail: the peer exchange kernel works in 16-byte units)
+        n4 = (param.numel() + 3) // 4 * 4
+        self.m = torch.zeros(n4, dtype=param.dtype, device=param.device)[:param.numel()].view_as(param)
+        self.v = torch.zeros(n4, dtype=param.dtype, device=param.device)[:param.numel()].view_as(param)
         # the step count lives on the device: a step skipped by the NaN guard must not advance the bias correction
         # (the reference skips optimizer.step() altogether, trainer.py:416-426)
         self.d_step = torch.zeros(1, dtype=torch.int64, device=param.device)
@@ -124,7 +126,9 @@ class GFNeRFEngine:
         self.enc = Hash3DAnchoredCore(log2_table_size, self.n_volumes, device=self.device, generator=gen)
         self.enc.feat_pool_.requires_grad_(False)
         self.enc.Reset(generator=gen)   # U(-0.01, 0.01), gfnerf/nerfacto_field.py:200; reproducible from `seed`
-        self.mlp = init_mlp_params(hidden, gen, self.device)
+        mlp0 = init_mlp_params(hidden, gen, self.device)
+        self.mlp = torch.zeros((mlp0.numel() + 3) // 4 * 4, device=self.device)[:mlp0.numel()]   # room for a vector tail
+        self.mlp.copy_(mlp0)
         self.emb = (torch.randn(num_images, APPEARANCE_DIM, generator=gen).to(self.device)
                     if use_appearance_embedding else None)
         self.opt_table = _Adam(self.enc.feat_pool_.detach().view(-1), lr_table, grad_scale=GRAD_SCALE,
@@ -133,9 +137,13 @@ class GFNeRFEngine:
         small = FlatBucket([self.mlp.shape] + ([self.emb.shape] if self.emb is not None else []), device=self.device)
         self.opt_mlp = _Adam(self.mlp, lr_mlp, grad=small.views[0])
         self.opt_emb = _Adam(self.emb.view(-1), lr_mlp, grad=small.views[1].view(-1)) if self.emb is not None else None
+        self._small = small
         self._small_grads = small.flat
         self.sync = GradSync(dist_group, self.device)
         self.world = self.sync.world
+        self.peer = None
+        if self.world > 1 and self.device.type == "cuda" and os.environ.get("GF_PEER_EXCHANGE", "1") != "0":
+            self._setup_peer_exchange(dist_group)
         if self.world > 1:
             # identical initial parameters on every replica, whatever seed each rank was built with (what DDP's
             # constructor does; ranks seeded seed + rank -- ddp.rank_seed -- would otherwise average gradients of
@@ -203,6 +211,86 @@ class GFNeRFEngine:
         return out
 
     # ---- workspace -----------------------------------------------------------------------
+    # ---- data-parallel exchange over NVLink peer memory (csrc/peer.cu) ------------------------------------------
+    def _setup_peer_exchange(self, group):
+        """Move the buffers the ranks exchange -- table gradient, fp16 gather table, small-gradient bucket -- into
+        peer-mapped memory.  Falls back to the NCCL all-reduce path (saying so) if the node cannot map peers."""
+        from .peer import PeerExchange
+        import torch.distributed as dist
+        ok = torch.ones(1, dtype=torch.int32, device=self.device)
+        try:
+            peer = PeerExchange(group, self.device, {
+                "table_grad": 4 * self.opt_table.param.numel(), "shadow": 2 * self.enc.feat_pool_.numel(),
+                "small": 4 * self._small.flat.numel()})
+        except RuntimeError as e:
+            peer, ok[0] = None, 0
+            import sys
+            sys.stderr.write(f"gfnerf_b200: peer-memory exchange unavailable ({e}); using NCCL all-reduce\n")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)     # all ranks or none
+        if int(ok.item()) == 0:
+            return
+        self.peer = peer
+        self.opt_table.grad = peer.tensor("table_grad", torch.float32, tuple(self.opt_table.param.shape))
+        self.enc._shadow = peer.tensor("shadow", torch.float16, tuple(self.enc.feat_pool_.shape))
+        self.enc._shadow_key = None
+        self._small.rebind(peer.tensor("small", torch.float32, (self._small.flat.numel(),)))
+        self._small_grads = self._small.flat
+        self.opt_mlp.grad = self._small.views[0]
+        if self.opt_emb is not None:
+            self.opt_emb.grad = self._small.views[1].view(-1)
+        n4 = (self.opt_table.n_active + 3) // 4
+        chunk4 = (n4 + self.world - 1) // self.world
+        r = self.sync.rank
+        self._peer_own = (min(r * chunk4 * 4, self.opt_table.n_active), min((r + 1) * chunk4 * 4, self.opt_table.n_active))
+        self._peer_chunk = chunk4 * 4
+
+    def _peer_exchange(self, lr_scale: float):
+        """reduce-scatter + Adam + all-gather of the table, all-reduce + Adam of the small parameters, between two
+        cross-GPU barriers, all on the current stream (see csrc/peer.cu)."""
+        L, st, peer, W = _lib.lib(), _lib.cur_stream(), self.peer, self.world
+        with self._stage("exchange"):
+            flag = self._nan_flag([self._small_grads, self.opt_table.grad[:self.opt_table.n_active]])   # this rank's
+            ep = peer.next_epoch()
+            peer.barrier("in", ep, local_flag=flag, want_any=flag is not None)
+            skip = peer.any_flag if flag is not None else None
+            self.last_nan_flag = skip
+
+            def run(opt, lo, hi, grad_ptrs, shadow_ptrs, lr):
+                n = (opt.param.numel() + 3) // 4 * 4 if shadow_ptrs is None else opt.n_active
+                _lib.check(L.gf_peer_reduce_adam(
+                    W, n, lo, hi if hi is not None else n, grad_ptrs, _lib.ptr(opt.param), _lib.ptr(opt.m),
+                    _lib.ptr(opt.v), shadow_ptrs, float(lr), opt.betas[0], opt.betas[1], opt.eps, _lib.ptr(opt.d_step),
+                    float(W) * opt.grad_scale, _lib.ptr(skip), st), "gf_peer_reduce_adam")
+
+            run(self.opt_table, self._peer_own[0], self._peer_own[1], peer.ptrs("table_grad"), peer.ptrs("shadow"),
+                self.opt_table.lr * lr_scale)
+            run(self.opt_mlp, 0, None, peer.ptrs("small", 4 * self._small.offsets[0]), None, self.opt_mlp.lr * lr_scale)
+            if self.opt_emb is not None:
+                run(self.opt_emb, 0, None, peer.ptrs("small", 4 * self._small.offsets[1]), None,
+                    self.opt_emb.lr * lr_scale)
+            peer.barrier("out", ep)
+            # every rank has read my gradients: zero them for the next step
+            self.opt_table.grad[:self.opt_table.n_active].zero_()
+            self._small_grads.zero_()
+        self.enc.mark_shadow_fresh()
+
+    def sync_master_params(self):
+        """Peer exchange only: every rank keeps the fp32 master copy (and Adam moments) of ITS rows of the table up to
+        date -- the forward reads the fp16 gather table, which is complete everywhere.  Before reading `feat_pool_`
+        (checkpoint, inspection) collect the owners' rows; not on the step path."""
+        if self.peer is None:
+            return
+        import torch.distributed as dist
+        self.flush()
+        n, chunk = self.opt_table.n_active, self._peer_chunk
+        for t in (self.opt_table.param, self.opt_table.m, self.opt_table.v):
+            mine = torch.zeros(chunk, dtype=t.dtype, device=t.device)
+            lo, hi = self._peer_own
+            mine[:hi - lo] = t[lo:hi]
+            allr = torch.empty(chunk * self.world, dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(allr, mine, group=self.sync.group)
+            t[:n] = allr[:n]
+
     def _buf(self, name, shape, dtype, zero=False):
         n = int(np.prod(shape))
         t = self._ws.get(name)
@@ -431,7 +519,12 @@ class GFNeRFEngine:
                         self.opt_emb.grad.view(-1, APPEARANCE_DIM).index_add_(0, rel_camera_indices.to(torch.int64),
                                                                               d_ray_emb)
                 g_table = self.opt_table.grad.view(-1, 2)
-                if self.world > 1 and optimizer_step:
+                if self.peer is not None and optimizer_step:
+                    with self._stage("hash_bwd"):
+                        self.enc.launch_backward(cs.pts01, cs.anchor, d_feat, True, g_table, d_n_ptr=cs.total,
+                                                 keep_x128=True)
+                    self._peer_exchange(lr_scale)
+                elif self.world > 1 and optimizer_step:
                     # data parallel: the small bucket's all-reduce starts now and runs under the scatter; the table is
                     # scattered and all-reduced in LEVEL_GROUP-level groups.  Level l owns rows [l*T/2, l*T/2 + T)
                     # (level_base_row: windows overlap by half), so once levels < l1 are scattered the rows below

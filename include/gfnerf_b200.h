@@ -366,6 +366,37 @@ int gf_adam_step_counted(int64_t n, float* param, float* grad, float* exp_avg, f
                          void* shadow_f16, float lr, float beta1, float beta2, float eps,
                          int64_t* d_step, float grad_div, int zero_grad, const int32_t* skip_flag, void* stream);
 
+/* ---- data-parallel exchange over NVLink peer memory (csrc/peer.cu) ----------------------------------
+ * Replaces the DDP gradient all-reduce + replicated optimizer step of the reference's multi-GPU setup
+ * (gfnerf/gf_pipeline.py:136-138, nerfstudio/engine/optimizers.py:125-137) for one node: one process per GPU, every
+ * rank's exchange buffers mapped into every other rank (CUDA IPC).
+ *
+ * gf_peer_alloc / free: a zero-filled device allocation that can be exported (cudaMalloc; sub-blocks of a caching
+ * allocator cannot).  gf_peer_export: its 64-byte IPC handle.  gf_peer_import / close: map / unmap a peer's handle
+ * (peer access is enabled lazily). */
+int gf_peer_alloc(int64_t bytes, void** dptr);
+int gf_peer_free(void* dptr);
+int gf_peer_export(const void* dptr, void* handle64);
+int gf_peer_import(const void* handle64, void** dptr);
+int gf_peer_close(void* dptr);
+/* Cross-GPU barrier as one single-CTA kernel on `stream`.  flag_ptrs: host array [world] of device pointers, entry r =
+ * rank r's uint32[world] flag array (peer-mapped, zero at start).  epoch: 1, 2, 3, ... -- the same on every rank, one
+ * flag array per barrier site.  d_local_flag (may be NULL): this rank's int32 flag; d_any_flag (may be NULL) receives
+ * the OR over all ranks.  A wait longer than ~2 s sets *d_error (int32, may be NULL) instead of hanging. */
+int gf_peer_barrier(int world, int rank, uint32_t epoch, void* const* flag_ptrs, const int32_t* d_local_flag,
+                    int32_t* d_any_flag, int32_t* d_error, void* stream);
+/* Reduce-scatter + Adam + all-gather of one flat fp32 parameter array of n elements in ONE kernel: for the elements
+ * [lo, hi) this rank owns (multiples of 4), sum grad_ptrs[0..world) (host array of device pointers to every rank's
+ * gradient array, summed in rank order -- bit-identical whoever computes it), divide by grad_div, apply torch.optim.Adam
+ * (as gf_adam_step_counted: bias corrections from *d_step + 1, *d_step advanced unless skipped) to param / exp_avg /
+ * exp_avg_sq, and -- if shadow_ptrs != NULL -- store the updated elements as fp16 into EVERY rank's shadow array.
+ * Gradients are left untouched (peers may still be reading them): the caller zeroes them after the closing barrier.
+ * *skip_flag != 0: nothing is updated. */
+int gf_peer_reduce_adam(int world, int64_t n, int64_t lo, int64_t hi, void* const* grad_ptrs, float* param,
+                        float* exp_avg, float* exp_avg_sq, void* const* shadow_ptrs, float lr, float beta1,
+                        float beta2, float eps, int64_t* d_step, float grad_div, const int32_t* skip_flag,
+                        void* stream);
+
 /* ---- ray generation (the step before the path) --------
  * Cameras.generate_rays for PERSPECTIVE cameras without distortion (nerfstudio/cameras/cameras.py:583-727, with
  * GF-NeRF's lookat_directions :704,723): cam_idx int64 [n], coords_yx f32 [n,2] = pixel (y, x) as the pixel samplers
