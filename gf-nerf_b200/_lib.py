@@ -68,7 +68,7 @@ _SIGS = {
     "gf_adam_step": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _int, _vp],
 }
 
-EXPORTS = ["gf_last_error", "gf_version", "gf_launch_count", "gf_mlp_param_count"] + sorted(_SIGS)
+EXPORTS = ["gf_last_error", "gf_version", "gf_launch_count", "gf_mlp_param_count", "gf_mlp_mask_words"] + sorted(_SIGS)
 
 
 def lib():
@@ -84,7 +84,7 @@ def lib():
         L.gf_last_error.restype = C.c_char_p
         L.gf_version.restype = C.c_char_p
         L.gf_launch_count.restype = C.c_int64
-        for name, sig in list(_SIGS.items()) + [("gf_mlp_param_count", [_int])]:
+        for name, sig in list(_SIGS.items()) + [("gf_mlp_param_count", [_int]), ("gf_mlp_mask_words", [_int])]:
             try:
                 fn = getattr(L, name)
             except AttributeError as e:  # a stale build: fail loudly, never fall back

@@ -19,11 +19,13 @@
 
 namespace gf {
 
-constexpr int kH = 64;
 // parameter blob offsets (torch nn.Linear layout), see include/gfnerf_b200.h
-constexpr int kW0 = 0, kB0 = kW0 + kH * 32, kW1 = kB0 + kH, kB1 = kW1 + 16 * kH, kW2 = kB1 + 16,
-              kB2 = kW2 + kH * 63, kW3 = kB2 + kH, kB3 = kW3 + kH * kH, kW4 = kB3 + kH, kB4 = kW4 + 3 * kH,
-              kParamCount = kB4 + 3;
+template <int H>
+struct Blob {
+  static constexpr int kW0 = 0, kB0 = kW0 + H * 32, kW1 = kB0 + H, kB1 = kW1 + 16 * H, kW2 = kB1 + 16,
+                       kB2 = kW2 + H * 63, kW3 = kB2 + H, kB3 = kW3 + H * H, kW4 = kB3 + H, kB4 = kW4 + 3 * H,
+                       kParamCount = kB4 + 3;
+};
 
 // ---------------------------------------------------------------------------------------------
 // per-ray part of the head's first layer
@@ -56,9 +58,11 @@ constexpr int kRbRays = 32;  // rays per CTA of the ray-bias kernels
 constexpr int kRbIn = 48;    // SH(16) | emb(32)
 
 // ray_bias[r][j] = b2[j] + W2[j][0:16] . SH(dir_r) + W2[j][31:63] . emb_r      (fp32)
+template <int kH>
 __global__ void __launch_bounds__(256)
 ray_bias_kernel(int64_t n_rays, const float* __restrict__ params, const float* __restrict__ dirs,
                 const float* __restrict__ emb, float* __restrict__ ray_bias) {
+  constexpr int kW2 = Blob<kH>::kW2, kB2 = Blob<kH>::kB2;
   __shared__ float s_w[kH][kRbIn + 1];
   __shared__ float s_in[kRbRays][kRbIn + 1];
   for (int i = threadIdx.x; i < kH * kRbIn; i += blockDim.x) {
@@ -81,7 +85,7 @@ ray_bias_kernel(int64_t n_rays, const float* __restrict__ params, const float* _
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kRbRays * kH; i += blockDim.x) {
-    const int rr = i >> 6, j = i & 63;
+    const int rr = i / kH, j = i % kH;
     const int64_t r = r0 + rr;
     if (r >= n_rays) continue;
     float acc = __ldg(params + kB2 + j);
@@ -92,10 +96,12 @@ ray_bias_kernel(int64_t n_rays, const float* __restrict__ params, const float* _
 }
 
 // G = d_ray_bias [R,64]:  d_b2 += sum_r G ; d_W2[:, SH|emb] += G^T [SH|emb] ; d_emb = G W2[:, emb]
+template <int kH>
 __global__ void __launch_bounds__(256)
 ray_bias_bwd_kernel(int64_t n_rays, const float* __restrict__ params, const float* __restrict__ dirs,
                     const float* __restrict__ emb, const float* __restrict__ g_rb, float* __restrict__ d_params,
                     float* __restrict__ d_emb) {
+  constexpr int kW2 = Blob<kH>::kW2, kB2 = Blob<kH>::kB2;
   __shared__ float s_g[kRbRays][kH + 1];
   __shared__ float s_in[kRbRays][kRbIn + 1];
   const int64_t r0 = (int64_t)blockIdx.x * kRbRays;
@@ -113,7 +119,7 @@ ray_bias_bwd_kernel(int64_t n_rays, const float* __restrict__ params, const floa
     s_in[rr][16 + k] = (emb && r < n_rays) ? __ldg(emb + r * 32 + k) : 0.f;
   }
   for (int i = threadIdx.x; i < kRbRays * kH; i += blockDim.x) {
-    const int rr = i >> 6, j = i & 63;
+    const int rr = i / kH, j = i % kH;
     const int64_t r = r0 + rr;
     s_g[rr][j] = r < n_rays ? __ldg(g_rb + r * kH + j) : 0.f;
   }
@@ -155,57 +161,80 @@ using namespace gf;
 int gf_launch_mlp_fwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
                          const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, void* relu_masks,
                          cudaStream_t st);
-
 int gf_launch_mlp_bwd_tc(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
                          const int32_t* ray_id, const float* ray_bias, const void* relu_masks, const float* d_sigma,
                          const float* d_rgb, void* d_feat, float* d_params, float* d_ray_bias, float gscale,
                          cudaStream_t st);
+// hidden width 128 (mlp_tc128.cu)
+int gf_launch_mlp_fwd_tc128(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
+                            const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, void* relu_masks,
+                            cudaStream_t st);
+int gf_launch_mlp_bwd_tc128(int64_t n, const int32_t* d_n_ptr, const float* params, const void* feat_f16,
+                            const int32_t* ray_id, const float* ray_bias, const void* relu_masks, const float* d_sigma,
+                            const float* d_rgb, void* d_feat, float* d_params, float* d_ray_bias, float gscale,
+                            cudaStream_t st);
+
+static inline bool width_built(int hidden) { return hidden == 64 || hidden == 128; }
 
 extern "C" {
 
-int64_t gf_mlp_param_count(int hidden) { return hidden == kH ? (int64_t)kParamCount : -1; }
+int64_t gf_mlp_param_count(int hidden) {
+  return hidden == 64 ? (int64_t)Blob<64>::kParamCount : hidden == 128 ? (int64_t)Blob<128>::kParamCount : -1;
+}
+
+int gf_mlp_mask_words(int hidden) { return hidden == 64 ? 8 : hidden == 128 ? 16 : -1; }
 
 int gf_mlp_ray_bias(int64_t n_rays, int hidden, const float* params, const float* ray_dirs, const float* ray_emb,
                     float* ray_bias, void* stream) {
-  GF_REQUIRE(hidden == kH, "gf_mlp_ray_bias: hidden width %d is not built (64 only)", hidden);
+  GF_REQUIRE(width_built(hidden), "gf_mlp_ray_bias: hidden width %d is not built (64 and 128 are)", hidden);
   GF_REQUIRE(n_rays >= 0, "gf_mlp_ray_bias: bad sizes");
   if (n_rays == 0) return GF_OK;
   GF_REQUIRE(params && ray_dirs && ray_bias, "gf_mlp_ray_bias: null pointer");
-  ray_bias_kernel<<<(int)div_up(n_rays, kRbRays), 256, 0, (cudaStream_t)stream>>>(n_rays, params, ray_dirs, ray_emb,
-                                                                                 ray_bias);
+  const int grid = (int)div_up(n_rays, kRbRays);
+  if (hidden == 64)
+    ray_bias_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(n_rays, params, ray_dirs, ray_emb, ray_bias);
+  else
+    ray_bias_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(n_rays, params, ray_dirs, ray_emb, ray_bias);
   return check_launch("ray_bias_kernel");
 }
 
 int gf_mlp_ray_bias_backward(int64_t n_rays, int hidden, const float* params, const float* ray_dirs,
                              const float* ray_emb, const float* d_ray_bias, float* d_params, float* d_ray_emb,
                              void* stream) {
-  GF_REQUIRE(hidden == kH, "gf_mlp_ray_bias_backward: hidden width %d is not built (64 only)", hidden);
+  GF_REQUIRE(width_built(hidden), "gf_mlp_ray_bias_backward: hidden width %d is not built (64 and 128 are)", hidden);
   GF_REQUIRE(n_rays >= 0, "gf_mlp_ray_bias_backward: bad sizes");
   if (n_rays == 0) return GF_OK;
   GF_REQUIRE(params && ray_dirs && d_ray_bias, "gf_mlp_ray_bias_backward: null pointer");
   GF_REQUIRE(!d_ray_emb || ray_emb, "gf_mlp_ray_bias_backward: d_ray_emb without ray_emb");
-  ray_bias_bwd_kernel<<<(int)div_up(n_rays, kRbRays), 256, 0, (cudaStream_t)stream>>>(
-      n_rays, params, ray_dirs, ray_emb, d_ray_bias, d_params, d_ray_emb);
+  const int grid = (int)div_up(n_rays, kRbRays);
+  if (hidden == 64)
+    ray_bias_bwd_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(n_rays, params, ray_dirs, ray_emb, d_ray_bias,
+                                                                    d_params, d_ray_emb);
+  else
+    ray_bias_bwd_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(n_rays, params, ray_dirs, ray_emb, d_ray_bias,
+                                                                     d_params, d_ray_emb);
   return check_launch("ray_bias_bwd_kernel");
 }
 
 int gf_mlp_forward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params, const void* feat_f16,
                    const int32_t* ray_id, const float* ray_bias, float* sigma, float* rgb, void* relu_masks,
                    void* stream) {
-  GF_REQUIRE(hidden == kH, "gf_mlp_forward: hidden width %d is not built (64 only)", hidden);
+  GF_REQUIRE(width_built(hidden), "gf_mlp_forward: hidden width %d is not built (64 and 128 are)", hidden);
   GF_REQUIRE(n >= 0, "gf_mlp_forward: bad sizes");
   if (n == 0) return GF_OK;
   GF_REQUIRE(params && feat_f16 && ray_id && ray_bias && sigma && rgb, "gf_mlp_forward: null pointer");
   GF_REQUIRE((reinterpret_cast<uintptr_t>(relu_masks) & 15) == 0, "gf_mlp_forward: relu_masks must be 16-byte aligned");
-  return gf_launch_mlp_fwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, sigma, rgb, relu_masks,
-                              (cudaStream_t)stream);
+  GF_REQUIRE((reinterpret_cast<uintptr_t>(ray_bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat_f16) & 15) == 0,
+             "gf_mlp_forward: ray_bias and feat must be 16-byte aligned");
+  return (hidden == 64 ? gf_launch_mlp_fwd_tc : gf_launch_mlp_fwd_tc128)(n, d_n_ptr, params, feat_f16, ray_id, ray_bias,
+                                                                         sigma, rgb, relu_masks, (cudaStream_t)stream);
 }
 
 int gf_mlp_backward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params, const void* feat_f16,
                     const int32_t* ray_id, const float* ray_bias, const void* relu_masks, const float* d_sigma,
                     const float* d_rgb,
                     void* d_feat_scaled_f16, float* d_params, float* d_ray_bias, float grad_scale, void* stream) {
-  GF_REQUIRE(hidden == kH, "gf_mlp_backward: hidden width %d is not built (64 only)", hidden);
+  GF_REQUIRE(width_built(hidden), "gf_mlp_backward: hidden width %d is not built (64 and 128 are)", hidden);
   GF_REQUIRE(n >= 0 && grad_scale > 0.f, "gf_mlp_backward: bad sizes");
   if (n == 0) return GF_OK;
   GF_REQUIRE(params && feat_f16 && ray_id && ray_bias && relu_masks && d_sigma && d_rgb && d_feat_scaled_f16,
@@ -213,8 +242,9 @@ int gf_mlp_backward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* 
   GF_REQUIRE((reinterpret_cast<uintptr_t>(relu_masks) & 15) == 0, "gf_mlp_backward: relu_masks must be 16-byte aligned");
   GF_REQUIRE((d_params == nullptr) == (d_ray_bias == nullptr),
              "gf_mlp_backward: d_params and d_ray_bias go together (both NULL = frozen MLP)");
-  return gf_launch_mlp_bwd_tc(n, d_n_ptr, params, feat_f16, ray_id, ray_bias, relu_masks, d_sigma, d_rgb, d_feat_scaled_f16,
-                              d_params, d_ray_bias, grad_scale, (cudaStream_t)stream);
+  return (hidden == 64 ? gf_launch_mlp_bwd_tc : gf_launch_mlp_bwd_tc128)(
+      n, d_n_ptr, params, feat_f16, ray_id, ray_bias, relu_masks, d_sigma, d_rgb, d_feat_scaled_f16, d_params, d_ray_bias,
+      grad_scale, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -114,6 +114,9 @@ class GFNeRFEngine:
         self.sampler = sampler
         self.device = sampler.device
         self.hidden = hidden
+        self.mask_words = int(_lib.lib().gf_mlp_mask_words(hidden))
+        if self.mask_words < 0:
+            raise ValueError(f"gfnerf_b200: hidden width {hidden} is not built (64 and 128 are)")
         self.nan_guard = bool(nan_guard)    # skip the optimizer step on a NaN gradient (trainer.py:416-426)
         # S3IM on top of the Charbonnier loss (gfnerf/nerfacto.py:186-197, 686-688); 0 = off
         self.s3im = (float(s3im_loss_mult), int(s3im_kernel_size), int(s3im_stride), int(s3im_repeat_time),
@@ -311,7 +314,7 @@ class GFNeRFEngine:
         sigma = self._buf("sigma", (cap,), torch.float32)
         rgb = self._buf("rgb", (cap, 3), torch.float32)
         ray_bias = self._buf("ray_bias", (R, self.hidden), torch.float32)
-        masks = self._buf("relu_masks", (cap, 2, 4), torch.int32) if train else None
+        masks = self._buf("relu_masks", (cap, self.mask_words), torch.int32) if train else None
         with self._stage("hash_fwd"):
             self.enc.launch_forward(cs.pts01, cs.anchor, out_f16=feat, d_n_ptr=cs.total, recast=False)
             if self.res is not None:
@@ -490,7 +493,7 @@ class GFNeRFEngine:
             with self._stage("mlp_bwd"):   # block stage: frozen MLP, only d_feat
                 _lib.check(L.gf_mlp_backward(cap, _lib.ptr(cs.total), self.hidden, _lib.ptr(self.mlp), _lib.ptr(feat),
                                              _lib.ptr(cs.ray_id), _lib.ptr(ray_bias),
-                                             _lib.ptr(self._buf("relu_masks", (cap, 2, 4), torch.int32)),
+                                             _lib.ptr(self._buf("relu_masks", (cap, self.mask_words), torch.int32)),
                                              _lib.ptr(d_sigma), _lib.ptr(d_rgb), _lib.ptr(d_feat),
                                              None if block else _lib.ptr(self.opt_mlp.grad),
                                              _lib.ptr(d_ray_bias), grad_scale, st), "gf_mlp_backward")

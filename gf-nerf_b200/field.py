@@ -74,7 +74,7 @@ class _FusedFieldFn(torch.autograd.Function):
         sigma = torch.empty(V, dtype=torch.float32, device=dev)
         rgb = torch.empty((V, 3), dtype=torch.float32, device=dev)
         # the forward's ReLU masks, handed to the backward (include/gfnerf_b200.h gf_mlp_forward)
-        masks = torch.empty((V, 2, 4), dtype=torch.int32, device=dev)
+        masks = torch.empty((V, int(L.gf_mlp_mask_words(hidden))), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.gf_mlp_ray_bias(R, hidden, _lib.ptr(blob), _lib.ptr(dirs), _lib.ptr(emb), _lib.ptr(ray_bias),
                                          st), "gf_mlp_ray_bias")

@@ -276,7 +276,8 @@ int gf_composite_backward(int64_t n_rays, const int32_t* offsets,
  * gfnerf/nerfacto_field.py:174-179,217-227), trunc_exp(x+1) (:499),
  * the tcnn SH degree-4 direction encoding (:152-158,521), the appearance
  * embedding lookup (:530-537) and the concat (:540-547).
- * fp16 tensor-core math, fp32 accumulate.  Hidden width H = 64.
+ * fp16 tensor-core math, fp32 accumulate.  Hidden width H = 64 (nerfstudio's default, csrc/mlp_tc.cu) or H = 128 (the
+ * reference's shipped gf-nerf config, gfnerf/config.py:124-125; csrc/mlp_tc128.cu); both stacks have the same width.
  *
  * params: one fp32 blob, torch nn.Linear layout (weight [out,in] row-major, then bias):
  *   base.0: W[H,32] b[H] ; base.1: W[16,H] b[16]
@@ -284,6 +285,9 @@ int gf_composite_backward(int64_t n_rays, const int32_t* offsets,
  * (gf_mlp_param_count(H) floats).  Head input order: SH(16) | geo(15) | emb(32).
  */
 int64_t gf_mlp_param_count(int hidden);   /* -1 if the width is not built */
+/* 32-bit words of ReLU masks per sample that gf_mlp_forward writes and gf_mlp_backward reads: 8 (H = 64), 16 (H = 128);
+ * -1 if the width is not built */
+int gf_mlp_mask_words(int hidden);
 
 /* Per-RAY part of the head's first layer (fp32):
  *   ray_bias[r][j] = b2[j] + W2[j][0:16] . SH4(dir_r) + W2[j][31:63] . emb_r
@@ -297,11 +301,12 @@ int gf_mlp_ray_bias(int64_t n_rays, int hidden, const float* params, const float
  * rgb [n,3] = sigmoid(head).
  * relu_masks == NULL (inference): plain fp16 weights / activations, fp32 accumulate (outputs within ~1e-3 of the
  * reference's fp32 nn.Linear stack, gfnerf/mlp.py:45-57).
- * relu_masks != NULL (training): uint32 [n][2][4], 16-byte aligned.  Split precision: weights and hidden activations
+ * relu_masks != NULL (training): uint32 [n][gf_mlp_mask_words(H)] = [n][2][H / 16], 16-byte aligned.  Split precision: weights and hidden activations
  * are carried as fp16 pairs hi + lo (three tensor-core products per layer), so pre-activations -- and with them the
  * ReLU masks -- agree with the fp32 reference far inside fp16 rounding (outputs within ~1e-4).  Written per sample
- * and per 32-column half of the 64-wide hidden layers: {mask of base.0's ReLU, of head.0's, of head.1's, 0}; bit
- * layout private to the library (csrc/mlp_tc.cu mask_bits_of_pair).  gf_mlp_backward consumes it. */
+ * and per column half of the hidden layers, one word per 32 columns: H = 64 {mask of base.0's ReLU, of head.0's, of
+ * head.1's, 0}, H = 128 {base.0 x2, head.0 x2, head.1 x2, 0, 0}; bit layout private to the library
+ * (csrc/mlp_tc_common.cuh mask_bits_of_pair).  gf_mlp_backward consumes it. */
 int gf_mlp_forward(int64_t n, const int32_t* d_n_ptr, int hidden, const float* params,
                    const void* feat_f16, const int32_t* ray_id, const float* ray_bias,
                    float* sigma, float* rgb, void* relu_masks, void* stream);

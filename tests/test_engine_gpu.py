@@ -10,16 +10,18 @@ from tests.helpers import load_rig, make_sampler
 pytestmark = pytest.mark.gpu
 
 
-def make_engine(rig, log2T=14, mode=1, seed=0):
+def make_engine(rig, log2T=14, mode=1, seed=0, hidden=64):
     from gfnerf_b200.engine import GFNeRFEngine
     s = make_sampler(rig, mode=mode)
-    return GFNeRFEngine(s, log2_table_size=log2T, num_images=rig["c2w"].shape[0], seed=seed)
+    return GFNeRFEngine(s, log2_table_size=log2T, num_images=rig["c2w"].shape[0], seed=seed, hidden=hidden)
 
 
-def test_one_step_matches_oracle_chain():
+# hidden 64: nerfstudio's default field; hidden 128: the reference's shipped gf-nerf config (gfnerf/config.py:124-125)
+@pytest.mark.parametrize("hidden", [64, 128])
+def test_one_step_matches_oracle_chain(hidden):
     from gfnerf_b200.persoctree import rig_rays
     rig = load_rig("rig8")
-    eng = make_engine(rig)
+    eng = make_engine(rig, hidden=hidden)
     # post-training-like feature scale so that densities are not all ~e
     eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
     eng.enc.shadow(force=True)
@@ -47,14 +49,14 @@ def test_one_step_matches_oracle_chain():
     prim, bias = eng.enc.prim_pool_.cpu().numpy(), eng.enc.bias_pool_.cpu().numpy()
     feat = orc.hash_forward(table0, prim, bias, pts01, anchors, eng.enc.level_scales_host)
     ray_emb = emb0[cam]
-    sigma, rgb = orc.mlp_forward(mlp0, feat, ray_id, d, ray_emb, 64)
+    sigma, rgb = orc.mlp_forward(mlp0, feat, ray_id, d, ray_emb, hidden)
     comp = orc.composite_forward(offsets, sigma, smp["dists"][m], rgb, smp["ts"][m])
     loss, g_rgb = orc.charbonnier(comp["rgb"], target)
     np.testing.assert_allclose(out.rgb.cpu().numpy(), comp["rgb"], rtol=1e-2, atol=2e-3)
     np.testing.assert_allclose(out.accumulation.cpu().numpy(), comp["acc"], rtol=1e-2, atol=2e-3)
     assert abs(float(out.loss) - loss) < 1e-2 * loss
     d_sigma, d_rgb = orc.composite_backward(offsets, sigma, smp["dists"][m], rgb, g_rgb)
-    d_feat, d_params, d_emb = orc.mlp_backward(mlp0, feat, ray_id, d, ray_emb, d_sigma, d_rgb, 64)
+    d_feat, d_params, d_emb = orc.mlp_backward(mlp0, feat, ray_id, d, ray_emb, d_sigma, d_rgb, hidden)
     g_table = orc.hash_backward(eng.enc.local_size_, prim, bias, pts01, anchors, d_feat, eng.enc.level_scales_host)
     got_t = eng.opt_table.unscaled_grad().view(-1, 2).double().cpu().numpy()
     sc = np.abs(g_table).max()

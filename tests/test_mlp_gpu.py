@@ -8,10 +8,20 @@ import torch
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
-H = 64
+WIDTHS = [64, 128]     # nerfstudio's default width / the reference's shipped gf-nerf config (gfnerf/config.py:124-125)
 
 
-def make_case(n, R, seed, with_emb=True, ray_stride=1):
+def offsets(H):
+    """name -> (start, end) in the parameter blob (include/gfnerf_b200.h)"""
+    out, o = {}, 0
+    for name, (a, b) in zip(("0", "1", "2", "3", "4"), ((H, 32), (16, H), (H, 63), (H, H), (3, H))):
+        out["w" + name] = (o, o + a * b); o += a * b
+        out["b" + name] = (o, o + a); o += a
+    out["count"] = o
+    return out
+
+
+def make_case(n, R, seed, with_emb=True, ray_stride=1, H=64):
     """ray_stride > 1 leaves ray ids without samples in between (rays that missed the octree)"""
     rng = np.random.RandomState(seed)
     g = torch.Generator().manual_seed(seed)
@@ -29,7 +39,7 @@ def make_case(n, R, seed, with_emb=True, ray_stride=1):
     return params, feat, ray_id, dirs, emb
 
 
-def _split_params(p):
+def _split_params(p, H):
     o, out = 0, []
     for a, b in ((H, 32), (16, H), (H, 63), (H, H), (3, H)):
         out.append(p[o:o + a * b].reshape(a, b)); o += a * b
@@ -53,31 +63,33 @@ def Qtr(x):
     return Q(hi) + Q(x - hi)
 
 
-def emulate_split_forward(params, feat, ray_id, dirs, emb):
+def emulate_split_forward(params, feat, ray_id, dirs, emb, H, bias_fp32=False):
     """The kernel's split-precision forward in numpy: weights, biases and hidden activations of layers 0..3 as fp16
     pairs, fp32 accumulate; the output layer takes h3 as plain fp16.  Returns (sigma, rgb, relu masks)."""
-    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = _split_params(params)
+    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = _split_params(params, H)
+    Qb = (lambda b: b) if bias_fp32 else Qhl      # H = 128 adds fp32 biases in the epilogue, H = 64 a bias MMA (hi + lo)
     x = feat.astype(np.float32)
-    p1 = x @ Qhl(w0).T + Qhl(b0)
+    p1 = x @ Qhl(w0).T + Qb(b0)
     h1 = Qtr(np.maximum(p1, 0))
-    h = Qtr(h1 @ Qhl(w1).T + Qhl(b1))
+    h = Qtr(h1 @ Qhl(w1).T + Qb(b1))
     rb = orc.sh4(dirs) @ w2[:, :16].T + b2 + (emb @ w2[:, 31:].T if emb is not None else 0)
     p2 = h[:, 1:] @ Qhl(w2[:, 16:31]).T + rb[ray_id]
     h2 = Qtr(np.maximum(p2, 0))
-    p3 = h2 @ Qhl(w3).T + Qhl(b3)
+    p3 = h2 @ Qhl(w3).T + Qb(b3)
     h3 = Q(np.maximum(p3, 0))
-    o = h3 @ Q(w4).T + Qhl(b4)
+    o = h3 @ Q(w4).T + Qb(b4)
     return np.exp(h[:, 0] + 1), 1 / (1 + np.exp(-o)), (p1 > 0, p2 > 0, p3 > 0)
 
 
-def emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma, d_rgb):
+def emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma, d_rgb, H):
     """numpy restatement of the reference field's backward (orc.mlp_backward) with fp16 rounding at the points where
     the kernel holds fp16 (weights, activations and gradient fragments; biases as fp16 pairs); fp32 accumulation.
     The ReLU masks are the split-precision forward's, as in the kernel."""
-    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = _split_params(params)
-    _, _, (m1, m2, m3) = emulate_split_forward(params, feat, ray_id, dirs, emb)
+    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = _split_params(params, H)
+    _, _, (m1, m2, m3) = emulate_split_forward(params, feat, ray_id, dirs, emb, H, bias_fp32=H == 128)
     # b0, b1, b3, b4 enter through a bias MMA (two fp16 columns: hi + lo); b2 is part of the fp32 per-ray bias
-    b0, b1, b3, b4 = Qhl(b0), Qhl(b1), Qhl(b3), Qhl(b4)
+    if H == 64:
+        b0, b1, b3, b4 = Qhl(b0), Qhl(b1), Qhl(b3), Qhl(b4)
     x = feat.astype(np.float32)
     h1 = Q(np.maximum(x @ Q(w0).T + b0, 0))
     h = h1 @ Q(w1).T + b1
@@ -109,7 +121,7 @@ def emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma, d_rgb):
     return Q(gh1) @ Q(w0), dp, demb
 
 
-def gpu_forward(params, feat, ray_id, dirs, emb):
+def gpu_forward(params, feat, ray_id, dirs, emb, H):
     from gfnerf_b200 import _lib
     L, st = _lib.lib(), _lib.cur_stream()
     n, R = feat.shape[0], dirs.shape[0]
@@ -118,39 +130,47 @@ def gpu_forward(params, feat, ray_id, dirs, emb):
     rb = torch.empty((R, H), device="cuda")
     _lib.check(L.gf_mlp_ray_bias(R, H, _lib.ptr(tp), _lib.ptr(td), _lib.ptr(te), _lib.ptr(rb), st))
     sigma, rgb = torch.empty(n, device="cuda"), torch.empty((n, 3), device="cuda")
-    masks = torch.zeros((n, 2, 4), dtype=torch.int32, device="cuda")
+    masks = torch.zeros((n, 2, H // 16), dtype=torch.int32, device="cuda")
+    assert L.gf_mlp_mask_words(H) == 2 * (H // 16)
     _lib.check(L.gf_mlp_forward(n, None, H, _lib.ptr(tp), _lib.ptr(tf), _lib.ptr(tr), _lib.ptr(rb), _lib.ptr(sigma),
                                 _lib.ptr(rgb), _lib.ptr(masks), st))
     return (tp, tf, tr, td, te, rb, masks), sigma, rgb
 
 
-def unpack_masks(masks, layer):
-    """relu_masks uint32 [n][2][4] -> bool [n, 64] of hidden layer `layer` (csrc/mlp_tc.cu mask_bits_of_pair: the two
-    bits of column pair q sit at 7 - q and 23 - q for q < 8, at 15 - (q - 8) and 31 - (q - 8) above)"""
-    w = masks.cpu().numpy().view(np.uint32)[:, :, layer]                     # [n, 2]
-    out = np.zeros((w.shape[0], 64), bool)
+def unpack_masks(masks, layer, H):
+    """relu_masks uint32 [n][2][H / 16] -> bool [n, H] of hidden layer `layer`: per column half, one word per 32 columns
+    (H = 64: word `layer`; H = 128: words 2 layer, 2 layer + 1), bits as csrc/mlp_tc_common.cuh mask_bits_of_pair puts
+    them: the two bits of column pair q sit at 7 - q and 23 - q for q < 8, at 15 - (q - 8) and 31 - (q - 8) above"""
+    w = masks.cpu().numpy().view(np.uint32)
+    half, chunks = H // 2, H // 64
+    out = np.zeros((w.shape[0], H), bool)
     for hf in range(2):
-        for q in range(16):
-            b0, b1 = (7 - q, 23 - q) if q < 8 else (15 - (q - 8), 31 - (q - 8))
-            out[:, 32 * hf + 2 * q] = (w[:, hf] >> np.uint32(b0)) & 1
-            out[:, 32 * hf + 2 * q + 1] = (w[:, hf] >> np.uint32(b1)) & 1
+        for c in range(chunks):
+            word = w[:, hf, chunks * layer + c]
+            for q in range(16):
+                b0, b1 = (7 - q, 23 - q) if q < 8 else (15 - (q - 8), 31 - (q - 8))
+                out[:, half * hf + 32 * c + 2 * q] = (word >> np.uint32(b0)) & 1
+                out[:, half * hf + 32 * c + 2 * q + 1] = (word >> np.uint32(b1)) & 1
     return out
 
 
 def test_param_count_and_unsupported_width():
     from gfnerf_b200 import _lib
-    assert _lib.lib().gf_mlp_param_count(64) == orc.mlp_param_count(64) == 11603
-    assert _lib.lib().gf_mlp_param_count(48) == -1
+    assert _lib.lib().gf_mlp_param_count(64) == orc.mlp_param_count(64) == 11603 == offsets(64)["count"]
+    assert _lib.lib().gf_mlp_param_count(128) == orc.mlp_param_count(128) == 31379 == offsets(128)["count"]
+    assert _lib.lib().gf_mlp_param_count(48) == -1 and _lib.lib().gf_mlp_mask_words(48) == -1
 
 
+@pytest.mark.parametrize("H", WIDTHS)
 @pytest.mark.parametrize("n,R,seed,with_emb", [(5000, 37, 0, True), (31, 2, 1, False), (4096, 1, 2, True)])
-def test_forward_matches_oracle(n, R, seed, with_emb):
-    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb)
-    (tp, tf, tr, td, te, rb, masks), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb)
+def test_forward_matches_oracle(n, R, seed, with_emb, H):
+    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb, H=H)
+    (tp, tf, tr, td, te, rb, masks), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb, H)
     # per-ray bias: fp32 against the oracle's SH and the reference weight slices
     sh = orc.sh4(dirs)
-    w2 = params[3152:3152 + 64 * 63].reshape(64, 63)
-    b2 = params[7184:7184 + 64]
+    off = offsets(H)
+    w2 = params[slice(*off["w2"])].reshape(H, 63)
+    b2 = params[slice(*off["b2"])]
     ref_rb = sh.astype(np.float64) @ w2[:, :16].T.astype(np.float64) + b2
     if emb is not None:
         ref_rb = ref_rb + emb.astype(np.float64) @ w2[:, 31:].T.astype(np.float64)
@@ -164,17 +184,17 @@ def test_forward_matches_oracle(n, R, seed, with_emb):
           "max abs err rgb", np.max(np.abs(rgb.cpu().numpy() - ref_rgb)))
     # the ReLU masks handed to the backward: those of the fp32 reference except where a pre-activation is within
     # ~1e-5 of zero, and exactly those of the numpy restatement of the split arithmetic away from such ties
-    emu_sigma, emu_rgb, emu_masks = emulate_split_forward(params, feat, ray_id, dirs, emb)
+    emu_sigma, emu_rgb, emu_masks = emulate_split_forward(params, feat, ray_id, dirs, emb, H, bias_fp32=H == 128)
     np.testing.assert_allclose(sigma.cpu().numpy(), emu_sigma, rtol=1e-5)
     np.testing.assert_allclose(rgb.cpu().numpy(), emu_rgb, rtol=1e-4, atol=1e-5)
-    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = _split_params(params)
+    w0, b0, w1, b1, w2, b2, w3, b3, w4, b4 = _split_params(params, H)
     x = feat.astype(np.float64)
     p1 = x @ w0.T.astype(np.float64) + b0
     h = np.maximum(p1, 0) @ w1.T.astype(np.float64) + b1
     p2 = h[:, 1:] @ w2[:, 16:31].T.astype(np.float64) + ref_rb[ray_id]
     p3 = np.maximum(p2, 0) @ w3.T.astype(np.float64) + b3
     for layer, pre in enumerate((p1, p2, p3)):
-        got = unpack_masks(masks, layer)
+        got = unpack_masks(masks, layer, H)
         flips = got != (pre > 0)
         print(f"layer {layer}: {flips.sum()} of {flips.size} ReLU masks differ from the fp64 reference; "
               f"largest |pre-activation| among them {np.abs(pre[flips]).max() if flips.any() else 0:.2e}")
@@ -182,14 +202,15 @@ def test_forward_matches_oracle(n, R, seed, with_emb):
         assert not flips.any() or np.abs(pre[flips]).max() < 2e-5 * max(1.0, np.abs(pre).max())
 
 
-def test_device_side_count_limits_work():
+@pytest.mark.parametrize("H", WIDTHS)
+def test_device_side_count_limits_work(H):
     from gfnerf_b200 import _lib
-    params, feat, ray_id, dirs, emb = make_case(1000, 5, 3)
-    (tp, tf, tr, td, te, rb, masks), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb)
+    params, feat, ray_id, dirs, emb = make_case(1000, 5, 3, H=H)
+    (tp, tf, tr, td, te, rb, masks), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb, H)
     n_dev = torch.tensor([613], dtype=torch.int32, device="cuda")
     for split in (True, False):          # training forward (split precision + masks) / inference forward (plain fp16)
         s2, c2 = torch.zeros(1000, device="cuda"), torch.zeros((1000, 3), device="cuda")
-        m2 = torch.zeros((1000, 2, 4), dtype=torch.int32, device="cuda") if split else None
+        m2 = torch.zeros((1000, 2, H // 16), dtype=torch.int32, device="cuda") if split else None
         _lib.check(_lib.lib().gf_mlp_forward(1000, _lib.ptr(n_dev), H, _lib.ptr(tp), _lib.ptr(tf), _lib.ptr(tr),
                                              _lib.ptr(rb), _lib.ptr(s2), _lib.ptr(c2), _lib.ptr(m2), _lib.cur_stream()))
         if split:
@@ -200,18 +221,20 @@ def test_device_side_count_limits_work():
         assert not s2[613:].any() and not c2[613:].any()
 
 
-# the per-ray gradient of the head's first-layer bias leaves a 128-sample tile through 8 "ray slots" (an MMA against a
-# one-hot matrix) when the tile's ray ids span < 8, else through a CUDA-core reduction: long rays, rays with gaps in
-# their ids (stride 2: slots 0, 2, 4, 6; stride 3: mixed), many short rays (every tile overflows the slots)
+# the per-ray gradient of the head's first-layer bias leaves a 128-sample tile through 8 (H = 128: 16) "ray slots" (an
+# MMA against a one-hot matrix) when the tile's ray ids span fewer, else through a CUDA-core path: long rays, rays with
+# gaps in their ids (stride 2: slots 0, 2, 4, 6; stride 3: mixed), many short rays (every tile overflows the slots)
+@pytest.mark.parametrize("H", WIDTHS)
 @pytest.mark.parametrize("n,R,seed,with_emb,stride", [(6000, 41, 5, True, 1), (130, 3, 6, False, 1), (129, 1, 7, True, 1),
                                                       (6000, 41, 5, True, 2), (6000, 60, 5, True, 3),
                                                       (6000, 800, 5, True, 1)])
-def test_backward_matches_oracle(n, R, seed, with_emb, stride):
+def test_backward_matches_oracle(n, R, seed, with_emb, stride, H):
     from gfnerf_b200 import _lib
     L, st = _lib.lib(), _lib.cur_stream()
-    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb, stride)
+    params, feat, ray_id, dirs, emb = make_case(n, R, seed, with_emb, stride, H=H)
     R = dirs.shape[0]
-    (tp, tf, tr, td, te, rb, masks), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb)
+    off = offsets(H)
+    (tp, tf, tr, td, te, rb, masks), sigma, rgb = gpu_forward(params, feat, ray_id, dirs, emb, H)
     rng = np.random.RandomState(seed + 100)
     d_sigma = (rng.normal(size=n) * 1e-4).astype(np.float32)
     d_rgb = (rng.normal(size=(n, 3)) * 1e-4).astype(np.float32)       # the magnitude a mean over ~8k rays produces
@@ -219,7 +242,7 @@ def test_backward_matches_oracle(n, R, seed, with_emb, stride):
                                                         d_rgb, H)
     tds, tdc = torch.from_numpy(d_sigma).cuda(), torch.from_numpy(d_rgb).cuda()
     d_feat = torch.zeros((n, 32), dtype=torch.float16, device="cuda")
-    d_params = torch.zeros(11603, device="cuda")
+    d_params = torch.zeros(off["count"], device="cuda")
     d_rb = torch.zeros((R, H), device="cuda")
     _lib.check(L.gf_mlp_backward(n, None, H, _lib.ptr(tp), _lib.ptr(tf), _lib.ptr(tr), _lib.ptr(rb), _lib.ptr(masks),
                                  _lib.ptr(tds), _lib.ptr(tdc), _lib.ptr(d_feat), _lib.ptr(d_params), _lib.ptr(d_rb),
@@ -239,14 +262,13 @@ def test_backward_matches_oracle(n, R, seed, with_emb, stride):
     if n >= 1000:
         assert rel_l2 < 2e-3
     # (2) against the same reference with the kernel's fp16 quantisation points emulated in numpy: tight
-    emu, emu_dp, emu_demb = emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma * 8192.0, d_rgb * 8192.0)
+    emu, emu_dp, emu_demb = emulate_fp16_backward(params, feat, ray_id, dirs, emb, d_sigma * 8192.0, d_rgb * 8192.0, H)
     emu, emu_dp = emu / 8192.0, emu_dp / 8192.0
     d2 = np.abs(got_dfeat - emu)
     print(f"d_feat vs fp16-emulating oracle: max {d2.max() / s:.2e} of max")
     assert np.all(d2 <= 2e-3 * np.abs(emu) + 2e-3 * s + 2.0 ** -24 / 128)
     got = d_params.cpu().numpy().astype(np.float64)
-    names = [("w0", 0, 2048), ("b0", 2048, 2112), ("w1", 2112, 3136), ("b1", 3136, 3152), ("w2", 3152, 7184),
-             ("b2", 7184, 7248), ("w3", 7248, 11344), ("b3", 11344, 11408), ("w4", 11408, 11600), ("b4", 11600, 11603)]
+    names = [(k,) + off[k] for k in ("w0", "b0", "w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")]
     for name, a, b in names:
         r, e, g = ref_dparams[a:b], emu_dp[a:b], got[a:b]
         sc = np.abs(r).max() + 1e-30
@@ -263,7 +285,7 @@ def test_backward_matches_oracle(n, R, seed, with_emb, stride):
         if n >= 1000:
             assert np.linalg.norm(got_e - ref_demb) / np.linalg.norm(ref_demb) < 2e-3
     else:
-        w2g = got[3152:7184].reshape(64, 63)
+        w2g = got[slice(*off["w2"])].reshape(H, 63)
         assert not w2g[:, 31:].any()        # no embedding: those columns get no gradient
     # frozen-MLP variant (focal stage): same d_feat, no parameter gradients
     d_feat2 = torch.zeros_like(d_feat)

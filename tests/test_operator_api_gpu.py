@@ -10,15 +10,16 @@ from tests.helpers import load_rig, make_sampler, rig_octree
 pytestmark = pytest.mark.gpu
 
 
-def build(rig, log2T=14, seed=0):
+def build(rig, log2T=14, seed=0, hidden=64):
     import gfnerf_b200 as gf
     from gfnerf_b200.engine import GFNeRFEngine
-    eng = GFNeRFEngine(make_sampler(rig, mode=1), log2_table_size=log2T, num_images=rig["c2w"].shape[0], seed=seed)
+    eng = GFNeRFEngine(make_sampler(rig, mode=1), log2_table_size=log2T, num_images=rig["c2w"].shape[0], seed=seed,
+                       hidden=hidden)
     eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
     eng.enc.shadow(force=True)
     ps = gf.PersSampler(rig["c2w"], rig["intri"], rig["bounds"], bbox_levels=10, mode=1, octree=rig_octree(rig))
-    field = gf.GFNeRFField(torch.zeros(2, 3), rig["c2w"].shape[0], log2_hashmap_size=log2T,
-                           use_appearance_embedding=True, n_volumes=eng.n_volumes).cuda()
+    field = gf.GFNeRFField(torch.zeros(2, 3), rig["c2w"].shape[0], log2_hashmap_size=log2T, hidden_dim=hidden,
+                           hidden_dim_color=hidden, use_appearance_embedding=True, n_volumes=eng.n_volumes).cuda()
     # identical parameters: table, primes, MLP blob, embedding
     field.base_encoding_init.load_states(eng.enc.States(), 0)
     o = 0
@@ -43,9 +44,10 @@ def bundle(rig, R, seed):
     return rb, T(o), T(d), T(cam)
 
 
-def test_operator_path_equals_fused_engine():
+@pytest.mark.parametrize("hidden", [64, 128])     # 128: the reference's shipped gf-nerf config (gfnerf/config.py:124-125)
+def test_operator_path_equals_fused_engine(hidden):
     rig = load_rig("rig8")
-    eng, model = build(rig)
+    eng, model = build(rig, hidden=hidden)
     R = 384
     rb, o, d, cam = bundle(rig, R, seed=5)
     target = torch.rand(R, 3, generator=torch.Generator().manual_seed(1)).cuda()
