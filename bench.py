@@ -181,9 +181,9 @@ def reference_arm(args):
     }))
 
 
-def workload_name():
+def workload_name(hidden=64):
     return ("GF-NeRF global stage: Hash3DAnchored 16 levels log2T=19 + PersSampler (400-camera synthetic aerial rig), "
-            f"{RAYS_PER_GPU} rays/GPU/step, up to 1024 samples/ray, H=64 MLPs, fwd+bwd+Adam")
+            f"{RAYS_PER_GPU} rays/GPU/step, up to 1024 samples/ray, H={hidden} MLPs, fwd+bwd+Adam")
 
 
 def render_arm(args):
@@ -230,6 +230,62 @@ def render_arm(args):
     }))
 
 
+def operator_api_arm(rig, dev, steps, warmup, hidden, log2t):
+    """The same training iteration through the REFERENCE's operator boundary instead of the fused engine: the call
+    sequence of gfnerf/nerfacto.py:522-619 (PersSampler.generate_ray_samples -> GFNeRFField -> get_weights_f2nerf ->
+    RGB / depth / accumulation renderers -> octree feedback) on its dense [R, 1024] tensors, torch autograd for the
+    backward, the caller's own torch.optim.Adam(lr 1e-2, eps 1e-15) (gfnerf/config.py:132-135) for the update --
+    what a gf_pipeline.py user gets by swapping the reference's modules for gfnerf_b200's.  Host buffers in (pinned
+    ray bundle + target, H2D inside the timed region), the loss read back every step."""
+    import torch
+    import gfnerf_b200 as gf
+    from tests.helpers import rig_octree
+    R = RAYS_PER_GPU
+    ps = gf.PersSampler(rig["c2w"], rig["intri"], rig["bounds"], bbox_levels=10, mode=0, octree=rig_octree(rig),
+                        ray_march_fineness_decay_end_iter=0, device=dev, seed=1234)
+    field = gf.GFNeRFField(torch.zeros(2, 3), rig["c2w"].shape[0], log2_hashmap_size=log2t, hidden_dim=hidden,
+                           hidden_dim_color=hidden, use_appearance_embedding=True, n_volumes=ps.get_n_volumes(),
+                           generator=torch.Generator().manual_seed(0)).to(dev)
+    model = gf.GFNeRFModel(ps, field).to(dev)
+    model.train()
+    params = list(field.base_encoding_init.get_params()) + list(field.base_network.parameters()) + \
+        list(field.mlp_head.parameters()) + list(field.embedding_appearance.parameters())
+    opt = torch.optim.Adam(params, lr=1e-2, eps=1e-15)
+    host = make_batches(rig, R, N_BATCHES, seed=4321)
+    pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
+    ones = torch.ones(R, 1, device=dev)
+    h2d = int(sum(a.numel() * a.element_size() for a in pinned[0]))
+
+    def step(i):
+        o, d, cam, tgt = (a.to(dev, non_blocking=True) for a in pinned[i % N_BATCHES])
+        # steps: past the fineness decay and never on a ProcOctree milestone (every 1000), like the engine arm
+        rb = gf.RayBundle(origins=o, directions=d, lookat_directions=d, pixel_area=ones, camera_indices=cam.view(-1, 1),
+                          rel_camera_indices=cam.view(-1, 1), steps=torch.full((R, 1), 20001 + i % 900, device=dev))
+        out = model.get_outputs(rb)
+        diff = out["rgb"] - tgt
+        loss = torch.sqrt(diff * diff + 1e-12).sum() / R          # CharbonnierLoss, losses.py:73-84
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss.item())                                 # D2H of the step's result
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = [step(warmup + i) for i in range(steps)]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    assert all(np.isfinite(losses)), losses
+    return {"value": R / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "path": "gfnerf_b200.GFNeRFModel.get_outputs (PersSampler -> GFNeRFField -> get_weights_f2nerf -> renderers "
+                    "-> UpdateOctNodes; dense [R,1024] tensors, all slots evaluated like the reference) + torch autograd "
+                    "+ torch.optim.Adam: the drop-in for gfnerf/nerfacto.py:522-619 under nerfstudio's trainer"}
+
+
 # --------------------------------------------------------------------------------------------
 _REAL_STDOUT = None
 
@@ -258,6 +314,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-operator-api", action="store_true",
+                    help="skip the e2e_operator_api leg (the same step through GFNeRFModel.get_outputs + autograd)")
     ap.add_argument("--no-sample-ahead", action="store_true",
                     help="sample each batch at the start of its own step instead of under the previous backward")
     ap.add_argument("--workload", default="global", choices=["global", "focal", "render"],
@@ -265,6 +323,9 @@ def main():
                          "one private residual sub-encoder per GPU (log2T 21), no gradient exchange.  render: config 5 "
                          "-- forward-only 1920x1080 frames, log2T 23, eval sampling; a step = one frame")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
+    ap.add_argument("--hidden", type=int, default=64, choices=[64, 128],
+                    help="MLP width: 64 = the north star's / nerfstudio's default (the bench line); 128 = the "
+                         "reference's shipped gf-nerf config (gfnerf/config.py:124-125)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -302,7 +363,8 @@ def main():
     sampler.ray_march_fineness_ = 1.0
     log2t = 21 if args.workload == "focal" else LOG2T
     # (the engine broadcasts rank 0's initial parameters when it is given a group)
-    eng = GFNeRFEngine(sampler, log2_table_size=log2t, num_images=rig["c2w"].shape[0], seed=0, dist_group=group)
+    eng = GFNeRFEngine(sampler, log2_table_size=log2t, num_images=rig["c2w"].shape[0], seed=0, dist_group=group,
+                       hidden=args.hidden)
     if args.workload == "focal":
         eng.start_block_stage(seed=100 + rank)
 
@@ -381,12 +443,14 @@ def main():
             j = json.load(f)
         peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "src": "measured"}
     # algorithmic bytes / flops per launch (DESIGN.md "roofline accounting")
+    mlp_macs = float(114 * args.hidden + args.hidden * args.hidden)
     algo = {
         "hash_fwd": ("hbm", 660.0 * v_mean), "hash_bwd": ("hbm", 660.0 * v_mean),
         "sample_rays": ("hbm", 32.0 * v_mean + 24.0 * RAYS_PER_GPU), "compact": ("hbm", (32.0 + 36.0) * v_mean),
         "composite_fwd": ("hbm", (28.0 + 12.0) * v_mean + 20.0 * RAYS_PER_GPU),
         "composite_bwd": ("hbm", 44.0 * v_mean + 20.0 * RAYS_PER_GPU),
-        "mlp_fwd": ("tensor", 2.0 * 11392.0 * v_mean), "mlp_bwd": ("tensor", 2.0 * 2.0 * 11392.0 * v_mean),
+        # multiply-adds per sample of the two stacks: 32 H + 16 H + 63 H + H^2 + 3 H (11 392 at H = 64)
+        "mlp_fwd": ("tensor", 2.0 * mlp_macs * v_mean), "mlp_bwd": ("tensor", 2.0 * 2.0 * mlp_macs * v_mean),
         # the 8.5 * T rows the levels can reach (the rest never gets a gradient: dense Adam leaves it untouched)
         "adam_table": ("hbm", 30.0 * 17 * (1 << log2t)),
     }
@@ -430,6 +494,12 @@ def main():
         for k in kernels:
             print(k, file=sys.stderr)
 
+    e2e_operator = None
+    if rank == 0 and world == 1 and args.workload == "global" and not args.no_operator_api:
+        try:
+            e2e_operator = operator_api_arm(rig, dev, max(3, min(args.steps, 10)), 3, args.hidden, log2t)
+        except Exception as e:   # a reported side number must never take the bench line down with it
+            e2e_operator = {"unavailable": f"{type(e).__name__}: {e}"}
     cpu_baseline = cpu_reference_path = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_reference_path = time_reference_cpu_path()
@@ -444,10 +514,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 tables + f16 tensor-core MLP, f32 accumulate / geometry / optimizer",
             "data": "synthetic",
-            "config": {"workload": workload_name() if args.workload == "global" else
+            "config": {"workload": workload_name(args.hidden) if args.workload == "global" else
                        "GF-NeRF focal stage: frozen global Hash3DAnchored + MLPs, one zero-initialised residual "
                        f"sub-encoder per GPU (log2T={log2t}), {RAYS_PER_GPU} rays/GPU/step, no gradient exchange",
-                       "rays_per_gpu": RAYS_PER_GPU, "log2T": log2t, "hidden": 64,
+                       "rays_per_gpu": RAYS_PER_GPU, "log2T": log2t, "hidden": args.hidden,
                        "samples_per_step_per_gpu": round(v_mean), "slots_per_step_per_gpu": RAYS_PER_GPU * 1024,
                        "l2_policy": "inputs larger than L2 (0.3 GB table+optimizer state, ~1 GB sample buffers, "
                                     f"{N_BATCHES} ray batches cycled)",
@@ -465,6 +535,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rays/s",
                     "h2d_bytes_per_step": int(sum(a.numel() * a.element_size() for a in pinned[0])) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+            "e2e_operator_api": e2e_operator,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roofline,

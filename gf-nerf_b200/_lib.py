@@ -41,6 +41,7 @@ _SIGS = {
     "gf_octree_build_fetch": [_vp, _vp, _vp],
     "gf_octree_search_order": [_vp],
     "gf_octree_proc": [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _i64, _vp],
+    "gf_octree_proc_device": [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp],
     "gf_sampler_points_anchors": [_i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "gf_octree_edge_pool": [_vp, _i64, _vp, _i64, _vp],
     "gf_sampler_edge_samples": [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -68,7 +69,8 @@ _SIGS = {
     "gf_adam_step": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _int, _vp],
 }
 
-EXPORTS = ["gf_last_error", "gf_version", "gf_launch_count", "gf_mlp_param_count", "gf_mlp_mask_words"] + sorted(_SIGS)
+EXPORTS = ["gf_last_error", "gf_version", "gf_launch_count", "gf_mlp_param_count", "gf_mlp_mask_words",
+           "gf_octree_proc_device_scratch_bytes"] + sorted(_SIGS)
 
 
 def lib():
@@ -84,14 +86,15 @@ def lib():
         L.gf_last_error.restype = C.c_char_p
         L.gf_version.restype = C.c_char_p
         L.gf_launch_count.restype = C.c_int64
-        for name, sig in list(_SIGS.items()) + [("gf_mlp_param_count", [_int]), ("gf_mlp_mask_words", [_int])]:
+        for name, sig in list(_SIGS.items()) + [("gf_mlp_param_count", [_int]), ("gf_mlp_mask_words", [_int]),
+                                                   ("gf_octree_proc_device_scratch_bytes", [_i64])]:
             try:
                 fn = getattr(L, name)
             except AttributeError as e:  # a stale build: fail loudly, never fall back
                 raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild with "
                                    "`python gf-nerf_b200/build.py --force`") from e
             fn.argtypes = sig
-            fn.restype = C.c_int64 if name == "gf_mlp_param_count" else _int
+            fn.restype = C.c_int64 if name in ("gf_mlp_param_count", "gf_octree_proc_device_scratch_bytes") else _int
         _lib = L
     return _lib
 

@@ -311,21 +311,30 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     if (compact_freq_ > 0 && iter_step % compact_freq_ == 0) ProcOctree(true, false, false);
   }
 
-  // PersOctree::ProcOctree (PersSampler.cpp:154-417): node blob + statistics to the host, gf_octree_proc, back
+  // PersOctree::ProcOctree (PersSampler.cpp:154-417) on the device (gf_octree_proc_device): the node blob and the
+  // statistics are rebuilt in HBM; the host reads back the new node count and the error word only
   void ProcOctree(bool compact, bool subdivide, bool brute_force) {
-    auto nodes = tree_nodes_.cpu().contiguous();
-    auto w = weight_stats_.cpu().contiguous(), a = alpha_stats_.cpu().contiguous(), v = visit_cnt_.cpu().contiguous();
-    int64_t n_out = 0;
-    GF_CHECK(gf_octree_proc(nodes.data_ptr(), n_nodes(), w.data_ptr<int64_t>(), a.data_ptr<int64_t>(),
-                            v.data_ptr<int64_t>(), compact, subdivide, brute_force, nullptr, nullptr, nullptr, 0, &n_out));
-    auto nodes_o = torch::empty({n_out * GF_TREE_NODE_BYTES}, torch::kUInt8);
-    auto w_o = torch::empty({n_out}, torch::kInt64), a_o = torch::empty({n_out}, torch::kInt64);
-    GF_CHECK(gf_octree_proc(nodes.data_ptr(), n_nodes(), w.data_ptr<int64_t>(), a.data_ptr<int64_t>(),
-                            v.data_ptr<int64_t>(), compact, subdivide, brute_force, nodes_o.data_ptr(),
-                            w_o.data_ptr<int64_t>(), a_o.data_ptr<int64_t>(), n_out, &n_out));
-    tree_nodes_ = nodes_o.to(torch::kCUDA);
-    weight_stats_ = w_o.to(torch::kCUDA);
-    alpha_stats_ = a_o.to(torch::kCUDA);
+    const int64_t n_in = n_nodes(), cap = subdivide ? 9 * n_in : n_in;
+    auto u8 = tree_nodes_.options();
+    auto i64 = weight_stats_.options();
+    const int64_t scratch_bytes = gf_octree_proc_device_scratch_bytes(n_in);
+    auto scratch = torch::empty({scratch_bytes}, u8);
+    auto nodes_o = torch::empty({cap * GF_TREE_NODE_BYTES}, u8);
+    auto w_o = torch::empty({cap}, i64), a_o = torch::empty({cap}, i64);
+    auto res = torch::zeros({2}, i64);   // [0] = nodes written, low word of [1] = error word
+    GF_CHECK(gf_octree_proc_device(tree_nodes_.data_ptr(), n_in, weight_stats_.data_ptr<int64_t>(),
+                                   alpha_stats_.data_ptr<int64_t>(), visit_cnt_.data_ptr<int64_t>(), compact, subdivide,
+                                   brute_force, nodes_o.data_ptr(), w_o.data_ptr<int64_t>(), a_o.data_ptr<int64_t>(), cap,
+                                   scratch.data_ptr(), scratch_bytes, res.data_ptr<int64_t>(),
+                                   reinterpret_cast<int32_t*>(res.data_ptr<int64_t>() + 1), stream()));
+    auto host = res.cpu();
+    const int64_t n_out = host.data_ptr<int64_t>()[0], err = host.data_ptr<int64_t>()[1] & 0xffffffffLL;
+    TORCH_CHECK(!(err & 1), "gf_octree_proc: the root was pruned (no valid leaf left in the octree)");
+    TORCH_CHECK(!(err & 2), "gf_octree_proc: a removed node is still linked (compact = 0 on a pruned tree?)");
+    TORCH_CHECK(err == 0, "gf_octree_proc_device: error word ", err);
+    tree_nodes_ = nodes_o.slice(0, 0, n_out * GF_TREE_NODE_BYTES).clone();
+    weight_stats_ = w_o.slice(0, 0, n_out).clone();
+    alpha_stats_ = a_o.slice(0, 0, n_out).clone();
     visit_cnt_ = torch::zeros({n_out}, visit_cnt_.options());
   }
 

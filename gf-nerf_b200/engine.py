@@ -190,17 +190,29 @@ class GFNeRFEngine:
         self._events = [] if on else None
         self.sampler.stage_hook = self._stage if on else None
 
+    # GF_NVTX=1: every stage of the step is an NVTX range ("gf/<stage>") -- what `ncu --nvtx --nvtx-include
+    # "gf/hash_fwd/"` / an nsys timeline filter on.  Off by default: two extra host calls per stage.
+    NVTX = os.environ.get("GF_NVTX", "0") == "1"
+
     @contextlib.contextmanager
     def _stage(self, name):
         ev = getattr(self, "_events", None)
-        if ev is None:
+        if ev is None and not self.NVTX:
             yield
             return
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        yield
-        e1.record()
-        ev.append((name, e0, e1))
+        if self.NVTX:
+            torch.cuda.nvtx.range_push("gf/" + name)
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        try:
+            yield
+        finally:
+            if ev is not None:
+                e1.record()
+                ev.append((name, e0, e1))
+            if self.NVTX:
+                torch.cuda.nvtx.range_pop()
 
     def stage_times(self, reset: bool = True):
         """-> {stage: (total ms, calls)} of everything recorded since the last reset (synchronises)."""

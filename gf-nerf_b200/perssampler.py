@@ -297,8 +297,42 @@ class PersSamplerCore:
         self._milestones(int(iter_step))
 
     def ProcOctree(self, compact: bool, subdivide: bool, brute_force: bool):
-        """PersOctree::ProcOctree (PersSampler.cpp:154-417): D2H of the node blob + stats, host compaction /
-        subdivision in C++ (gf_octree_proc, csrc/octree_host.cu), H2D -- the same round trip as the reference."""
+        """PersOctree::ProcOctree (PersSampler.cpp:154-417) on the device: one kernel (gf_octree_proc_device,
+        csrc/octree_device.cu) rebuilds the node blob and the statistics in HBM -- byte-identical to the reference's
+        host rebuild (gf_octree_proc, kept as the checker: `ProcOctreeHost`) without its D2H / H2D round trip of the
+        blob.  The only host read is the new node count + error word (12 bytes)."""
+        n_in = self.n_nodes
+        cap = 9 * n_in if subdivide else n_in
+        L, dev = _lib.lib(), self.device
+        scratch_bytes = int(L.gf_octree_proc_device_scratch_bytes(n_in))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        nodes_o = torch.empty(cap * 128, dtype=torch.uint8, device=dev)
+        w_o = torch.empty(cap, dtype=torch.int64, device=dev)
+        a_o = torch.empty(cap, dtype=torch.int64, device=dev)
+        res = torch.zeros(4, dtype=torch.int32, device=dev)           # [0:2] = n_out (int64), [2] = error word
+        with torch.cuda.device(dev):
+            _lib.check(L.gf_octree_proc_device(
+                _lib.ptr(self.tree_nodes_gpu_), n_in, _lib.ptr(self.tree_weight_stats_), _lib.ptr(self.tree_alpha_stats_),
+                _lib.ptr(self.tree_visit_cnt_), int(compact), int(subdivide), int(brute_force), _lib.ptr(nodes_o),
+                _lib.ptr(w_o), _lib.ptr(a_o), cap, _lib.ptr(scratch), scratch_bytes, _lib.ptr(res),
+                res.data_ptr() + 8, _lib.cur_stream()), "gf_octree_proc_device")
+        host = res.cpu()
+        n, err = int(host[:2].view(torch.int64).item()), int(host[2].item())
+        if err & 1:
+            raise RuntimeError("gf_octree_proc: the root was pruned (no valid leaf left in the octree)")
+        if err & 2:
+            raise RuntimeError("gf_octree_proc: a removed node is still linked (compact = 0 on a pruned tree?)")
+        if err:
+            raise RuntimeError(f"gf_octree_proc_device: error word {err}, {n} nodes needed, capacity {cap}")
+        self.tree_nodes_gpu_ = nodes_o[:n * 128].clone() if n < cap else nodes_o
+        self.tree_weight_stats_ = w_o[:n].clone() if n < cap else w_o
+        self.tree_alpha_stats_ = a_o[:n].clone() if n < cap else a_o
+        self.tree_visit_cnt_ = torch.zeros(n, dtype=torch.int64, device=dev)
+        self._octree_stale = True          # the host mirror (self.octree) is refreshed when somebody asks for it
+
+    def ProcOctreeHost(self, compact: bool, subdivide: bool, brute_force: bool):
+        """The reference's own schedule of the same work: D2H of the node blob + stats, host compaction / subdivision
+        in C++ (gf_octree_proc, csrc/octree_host.cu), H2D.  Kept as the checker of the device path."""
         import ctypes as C
         nodes = self.tree_nodes_gpu_.cpu().contiguous()
         w = self.tree_weight_stats_.cpu().contiguous()
@@ -313,11 +347,29 @@ class PersSamplerCore:
         w_o, a_o = torch.empty(n, dtype=torch.int64), torch.empty(n, dtype=torch.int64)
         _lib.check(L.gf_octree_proc(*args, _lib.ptr(nodes_o), _lib.ptr(w_o), _lib.ptr(a_o), n, C.byref(n_out)),
                    "gf_octree_proc")
-        oc = self.octree
+        oc = self._octree
         oc.load_blobs(nodes_o.numpy(), self.pers_trans_gpu_.cpu().numpy())
         oc.weight_stats, oc.alpha_stats = w_o.numpy(), a_o.numpy()
         oc.visit_cnt = np.zeros(n, np.int64)
+        self._octree_stale = False
         self._upload_octree(stats=True)
+
+    @property
+    def octree(self) -> Optional[PersOctree]:
+        """Host mirror of the device octree (numpy); downloaded again after the device changed the tree."""
+        if getattr(self, "_octree_stale", False) and self._octree is not None:
+            oc = self._octree
+            oc.load_blobs(self.tree_nodes_gpu_.cpu().numpy(), self.pers_trans_gpu_.cpu().numpy())
+            oc.weight_stats = self.tree_weight_stats_.cpu().numpy()
+            oc.alpha_stats = self.tree_alpha_stats_.cpu().numpy()
+            oc.visit_cnt = self.tree_visit_cnt_.cpu().numpy()
+            self._octree_stale = False
+        return self._octree
+
+    @octree.setter
+    def octree(self, value):
+        self._octree = value
+        self._octree_stale = False
 
     @staticmethod
     def invisible_nodes(nodes: torch.Tensor, w2c: torch.Tensor, intri: torch.Tensor, bound: torch.Tensor) -> torch.Tensor:

@@ -220,6 +220,21 @@ int gf_octree_proc(const void* nodes_in, int64_t n_in, const int64_t* weight_sta
                    const int64_t* visit_cnt_in, int compact, int subdivide, int brute_force, void* nodes_out,
                    int64_t* weight_stats_out, int64_t* alpha_stats_out, int64_t capacity, int64_t* n_out);
 
+/* The same ProcOctree ON THE DEVICE (csrc/octree_device.cu): every pointer is a device pointer, one single-CTA kernel
+ * on `stream`, byte-identical output to gf_octree_proc (which stays as the host-side checker), and the node blob never
+ * leaves HBM -- the reference's ProcOctree is a D2H copy + host rebuild + H2D copy every compact_freq steps and twice
+ * per subdivision milestone (PersSampler.cpp:154-417).  nodes_out / *_stats_out: room for `capacity` nodes (worst
+ * case 9 * n_in with subdivide, n_in without); scratch: gf_octree_proc_device_scratch_bytes(n_in) bytes, 16-byte
+ * aligned.  *d_n_out (device int64) = nodes written.  *d_error (device int32, OR-ed): 1 = the root was pruned,
+ * 2 = a removed node is still linked (compact = 0 on a pruned tree; the reference CHECK-fails), 4 = capacity too
+ * small (*d_n_out = nodes needed).  The host reads d_n_out / d_error when it needs them (8 + 4 bytes). */
+int64_t gf_octree_proc_device_scratch_bytes(int64_t n_in);
+int gf_octree_proc_device(const void* nodes_in, int64_t n_in, const int64_t* weight_stats_in,
+                          const int64_t* alpha_stats_in, const int64_t* visit_cnt_in, int compact, int subdivide,
+                          int brute_force, void* nodes_out, int64_t* weight_stats_out, int64_t* alpha_stats_out,
+                          int64_t capacity, void* scratch, int64_t scratch_bytes, int64_t* d_n_out, int32_t* d_error,
+                          void* stream);
+
 /* PersSampler::GetPointsAnchors (GetRaysTreeNodesIntersectsKernel + GetTreeNodeIdxFromTsKernel, :799-853, 924-980;
  * the proposal-sampler variant, cold): anchors i64 [n_rays, n_pts_per_ray] = index of the LEAF whose slab interval
  * along the ray contains t_cur (= (t_start + t_end) / 2, f32 [n_rays, n_pts_per_ray]), -1 if none; a sample exactly

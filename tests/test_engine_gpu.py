@@ -17,15 +17,17 @@ def make_engine(rig, log2T=14, mode=1, seed=0, hidden=64):
 
 
 # hidden 64: nerfstudio's default field; hidden 128: the reference's shipped gf-nerf config (gfnerf/config.py:124-125)
-@pytest.mark.parametrize("hidden", [64, 128])
-def test_one_step_matches_oracle_chain(hidden):
+# ("rig20", 19, 256): BASELINE.json configs[1] at its real size -- the 400-camera rig, its octree, a log2T = 19 table --
+# on as many rays of the bench's batch as the oracle marches in a second (value-level parity at the bench's size)
+@pytest.mark.parametrize("hidden,rig_name,log2T,R", [(64, "rig8", 14, 512), (128, "rig8", 14, 512), (64, "rig20", 19, 256),
+                                                     (128, "rig20", 19, 256)])
+def test_one_step_matches_oracle_chain(hidden, rig_name, log2T, R):
     from gfnerf_b200.persoctree import rig_rays
-    rig = load_rig("rig8")
-    eng = make_engine(rig, hidden=hidden)
+    rig = load_rig(rig_name)
+    eng = make_engine(rig, hidden=hidden, log2T=log2T)
     # post-training-like feature scale so that densities are not all ~e
     eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
     eng.enc.shadow(force=True)
-    R = 512
     o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=2)
     rng = np.random.RandomState(0)
     target = rng.rand(R, 3).astype(np.float32)

@@ -10,7 +10,9 @@ import sys
 
 WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
-        'lts__t_bytes.sum', 'l1tex__t_bytes.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sectors.sum', 'lts__t_sectors.sum.per_second', 'lts__t_sectors.sum.pct_of_peak_sustained_elapsed',
+        'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'lts__t_requests_srcunit_tex_op_red.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__thread_inst_executed_per_inst_executed.ratio',
@@ -58,11 +60,21 @@ def full(src, dst, title, cmd):
                 if w in hdr:
                     i = hdr.index(w)
                     f.write(f"| {w} | {r[i]} | {units[i]} |\n")
+            # L2 traffic in bytes and GB/s (a sector is 32 bytes): what `lts__t_bytes` would say
+            if 'lts__t_sectors.sum' in hdr and 'gpu__time_duration.sum' in hdr:
+                try:
+                    sec = float(r[hdr.index('lts__t_sectors.sum')].replace(',', ''))
+                    ti = hdr.index('gpu__time_duration.sum')
+                    t = float(r[ti].replace(',', '')) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}[units[ti]]
+                    f.write(f"| L2 bytes (lts__t_sectors x 32) | {sec * 32 / 1e6:.1f} | MB |\n")
+                    f.write(f"| L2 throughput | {sec * 32 / t / 1e9:.0f} | GB/s |\n")
+                except (ValueError, KeyError):
+                    pass
             f.write("\n")
 
 
 NAMES = [("sample_rays_kernel", "sample_rays"), ("compact_kernel", "compact"), ("hash_fwd_kernel", "hash_fwd"),
-         ("hash_bwd_kernel", "hash_bwd"), ("mlp_tc_kernel<0>", "mlp_fwd"), ("mlp_tc_kernel<2>", "mlp_bwd"),
+         ("hash_bwd_kernel", "hash_bwd"), ("mlp_tc_kernel<3>", "mlp_fwd"), ("mlp_tc_kernel<0>", "mlp_fwd_plain"), ("mlp_tc_kernel<2>", "mlp_bwd"),
          ("mlp_tc_kernel<1>", "mlp_bwd_frozen"), ("composite_fwd_kernel", "composite_fwd"),
          ("composite_bwd_kernel", "composite_bwd"), ("adam_kernel<1>", "adam_table")]
 
