@@ -91,14 +91,16 @@ def test_repeated_subdivision_and_pruning_stays_identical():
     assert oc.nodes.shape[0] > rig["tree_nodes"].size // 128
 
 
-def test_pruned_root_is_reported():
+def test_everything_pruned_leaves_the_bare_root_like_the_host():
+    """every leaf voted empty: the pruning sweep starts at node 1 (PersSampler.cpp:189), so the root stays an interior
+    node without children and is the one survivor -- on the host and on the device"""
     rig = load_rig("rig8")
     oc = _octree(rig)
-    oc.nodes["trans_idx"][:] = -1                         # every leaf voted empty
-    *_, err = _dev(oc, True, False, False)
-    assert err & 1
-    with pytest.raises(RuntimeError):
-        _cxx(oc, True, False, False)
+    oc.nodes["trans_idx"][:] = -1
+    ref_nodes, ref_w, ref_a = _cxx(oc, True, False, False)
+    got_nodes, got_w, got_a, err = _dev(oc, True, False, False)
+    assert err == 0 and ref_nodes.size == 128
+    assert np.array_equal(got_nodes, ref_nodes) and np.array_equal(got_w, ref_w) and np.array_equal(got_a, ref_a)
 
 
 def test_sampler_proc_octree_runs_on_the_device_and_matches_the_host_schedule():
