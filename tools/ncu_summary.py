@@ -73,7 +73,8 @@ def full(src, dst, title, cmd):
             f.write("\n")
 
 
-NAMES = [("sample_rays_kernel", "sample_rays"), ("compact_kernel", "compact"), ("hash_fwd_kernel", "hash_fwd"),
+NAMES = [("mlp_tc128_kernel<3>", "mlp128_fwd"), ("mlp_tc128_kernel<2>", "mlp128_bwd"), ("peer_reduce_adam", "exchange"),
+         ("sample_rays_kernel", "sample_rays"), ("compact_kernel", "compact"), ("hash_fwd_kernel", "hash_fwd"),
          ("hash_bwd_kernel", "hash_bwd"), ("mlp_tc_kernel<3>", "mlp_fwd"), ("mlp_tc_kernel<0>", "mlp_fwd_plain"), ("mlp_tc_kernel<2>", "mlp_bwd"),
          ("mlp_tc_kernel<1>", "mlp_bwd_frozen"), ("composite_fwd_kernel", "composite_fwd"),
          ("composite_bwd_kernel", "composite_bwd"), ("adam_kernel<1>", "adam_table")]
@@ -90,7 +91,7 @@ def traffic(src, dst, title, cmd):
     res = {}
     for r in rows[2:]:
         for pat, key in NAMES:
-            if pat in r[ki] and key not in res:
+            if pat in r[ki]:      # the LAST captured launch of each kernel (warm caches, trained-on table)
                 tot = 0.0
                 for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
                     i = hdr.index(m)
