@@ -564,18 +564,20 @@ class GFNeRFEngine:
     @torch.no_grad()
     def train_step_host(self, rays_o, rays_d, target_rgb, rel_camera_indices=None, next_rays=None, **kw) -> StepOutputs:
         """`train_step` for HOST tensors (pinned for true asynchrony), the call a data loader makes: the batch goes
-        host -> device on a copy stream into one of two staging slots, so the copy of batch k + 1 overlaps the
-        compute of batch k; the step's loss comes back device -> host asynchronously into a pinned ring
+        host -> device on a copy stream into one of three staging slots, so the copy of batch k + 1 overlaps the
+        compute of batch k (three, not two: the slot batch k + 1 is staged into was last read by step k - 2, so the copy
+        never waits for the step in flight -- with two slots every step started one H2D latency after the previous one
+        had drained); the step's loss comes back device -> host asynchronously into a pinned ring
         (`read_losses()`), so the host never blocks inside the training loop (the reference blocks five times per
         step on .item()).  next_rays = the NEXT call's (rays_o, rays_d) host tensors: they are
         staged now and sampled underneath this step's backward pass (`train_step(next_rays=...)`)."""
         dev = self.device
         if not hasattr(self, "_h2d"):
-            self._h2d = dict(stream=torch.cuda.Stream(device=dev), slot=0, free=[None, None], bufs=[{}, {}],
-                             losses=[], pinned=[], staged_rays=[None, None])
+            self._h2d = dict(stream=torch.cuda.Stream(device=dev), slot=0, free=[None] * 3, bufs=[{}, {}, {}],
+                             losses=[], pinned=[], staged_rays=[None] * 3)
         h = self._h2d
         slot = h["slot"]
-        h["slot"] ^= 1
+        h["slot"] = (slot + 1) % 3
         cur = torch.cuda.current_stream(dev)
 
         def stage(slot_, name, src):
@@ -594,7 +596,7 @@ class GFNeRFEngine:
         h["staged_rays"][slot] = None
         staged = []
         with torch.cuda.stream(h["stream"]):
-            if h["free"][slot] is not None and not have_rays:    # the step that last read this slot has finished
+            if h["free"][slot] is not None:    # the step that last read this slot (three calls ago) has finished
                 h["stream"].wait_event(h["free"][slot])
             for name, src in zip(names, host):
                 if src is None:
@@ -605,7 +607,7 @@ class GFNeRFEngine:
                     staged.append(stage(slot, name, src))
             nxt = None
             if next_rays is not None:
-                nslot = slot ^ 1
+                nslot = (slot + 1) % 3
                 if h["free"][nslot] is not None:
                     h["stream"].wait_event(h["free"][nslot])
                 nxt = (stage(nslot, "o", next_rays[0]), stage(nslot, "d", next_rays[1]))
