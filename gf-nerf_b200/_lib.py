@@ -64,6 +64,7 @@ _SIGS = {
     "gf_peer_import": [_vp, _vp],
     "gf_peer_close": [_vp],
     "gf_peer_barrier": [_int, _int, C.c_uint32, _vp, _vp, _vp, _vp, _vp],
+    "gf_peer_max_i64": [_int, _i64, _vp, _vp, _vp],
     "gf_peer_reduce_adam": [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _vp, _vp],
     "gf_adam_step_counted": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _vp, _f32, _int, _vp, _vp],
     "gf_adam_step": [_i64, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i64, _f32, _int, _vp],

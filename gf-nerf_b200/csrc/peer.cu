@@ -136,6 +136,23 @@ peer_reduce_adam_kernel(int64_t lo4, int64_t hi4, PeerPtrs grads, float4* __rest
   }
 }
 
+// dst[i] = max over the ranks of src_r[i]: the octree votes (MarkVistNodeKernel's atomicMax adders / marks and the
+// visit counts, PersSampler_cuda.cu:518-574) of ALL rays of the step, so that every replica applies the votes one
+// process seeing every ray would have produced -- an all-reduce(MAX) as (world - 1) peer loads per element
+template <int WORLD>
+__global__ void __launch_bounds__(256) peer_max_i64_kernel(int64_t n, PeerPtrs src, long long* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long v[WORLD];
+#pragma unroll
+    for (int r = 0; r < WORLD; r++) v[r] = __ldcg(reinterpret_cast<const long long*>(src.p[r]) + i);
+    long long m = v[0];
+#pragma unroll
+    for (int r = 1; r < WORLD; r++) m = v[r] > m ? v[r] : m;
+    dst[i] = m;
+  }
+}
+
 __global__ void peer_count_kernel(long long* d_step, const int* skip_flag) {
   if (!(skip_flag && *skip_flag)) *d_step += 1;
 }
@@ -210,6 +227,33 @@ int gf_peer_barrier(int world, int rank, uint32_t epoch, void* const* flag_ptrs,
   }
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(world, rank, epoch, f, d_local_flag, d_any_flag, d_error);
   return check_launch("peer_barrier_kernel");
+}
+
+int gf_peer_max_i64(int world, int64_t n, void* const* src_ptrs, int64_t* dst, void* stream) {
+  GF_REQUIRE(world >= 1 && world <= kMaxPeers && n >= 0 && src_ptrs, "gf_peer_max_i64: bad arguments");
+  if (n == 0) return GF_OK;
+  GF_REQUIRE(dst != nullptr, "gf_peer_max_i64: null output");
+  PeerPtrs p{};
+  for (int r = 0; r < world; r++) {
+    GF_REQUIRE(src_ptrs[r] != nullptr && (reinterpret_cast<uintptr_t>(src_ptrs[r]) & 7) == 0,
+               "gf_peer_max_i64: source pointer of rank %d is null or not 8-byte aligned", r);
+    p.p[r] = src_ptrs[r];
+  }
+  const int grid = stride_grid(n, 256, 4, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+#define GF_PEER_CASE(W) \
+  case W:               \
+    peer_max_i64_kernel<W><<<grid, 256, 0, st>>>(n, p, (long long*)dst); \
+    break;
+  switch (world) {
+    GF_PEER_CASE(1) GF_PEER_CASE(2) GF_PEER_CASE(3) GF_PEER_CASE(4) GF_PEER_CASE(5) GF_PEER_CASE(6) GF_PEER_CASE(7)
+    GF_PEER_CASE(8)
+    default:
+      set_error("gf_peer_max_i64: world size %d not built (1..8)", world);
+      return GF_ERR_INVALID;
+  }
+#undef GF_PEER_CASE
+  return check_launch("peer_max_i64_kernel");
 }
 
 int gf_peer_reduce_adam(int world, int64_t n, int64_t lo, int64_t hi, void* const* grad_ptrs, float* param,

@@ -153,7 +153,7 @@ class GFNeRFEngine:
             # different tables forever)
             self.sync.broadcast_([self.enc.feat_pool_.data, self.enc.prim_pool_, self.enc.bias_pool_, self.mlp]
                                  + ([self.emb] if self.emb is not None else []))
-            sampler.vote_reduce = self.sync.max_
+            sampler.vote_reduce = self._peer_vote_max if self.peer is not None else self.sync.max_
         self.enc.shadow(force=True)
         self._ws = {}
         self.step_count = 0
@@ -234,9 +234,12 @@ class GFNeRFEngine:
         import torch.distributed as dist
         ok = torch.ones(1, dtype=torch.int32, device=self.device)
         try:
+            # votes: two alternating buffers of 4 int64 per octree node (3 adders / marks + the visit count), with room
+            # for the tree to grow through the subdivision milestones
+            self._vote_cap = 4 * max(16 * int(self.sampler.n_nodes), 1 << 17)
             peer = PeerExchange(group, self.device, {
                 "table_grad": 4 * self.opt_table.param.numel(), "shadow": 2 * self.enc.feat_pool_.numel(),
-                "small": 4 * self._small.flat.numel()})
+                "small": 4 * self._small.flat.numel(), "votes": 2 * 8 * self._vote_cap})
         except RuntimeError as e:
             peer, ok[0] = None, 0
             import sys
@@ -288,6 +291,31 @@ class GFNeRFEngine:
             self.opt_table.grad[:self.opt_table.n_active].zero_()
             self._small_grads.zero_()
         self.enc.mark_shadow_fresh()
+
+    def _peer_vote_max(self, buffers):
+        """all-reduce(MAX) of the octree votes over peer memory, in stream order on the current (sampling-ahead) stream:
+        stage this rank's votes in one of two alternating peer buffers, one cross-GPU barrier, then every rank takes the
+        maximum over all ranks' buffers with peer loads (csrc/peer.cu gf_peer_max_i64).  Two buffers, so the barrier of
+        step k + 1 is what guarantees that every peer has finished reading the buffer this rank rewrites at k + 2."""
+        total = sum(int(b.numel()) for b in buffers)
+        if total > self._vote_cap:          # the octree outgrew the buffers (same decision on every rank): NCCL
+            return self.sync.max_(buffers)
+        L, peer = _lib.lib(), self.peer
+        peer.vote_epoch += 1
+        slot = peer.vote_epoch & 1
+        stage = peer.tensor("votes", torch.int64, (2, self._vote_cap))[slot]
+        off = 0
+        for b in buffers:
+            n = int(b.numel())
+            stage[off:off + n].copy_(b.view(-1))
+            off += n
+        peer.barrier("vote", peer.vote_epoch)
+        off = 0
+        for b in buffers:
+            n = int(b.numel())
+            _lib.check(L.gf_peer_max_i64(self.world, n, peer.ptrs("votes", 8 * (slot * self._vote_cap + off)),
+                                         _lib.ptr(b), _lib.cur_stream()), "gf_peer_max_i64")
+            off += n
 
     def sync_master_params(self):
         """Peer exchange only: every rank keeps the fp32 master copy (and Adam moments) of ITS rows of the table up to

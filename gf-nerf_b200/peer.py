@@ -46,6 +46,7 @@ class PeerExchange:
         sizes = dict(sizes)
         sizes["__flags_in"] = 256
         sizes["__flags_out"] = 256
+        sizes["__flags_vote"] = 256    # the octree-vote barrier runs on another stream: its own flags and epochs
         with torch.cuda.device(self.device):
             handles = {}
             for name, nbytes in sizes.items():
@@ -72,6 +73,7 @@ class PeerExchange:
                     table.append(p.value)
                 self._tables[name] = table
         self.epoch = 0
+        self.vote_epoch = 0
         self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.any_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         dist.barrier(group=group)    # every rank has mapped every buffer before anyone uses them

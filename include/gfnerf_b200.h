@@ -405,6 +405,12 @@ int gf_peer_close(void* dptr);
  * the OR over all ranks.  A wait longer than ~2 s sets *d_error (int32, may be NULL) instead of hanging. */
 int gf_peer_barrier(int world, int rank, uint32_t epoch, void* const* flag_ptrs, const int32_t* d_local_flag,
                     int32_t* d_any_flag, int32_t* d_error, void* stream);
+/* dst[i] = max over ranks r of src_ptrs[r][i], int64 [n]: all-reduce(MAX) of the octree votes (the adders / marks of
+ * MarkVistNodeKernel and the visit counts, PersSampler_cuda.cu:518-574) as peer loads, between gf_sampler_vote and
+ * gf_sampler_apply_votes.  The caller orders it behind a gf_peer_barrier ("every rank's votes are complete") and
+ * alternates between two vote buffers per rank, so no second barrier is needed. */
+int gf_peer_max_i64(int world, int64_t n, void* const* src_ptrs, int64_t* dst, void* stream);
+
 /* Reduce-scatter + Adam + all-gather of one flat fp32 parameter array of n elements in ONE kernel: for the elements
  * [lo, hi) this rank owns (multiples of 4), sum grad_ptrs[0..world) (host array of device pointers to every rank's
  * gradient array, summed in rank order -- bit-identical whoever computes it), divide by grad_div, apply torch.optim.Adam

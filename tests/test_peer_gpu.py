@@ -78,6 +78,20 @@ def _worker_exchange(rank, world, port, out):
                 assert torch.equal(sh, rsh), f"rank {rank} step {it}: gathered fp16 table differs"
             assert torch.equal(param[lo:hi], rp[lo:hi]) and torch.equal(m[lo:hi], rm[lo:hi]) and torch.equal(v[lo:hi], rv[lo:hi])
             assert int(d_step.item()) == int(rstep.item()) == (it + 1 if it == 0 else it)
+        # all-reduce(MAX) of int64 votes over peer loads (gf_peer_max_i64), two alternating buffers, one barrier
+        nv = 5001
+        pv = PeerExchange(dist.group.WORLD, dev, {"votes": 2 * 8 * nv})
+        for it in range(3):
+            pv.vote_epoch += 1
+            slot = pv.vote_epoch & 1
+            mine = torch.from_numpy(np.random.RandomState(100 * it + rank).randint(-5, 1 << 40, size=nv)).to(dev)
+            pv.tensor("votes", torch.int64, (2, nv))[slot].copy_(mine)
+            pv.barrier("vote", pv.vote_epoch)
+            got = torch.empty(nv, dtype=torch.int64, device=dev)
+            _lib.check(L.gf_peer_max_i64(world, nv, pv.ptrs("votes", 8 * slot * nv), _lib.ptr(got), st), "gf_peer_max_i64")
+            want = np.max([np.random.RandomState(100 * it + r).randint(-5, 1 << 40, size=nv) for r in range(world)], axis=0)
+            assert np.array_equal(got.cpu().numpy(), want)
+        pv.check()
         peer.check()
         dist.barrier()
         out.put((rank, "ok"))
