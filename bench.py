@@ -101,12 +101,12 @@ def oracle_step(orc, rig, state, batch):
     offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     feat = orc.hash_forward(state["table"], state["prim"], state["bias"], pts01, anchors, state["scales"])
     ray_emb = state["emb"][cam]
-    sigma, rgb = orc.mlp_forward(state["mlp"], feat, ray_id, d, ray_emb, 64)
+    sigma, rgb = orc.mlp_forward(state["mlp"], feat, ray_id, d, ray_emb, state["hidden"])
     delta, t = smp["dists"][m], smp["ts"][m]
     comp = orc.composite_forward(offsets, sigma, delta, rgb, t)
     loss, g_rgb = orc.charbonnier(comp["rgb"], target)
     d_sigma, d_rgb = orc.composite_backward(offsets, sigma, delta, rgb, g_rgb)
-    d_feat, d_params, d_emb = orc.mlp_backward(state["mlp"], feat, ray_id, d, ray_emb, d_sigma, d_rgb, 64)
+    d_feat, d_params, d_emb = orc.mlp_backward(state["mlp"], feat, ray_id, d, ray_emb, d_sigma, d_rgb, state["hidden"])
     g_table = orc.hash_backward(state["table"].shape[0] // 16, state["prim"], state["bias"], pts01, anchors, d_feat,
                                 state["scales"])
     state["t"] += 1
@@ -115,24 +115,25 @@ def oracle_step(orc, rig, state, batch):
     return loss, int(counts.sum())
 
 
-def oracle_state(rig, log2T):
+def oracle_state(rig, log2T, hidden=64):
     from oracle import oracle as orc
     from tests.helpers import fast_primes
     rng = np.random.RandomState(0)
     n_vol = rig["pers_trans"].size // 576
     n = 16 * (1 << log2T) * 2
-    bound = 1 / np.sqrt(np.array([32] * (64 * 33) + [64] * (16 * 65) + [63] * (64 * 64) + [64] * (64 * 65) + [64] * (3 * 65)))
+    H = hidden      # torch nn.Linear default init bounds, in the blob order of include/gfnerf_b200.h
+    bound = 1 / np.sqrt(np.array([32] * (H * 33) + [H] * (16 * (H + 1)) + [63] * (H * 64) + [H] * (H * (H + 1)) + [H] * (3 * (H + 1))))
     return dict(rng=rng, fineness=1.0, table=rng.uniform(-1e-2, 1e-2, size=(n // 2, 2)).astype(np.float32),
                 prim=fast_primes(16 * n_vol * 3, 7).reshape(16, n_vol, 3), bias=np.zeros((16 * n_vol, 3), np.float32),
-                scales=orc.hash_level_scales(), mlp=(rng.uniform(-1, 1, size=11603) * bound).astype(np.float32),
+                scales=orc.hash_level_scales(), mlp=(rng.uniform(-1, 1, size=bound.size) * bound).astype(np.float32), hidden=H,
                 emb=rng.normal(size=(rig["c2w"].shape[0], 32)).astype(np.float32),
                 m=np.zeros(n, np.float32), v=np.zeros(n, np.float32), t=0)
 
 
-def time_oracle(rays, steps, warmup, log2T=LOG2T):
+def time_oracle(rays, steps, warmup, log2T=LOG2T, hidden=64):
     from oracle import oracle as orc
     rig = load_rig()
-    state = oracle_state(rig, log2T)
+    state = oracle_state(rig, log2T, hidden)
     batches = make_batches(rig, rays, max(2, min(4, steps)), seed=99)
     orc.set_num_threads(os.cpu_count() or 1)
     for w in range(warmup):
@@ -167,18 +168,39 @@ def reference_arm(args):
     if rank != 0:
         return
     rays = 256
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
-    value, ms, cores, v = time_oracle(rays, steps, warmup)
-    sample = f"{rays} rays/step ({v:.0f} samples), {steps} steps after {warmup} warm-ups, same rig / table / MLP shapes"
+    # K and W as asked, bounded so that the run ends within a few minutes (a 256-ray step takes ~0.7 s on 16 cores)
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 5))
+    value, ms, cores, v = time_oracle(rays, steps, warmup, hidden=args.hidden)
+    sample = (f"{rays} rays/step ({v:.0f} samples) of the same workload (same rig / octree / table / MLP shapes), "
+              f"{steps} steps after {warmup} warm-ups, all host threads")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "rays_per_step": rays, "log2T": LOG2T},
+        "config": static_config("global", args.hidden, world, LOG2T),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cpu_reference_path": time_reference_cpu_path(),
     }))
+
+
+def static_config(workload, hidden, world, log2t):
+    """The workload both arms are measured on -- identical in the CUDA arm's and the reference arm's JSON line, so the
+    driver's config comparison sees one configuration; what a RUN did (sample counts, exchange path, ...) goes under
+    `run`, the bounded sample of the CPU arm under `cpu_baseline.sample`."""
+    return {"workload": workload_name(hidden) if workload == "global" else
+            "GF-NeRF focal stage: frozen global Hash3DAnchored + MLPs, one zero-initialised residual "
+            f"sub-encoder per GPU (log2T={log2t}), {RAYS_PER_GPU} rays/GPU/step, no gradient exchange",
+            "rays_per_gpu": RAYS_PER_GPU, "log2T": log2t, "hidden": hidden,
+            "slots_per_step_per_gpu": RAYS_PER_GPU * 1024,
+            "l2_policy": "inputs larger than L2 (0.3 GB table+optimizer state, ~1 GB sample buffers, "
+                         f"{N_BATCHES} ray batches cycled)",
+            "level_addressing": "reference (level l = table rows [l*T/2, l*T/2 + T): windows overlap by half, "
+                                "8.5*T of the 16*T rows reachable; DESIGN.md section 5)",
+            "march_fineness": "1.0 (the steady state of the schedule: PersSampler.cpp:958-967 decays 16 -> 1 "
+                              "over the first 10 k of 130 k iterations; the bench pins the other 120 k)",
+            "parallelism": f"dp{world}" if world > 1 else "single GPU"}
 
 
 def workload_name(hidden=64):
@@ -503,7 +525,7 @@ def main():
     cpu_baseline = cpu_reference_path = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_reference_path = time_reference_cpu_path()
-        cv, cms, cores, cvs = time_oracle(256, 3, 1)
+        cv, cms, cores, cvs = time_oracle(256, 3, 1, hidden=args.hidden)
         cpu_baseline = {"value": cv, "unit": "rays/s", "cores": cores, "kind": "port",
                         "sample": f"256 rays/step ({cvs:.0f} samples), 3 steps after 1 warm-up, same rig / table / MLP shapes"}
 
@@ -514,24 +536,15 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 tables + f16 tensor-core MLP, f32 accumulate / geometry / optimizer",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.hidden) if args.workload == "global" else
-                       "GF-NeRF focal stage: frozen global Hash3DAnchored + MLPs, one zero-initialised residual "
-                       f"sub-encoder per GPU (log2T={log2t}), {RAYS_PER_GPU} rays/GPU/step, no gradient exchange",
-                       "rays_per_gpu": RAYS_PER_GPU, "log2T": log2t, "hidden": args.hidden,
-                       "samples_per_step_per_gpu": round(v_mean), "slots_per_step_per_gpu": RAYS_PER_GPU * 1024,
-                       "l2_policy": "inputs larger than L2 (0.3 GB table+optimizer state, ~1 GB sample buffers, "
-                                    f"{N_BATCHES} ray batches cycled)",
-                       "level_addressing": "reference (level l = table rows [l*T/2, l*T/2 + T): windows overlap by half, "
-                                           "8.5*T of the 16*T rows reachable; DESIGN.md section 5)",
-                       "sample_ahead": bool(ahead),
-                       "march_fineness": "1.0 (the steady state of the schedule: PersSampler.cpp:958-967 decays 16 -> 1 "
-                                         "over the first 10 k of 130 k iterations; the bench pins the other 120 k)",
-                       "exchange": ("none (single GPU)" if world == 1 else
-                                    "peer memory over NVLink: one kernel per rank = reduce-scatter (fp32 gradient rows, "
-                                    "P2P loads) + Adam on the owned 1/N of the rows + all-gather (fp16 gather table, P2P "
-                                    "stores), between two one-CTA cross-GPU barriers; octree votes: NCCL MAX all-reduce"
-                                    if eng.peer is not None else "NCCL all-reduce of the fp32 table gradient + replicated Adam"),
-                       "parallelism": f"dp{world}" if world > 1 else "single GPU"},
+            "config": static_config(args.workload, args.hidden, world, log2t),
+            "run": {"samples_per_step_per_gpu": round(v_mean), "sample_ahead": bool(ahead),
+                    "exchange": ("none (single GPU)" if world == 1 else "none (focal stage: private sub-encoders)"
+                                 if args.workload == "focal" else
+                                 "peer memory over NVLink: one kernel per rank = reduce-scatter (fp32 gradient rows, "
+                                 "P2P loads) + Adam on the owned 1/N of the rows + all-gather (fp16 gather table, P2P "
+                                 "stores), between two one-CTA cross-GPU barriers; octree votes: barrier + MAX over peer "
+                                 "loads" if eng.peer is not None else
+                                 "NCCL all-reduce of the fp32 table gradient + replicated Adam; octree votes: NCCL MAX")},
             "e2e": {"value": e2e_value, "unit": "rays/s",
                     "h2d_bytes_per_step": int(sum(a.numel() * a.element_size() for a in pinned[0])) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
