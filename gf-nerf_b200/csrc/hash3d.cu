@@ -50,9 +50,15 @@ __global__ void cast_table_tail_kernel(const float* __restrict__ in, __half* __r
 }
 
 constexpr int kHashBlock = 256;
-
-template <bool POW2, typename AnchorT, bool OUT16, bool OUT32>
-__global__ void __launch_bounds__(kHashBlock)
+// Two register / scheduling variants of the forward gather (tools/hash_variants.py, r02u, bench samples):
+//   PREFETCH = false  48 registers, 5 CTAs per SM: the most warps in flight -- best when the table does not fit the
+//                     L2 and the gather waits on HBM (log2T = 23: 1.79 ms against 2.15 for the other one);
+//   PREFETCH = true   the 32 gathers of a four-level group are all issued before the first is consumed, 79 registers,
+//                     3 CTAs per SM -- best while the reachable rows fit the L2 and the kernel is bound by the L1 -> L2
+//                     request path, not by DRAM latency (log2T = 19: 0.949 ms against 0.985; log2T = 21, 71 MB of
+//                     rows: 0.970 against 1.338).
+template <bool POW2, typename AnchorT, bool OUT16, bool OUT32, bool PREFETCH>
+__global__ void __launch_bounds__(kHashBlock, PREFETCH ? 3 : 5)
 hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volumes, uint32_t local_size,
                 const __half2* __restrict__ feat, const int32_t* __restrict__ prim_pool,
                 const float* __restrict__ bias_pool, const float* __restrict__ scales,
@@ -72,19 +78,20 @@ hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
 #pragma unroll 1
     for (int q = 0; q < GF_N_LEVELS / 4; q++) {
       uint32_t packed[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int l = 4 * q + j;
+      // this level's cell and the fp16 table rows of its eight corners
+      auto gather = [&](int l, Cell& c, __half2 (&f)[8]) {
         const int tr = (l * n_volumes + vol) * 3;
-        const Cell c = cell_of(x, y, z, s_scale[l], bias_pool ? bias_pool + tr : nullptr);
+        c = cell_of(x, y, z, s_scale[l], bias_pool ? bias_pool + tr : nullptr);
         const uint32_t pa = (uint32_t)__ldg(prim_pool + tr), pb = (uint32_t)__ldg(prim_pool + tr + 1),
                        pc = (uint32_t)__ldg(prim_pool + tr + 2);
         uint32_t pos[8];
         corners<POW2>(c, pa, pb, pc, local_size, pos);
         const __half2* tab = feat + level_base_row(l, local_size);
-        __half2 f[8];
 #pragma unroll
         for (int d = 0; d < 8; d++) f[d] = __ldg(tab + pos[d]);
+      };
+      // trilinear blend in fp32, rounded to fp16 (:58-77)
+      auto blend = [](const Cell& c, const __half2 (&f)[8]) {
         float w[8];
         weights(c, w);
         // nvcc's contraction of w000*f000 + w001*f001 + ... (:73-77)
@@ -97,8 +104,24 @@ hash_fwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
           t0 = __fmaf_rn(w[d], __low2float(f[d]), t0);
           t1 = __fmaf_rn(w[d], __high2float(f[d]), t1);
         }
-        __half2 o = __floats2half2_rn(t0, t1);
-        packed[j] = *reinterpret_cast<uint32_t*>(&o);
+        const __half2 o = __floats2half2_rn(t0, t1);
+        return *reinterpret_cast<const uint32_t*>(&o);
+      };
+      if (PREFETCH) {   // all 32 gathers of the group in flight before the first blend
+        Cell cc[4];
+        __half2 ff[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) gather(4 * q + j, cc[j], ff[j]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) packed[j] = blend(cc[j], ff[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          Cell c;
+          __half2 f[8];
+          gather(4 * q + j, c, f);
+          packed[j] = blend(c, f);
+        }
       }
       if (base16) {  // focal stage: residual on top of the global encoder's features (nerfacto_field.py:477-489)
         const uint4 b = __ldg(base16 + i * 4 + q);
@@ -243,10 +266,19 @@ static int hash_forward_impl(int64_t n, const int32_t* d_n_ptr, int32_t n_volume
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stride_grid(n, kHashBlock, 8, 4);
   const bool p2 = is_pow2(local_size);
-#define GF_FWD(P2, AT, O16, O32)                                                                              \
-  hash_fwd_kernel<P2, AT, O16, O32><<<grid, kHashBlock, 0, st>>>(                                             \
+  // the rows the levels can reach (8.5 * local_size, 4 bytes each) against the 126 MB L2: which variant (see the kernel)
+  // GF_HASH_FWD_VARIANT = 0 / 1 forces one (A/B measurements, tools/hash_variants.py)
+  static const int forced = [] { const char* e = getenv("GF_HASH_FWD_VARIANT"); return e ? atoi(e) : -1; }();
+  const bool l2_resident = forced >= 0 ? forced != 0 : (int64_t)local_size * 34 <= (int64_t)100 << 20;
+#define GF_FWD_V(P2, AT, O16, O32, PF)                                                                        \
+  hash_fwd_kernel<P2, AT, O16, O32, PF><<<grid, kHashBlock, 0, st>>>(                                         \
       n, d_n_ptr, n_volumes, (uint32_t)local_size, (const __half2*)feat_f16, prim_pool, bias_pool,            \
       level_scales, pts, (const AT*)anchors, (uint4*)out_f16, (float4*)out_f32, (const uint4*)base_f16)
+#define GF_FWD(P2, AT, O16, O32)                    \
+  do {                                              \
+    if (l2_resident) GF_FWD_V(P2, AT, O16, O32, true); \
+    else GF_FWD_V(P2, AT, O16, O32, false);         \
+  } while (0)
 #define GF_FWD_O(P2, AT)                                     \
   do {                                                       \
     if (out_f16 && out_f32) GF_FWD(P2, AT, true, true);      \
@@ -260,6 +292,7 @@ static int hash_forward_impl(int64_t n, const int32_t* d_n_ptr, int32_t n_volume
   }
 #undef GF_FWD_O
 #undef GF_FWD
+#undef GF_FWD_V
   return check_launch("hash_fwd_kernel");
 }
 

@@ -302,3 +302,83 @@ def test_sampling_one_batch_ahead_is_identical():
     eng.train_step(o, d, tgt, cam, next_rays=batches[1][:2])
     out = eng.train_step(batches[2][0], batches[2][1], batches[2][3], batches[2][2])
     assert torch.isfinite(out.loss).all()
+
+
+def _oracle_forward(eng, rig, o, d, cam, res_table=None):
+    """sampler -> hash (+ residual encoder) -> MLPs -> composite by the oracle, eval-mode march (noise 1)"""
+    R = o.shape[0]
+    smp = orc.sampler_get_samples(o, d, np.ones(1024 + R + 10, np.float32), rig["tree_nodes"], rig["pers_trans"])
+    counts = smp["counts"]
+    m = counts[:, None] > np.arange(1024)[None]
+    pts01 = ((smp["warp_pts"][m] + np.float32(1.5)) * (np.float32(1.0) / np.float32(3.0))).astype(np.float32)
+    anchors = smp["anchors"][m][:, 0]
+    ray_id = np.repeat(np.arange(R), counts).astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    prim, bias = eng.enc.prim_pool_.cpu().numpy(), eng.enc.bias_pool_.cpu().numpy()
+    feat = orc.hash_forward(eng.enc.feat_pool_.detach().cpu().numpy(), prim, bias, pts01, anchors, eng.enc.level_scales_host)
+    if res_table is not None:     # focal stage: residual at the hash-feature level, summed in fp16 (nerfacto_field.py:477-489)
+        rprim, rbias = eng.res.prim_pool_.cpu().numpy(), eng.res.bias_pool_.cpu().numpy()
+        rfeat = orc.hash_forward(res_table, rprim, rbias, pts01, anchors, eng.res.level_scales_host)
+        feat = (feat.astype(np.float16) + rfeat.astype(np.float16)).astype(np.float32)
+    ray_emb = eng.emb.cpu().numpy()[cam]
+    sigma, rgb = orc.mlp_forward(eng.mlp.cpu().numpy(), feat, ray_id, d, ray_emb, eng.hidden)
+    comp = orc.composite_forward(offsets, sigma, smp["dists"][m], rgb, smp["ts"][m])
+    return dict(counts=counts, feat=feat, sigma=sigma, rgb=rgb, comp=comp, pts01=pts01, anchors=anchors, ray_id=ray_id,
+                offsets=offsets, smp=smp, m=m)
+
+
+def test_render_at_config5_size_matches_oracle():
+    """BASELINE.json configs[4] at its table size (log2T = 23, the bench rig): value-level parity of the forward-only
+    render on as many rays of a frame as the oracle does in a second."""
+    from gfnerf_b200.persoctree import frame_rays
+    rig = load_rig("rig20")
+    eng = make_engine(rig, log2T=23)
+    torch.manual_seed(7)
+    eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
+    eng.enc.shadow(force=True)
+    o, d = frame_rays(rig["c2w"][10], rig["intri"][0], 1920, 1080)
+    pick = np.random.RandomState(1).choice(o.shape[0], 192, replace=False)
+    o, d = np.ascontiguousarray(o[pick]), np.ascontiguousarray(d[pick])
+    cam = np.full(192, 10, np.int64)
+    out = eng.render(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(cam).cuda())
+    ref = _oracle_forward(eng, rig, o, d, cam)
+    assert int(out.n_samples.item()) == ref["counts"].sum() > 0
+    np.testing.assert_allclose(out.rgb.cpu().numpy(), np.clip(ref["comp"]["rgb"], 0, 1), rtol=1e-2, atol=2e-3)
+    np.testing.assert_allclose(out.accumulation.cpu().numpy(), ref["comp"]["acc"], rtol=1e-2, atol=2e-3)
+    np.testing.assert_allclose(out.depth.cpu().numpy(), ref["comp"]["depth"], rtol=1e-2, atol=2e-3)
+
+
+def test_focal_stage_at_config4_size_matches_oracle():
+    """BASELINE.json configs[3] at its table size: frozen global encoder (log2T = 19) + a private residual sub-encoder
+    with log2T = 21; forward values and the residual table's gradient against the oracle chain on 192 rays."""
+    from gfnerf_b200.persoctree import rig_rays
+    rig = load_rig("rig20")
+    eng = make_engine(rig, log2T=19)
+    torch.manual_seed(8)
+    eng.enc.feat_pool_.data.uniform_(-0.5, 0.5)
+    eng.enc.shadow(force=True)
+    eng.start_block_stage(log2_table_size=21, seed=5)
+    eng.res.feat_pool_.data.uniform_(-0.05, 0.05)        # a residual that has been trained on: non-zero
+    eng.res.shadow(force=True)
+    res0 = eng.res.feat_pool_.detach().cpu().numpy().copy()
+    R = 192
+    o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=9)
+    target = np.random.RandomState(2).rand(R, 3).astype(np.float32)
+    out = eng.train_step(*(torch.from_numpy(a).cuda() for a in (o, d, target, cam)), optimizer_step=False,
+                         update_octree=False)
+    ref = _oracle_forward(eng, rig, o, d, cam, res_table=res0)
+    assert int(out.n_samples.item()) == ref["counts"].sum()
+    np.testing.assert_allclose(out.rgb.cpu().numpy(), ref["comp"]["rgb"], rtol=1e-2, atol=2e-3)
+    loss, g_rgb = orc.charbonnier(ref["comp"]["rgb"], target)
+    assert abs(float(out.loss) - loss) < 1e-2 * loss
+    d_sigma, d_rgb = orc.composite_backward(ref["offsets"], ref["sigma"], ref["smp"]["dists"][ref["m"]], ref["rgb"], g_rgb)
+    d_feat, _, _ = orc.mlp_backward(eng.mlp.cpu().numpy(), ref["feat"], ref["ray_id"], d, eng.emb.cpu().numpy()[cam],
+                                    d_sigma, d_rgb, eng.hidden)
+    g_res = orc.hash_backward(eng.res.local_size_, eng.res.prim_pool_.cpu().numpy(), eng.res.bias_pool_.cpu().numpy(),
+                              ref["pts01"], ref["anchors"], d_feat, eng.res.level_scales_host)
+    got = eng.opt_res.unscaled_grad().view(-1, 2).double().cpu().numpy()
+    err = np.abs(got - g_res).max() / np.abs(g_res).max()
+    l2 = np.linalg.norm(got - g_res) / np.linalg.norm(g_res)
+    print("residual-table gradient (log2T = 21): max err / max", err, "rel L2", l2)
+    assert err < 1e-2 and l2 < 1e-2
+    assert not eng.opt_table.grad.any() and not eng.opt_mlp.grad.any()       # the global encoder and the MLPs are frozen
