@@ -437,7 +437,10 @@ def main():
         return ms, launches
 
     clocks = ClockSampler(local)
-    clocks.start()
+    if not os.environ.get("GF_NO_CLOCKS"):      # (A/B: does polling nvidia-smi perturb the timed region?)
+        clocks.start()
+    if os.environ.get("GF_MAIN_PRIO"):      # A/B: run the step on a non-default stream of the given priority
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=int(os.environ["GF_MAIN_PRIO"])))
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
     clocks.stop_flag = True
     ms_step = ms_total / args.steps

@@ -158,9 +158,16 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
   }
   __shared__ float s_scale[GF_N_LEVELS];
   __shared__ __align__(16) float s_stage[(kHashBlock / 32) * kScatterWarpWords];
+  // GRAD_F16: the warp's 32 gradient rows (64 bytes each, 2 KB contiguous) are fetched with four coalesced 16-byte
+  // loads per lane and transposed through shared memory (row stride 17 words: the per-level reads are conflict-free).
+  // Reading element (row, level) straight from global memory costs one 32-lane load at a 64-byte stride per level:
+  // 16 L1 wavefronts x 16 levels per warp, 14 % of the LSU data pipe that bounds this kernel in steady state (r02x)
+  constexpr int kGradRowWords = GF_N_LEVELS + 1;
+  __shared__ uint32_t s_grad[GRAD_F16 ? (kHashBlock / 32) * 32 * kGradRowWords : 1];
   if (threadIdx.x < GF_N_LEVELS) s_scale[threadIdx.x] = __ldg(scales + threadIdx.x);
   __syncthreads();
   const int lane = lane_id();
+  uint32_t* sg = s_grad + (GRAD_F16 ? (threadIdx.x >> 5) * 32 * kGradRowWords : 0);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   // warp-uniform trip count: every lane of a warp runs the same iterations
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
@@ -174,14 +181,29 @@ hash_bwd_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, int32_t n_volume
       z = __ldg(pts + 3 * i + 2);
       vol = (int)anchors[i];
     }
+    if (GRAD_F16) {
+      __syncwarp();  // the previous batch's readers are done with sg
+      const uint4* src = reinterpret_cast<const uint4*>(grad_in_v) + base * (GF_N_LEVELS / 4);
+#pragma unroll
+      for (int k = 0; k < GF_N_LEVELS / 4; k++) {
+        const int c = lane + 32 * k, row = c >> 2, part = c & 3;
+        const uint4 v = base + row < n ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+        uint32_t* dst = sg + row * kGradRowWords + part * 4;
+        dst[0] = v.x;
+        dst[1] = v.y;
+        dst[2] = v.z;
+        dst[3] = v.w;
+      }
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int l = level_begin; l < level_end; l++) {
       // this level's two gradients, quantised like the reference: fp16(g*128)  (:209)
       __half2 gh = __float2half2_rn(0.f);
-      if (valid) {
-        if (GRAD_F16) {
-          gh = __ldg(reinterpret_cast<const __half2*>(grad_in_v) + i * GF_N_LEVELS + l);
-        } else {
+      if (GRAD_F16) {
+        gh = *reinterpret_cast<const __half2*>(sg + lane * kGradRowWords + l);   // (rows past the end were zero-filled)
+      } else if (valid) {
+        {
           const float2 v = __ldg(reinterpret_cast<const float2*>(grad_in_v) + i * GF_N_LEVELS + l);
           gh = __floats2half2_rn(__fmul_rn(v.x, GF_GRAD_SCALE), __fmul_rn(v.y, GF_GRAD_SCALE));
         }
@@ -334,6 +356,7 @@ int gf_hash_backward_levels(int64_t n, const int32_t* d_n_ptr, int32_t n_volumes
   if (level_begin == level_end) return GF_OK;
   if (n == 0) return GF_OK;
   GF_REQUIRE(prim_pool && level_scales && pts && anchors && grad_in && grad_table, "gf_hash_backward: null pointer");
+  GF_REQUIRE((reinterpret_cast<uintptr_t>(grad_in) & 15) == 0, "gf_hash_backward: grad_in must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stride_grid(n, kHashBlock, 4, 4);
   const bool p2 = is_pow2(local_size);

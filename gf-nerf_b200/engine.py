@@ -438,7 +438,8 @@ class GFNeRFEngine:
         is a latency-bound kernel that leaves most issue slots of an SM idle; the backward kernels of the current
         batch run underneath it.  Results are identical to sampling at the start of the next step."""
         if not hasattr(self, "_pre_stream"):
-            self._pre_stream = torch.cuda.Stream(device=self.device)
+            # GF_PRESAMPLE_PRIO=-1: the side stream's CTAs are scheduled ahead of the main stream's (A/B knob)
+            self._pre_stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("GF_PRESAMPLE_PRIO", "0")))
             self._pre = None
             self._cs_slot = 0
         cur = torch.cuda.current_stream(self.device)
