@@ -77,9 +77,11 @@ __device__ __forceinline__ void weights(const Cell& c, float (&w)[8]) {
 }
 
 // ---- backward scatter ---------------------------------------------------------------------------------------
-// Shared-memory staging of the run reduction: one row per lane = 8 x (float2 contribution) + 8 x (u32 table row),
-// padded to 26 words so that the four lane quarters of a column read fall into disjoint bank halves.
-constexpr int kScatterRowWords = 26;
+// Shared-memory staging of the run reduction: one row per lane = 8 x {half2 contribution, u32 table row} (the
+// contributions ARE fp16 values, :148-151), padded to 18 words: the 8-byte row writes of a half-warp and the 8-byte
+// column reads of its two lane quarters each cover the 32 banks exactly once.  (r02y: 12 + 24 shared-memory
+// wavefronts per warp and level with float2 contributions and separate rows -> 16 + 16.)
+constexpr int kScatterRowWords = 18;
 constexpr int kScatterWarpWords = 32 * kScatterRowWords;
 
 // red.global.add.v2.f32 of (s0, s1) * out_scale to tab[row] unless both are zero or `mask` (0 / ~0) is off: one
@@ -173,26 +175,21 @@ __device__ __forceinline__ void hash_scatter_level(int l, float x, float y, floa
     maxrun = (int)__reduce_max_sync(0xffffffffu, head ? (unsigned)(end - lane) : 0u);
   }
   if (maxrun > aggregate) {  // warp-uniform; aggregate = longest run the shuffle path still takes (4)
-    float* row = s_warp + lane * kScatterRowWords;
+    uint2* row = reinterpret_cast<uint2*>(s_warp + lane * kScatterRowWords);
 #pragma unroll
-    for (int d = 0; d < 8; d++) {
-      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&cq[d]));
-      *reinterpret_cast<float2*>(row + 2 * d) = v;
-    }
-#pragma unroll
-    for (int d = 0; d < 8; d += 2) *reinterpret_cast<uint2*>(row + 16 + d) = make_uint2(pos[d], pos[d + 1]);
+    for (int d = 0; d < 8; d++) row[d] = make_uint2(cq[d], pos[d]);
     __syncwarp();
     const int d = lane & 7, j0 = lane & 24;
     const uint32_t stops = (heads >> 1) | 0x80808080u;  // bit j: lane j is the last of its run or of its quarter
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float* rj = s_warp + (j0 + k) * kScatterRowWords;
-      const float2 v = *reinterpret_cast<const float2*>(rj + 2 * d);
+      const uint2 e = reinterpret_cast<const uint2*>(s_warp + (j0 + k) * kScatterRowWords)[d];
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&e.x));
       a0 += v.x;
       a1 += v.y;
       if ((stops >> (j0 + k)) & 1u) {
-        red_add_f32x2<UNSCALE>(tab, __float_as_uint(rj[16 + d]), a0, a1, 0xffffffffu);
+        red_add_f32x2<UNSCALE>(tab, e.y, a0, a1, 0xffffffffu);
         a0 = a1 = 0.f;
       }
     }
