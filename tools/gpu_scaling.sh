@@ -9,7 +9,7 @@ mkdir -p $OUT
 run() {  # name, nproc, extra args...
   local name=$1 n=$2; shift 2
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
-      --master-port $((29500 + RANDOM % 400)) bench.py --gpus $n --steps 200 --warmup 10 "$@" \
+      --master-port $((29500 + RANDOM % 400)) bench.py --gpus $n --steps 200 --warmup 10 --no-cpu-baseline --no-operator-api "$@" \
       > $OUT/${TAG}_${name}.json 2> $OUT/${TAG}_${name}.err
   echo "$name rc=$?"
   python - <<PY
@@ -25,7 +25,8 @@ PY
 run bench_n8 8
 run bench_n4 4
 run bench_n2 2
-GF_PEER_EXCHANGE=0 run bench_n8_nccl 8
+run bench_n1 1
+[ "${NCCL_TOO:-0}" = 1 ] && GF_PEER_EXCHANGE=0 run bench_n8_nccl 8
 run bench_focal_n8 8 --workload focal
 timeout 300 python -m pytest tests/test_peer_gpu.py -x -q -p no:cacheprovider -s > $OUT/${TAG}_peer_tests.log 2>&1
 echo "peer tests rc=$?"; tail -6 $OUT/${TAG}_peer_tests.log
