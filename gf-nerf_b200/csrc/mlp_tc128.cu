@@ -333,12 +333,18 @@ mlp_tc128_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __
       mk1 = __ldg(relu_masks + 2 * (2 * row + hf) + 1);
     }
     const float* rb = ray_bias + (int64_t)(valid ? ray : 0) * kH + 64 * hf;
+    // real loads instead of prefetch hints (see mlp_tc.cu): two 4-byte loads pull the thread's two 128-byte bias lines
+    // into L1, and the four upstream gradients of the row go to registers now (hf == 0 consumes them)
+    float up[4] = {0.f, 0.f, 0.f, 0.f};
     if (valid) {
-      prefetch_l1(rb);
-      prefetch_l1(rb + 32);
-      if (BWD) {
-        if (hf == 0) prefetch_l1(d_rgb + 3 * row);
-        else prefetch_l1(d_sigma + row);
+      float touch;
+      asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(touch) : "l"(rb));
+      asm volatile("ld.global.nc.f32 %0, [%1];\n" : "=f"(touch) : "l"(rb + 32));
+      if (BWD && hf == 0) {
+        up[0] = __ldg(d_rgb + 3 * row);
+        up[1] = __ldg(d_rgb + 3 * row + 1);
+        up[2] = __ldg(d_rgb + 3 * row + 2);
+        up[3] = __ldg(d_sigma + row);
       }
     }
     const int64_t nrow = row + (int64_t)gridDim.x * kTile;
@@ -501,7 +507,7 @@ mlp_tc128_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           const float sg = sigmoidf_(__uint_as_float(v[c]) + s_bias[kBiasB4 + c]);
-          go[c] = __ldg(d_rgb + 3 * row + c) * gscale * sg * (1.f - sg);
+          go[c] = up[c] * gscale * sg * (1.f - sg);
         }
       }
       a[0] = pack_h2(go[0], go[1]);
@@ -587,7 +593,7 @@ mlp_tc128_kernel(int64_t n, const int32_t* __restrict__ d_n_ptr, const float* __
       tmem_ld16(lane_addr + kColD, v);
       tmem_wait_ld();
       // _TruncExp.backward: g * exp(clamp(x, -15, 15))  (nerfstudio/field_components/activations.py:33-36)
-      const float g0 = valid ? __ldg(d_sigma + row) * gscale * expf(fminf(fmaxf(pre, -15.f), 15.f)) : 0.f;
+      const float g0 = valid ? up[3] * gscale * expf(fminf(fmaxf(pre, -15.f), 15.f)) : 0.f;
       a[0] = pack_h2(g0, __uint_as_float(v[1]));
 #pragma unroll
       for (int j = 1; j < 8; j++) a[j] = pack_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));

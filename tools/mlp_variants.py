@@ -15,9 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tools", "trace")
 VARIANTS = {
     "base": [],
-    "split3_ld32": ["-DGF_MLP_SPLIT_CTAS=3", "-DGF_MLP_SPLIT_LD32"],
-    "bwd128": ["-DGF_MLP_BWD_REGS=128"],
-    "bwd128_split3_ld32": ["-DGF_MLP_BWD_REGS=128", "-DGF_MLP_SPLIT_CTAS=3", "-DGF_MLP_SPLIT_LD32"],
+    "early": ["-DGF_MLP_EARLY_LOADS"],
 }
 
 
@@ -61,7 +59,7 @@ def main():
         L.gf_mlp_forward.argtypes = [i64, vp, cint, vp, vp, vp, vp, vp, vp, vp, vp]
         L.gf_mlp_backward.argtypes = [i64, vp, cint, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp]
         sigma, rgb = torch.empty(n, device="cuda"), torch.empty(n, 3, device="cuda")
-        masks = torch.zeros(n, 2, 4, device="cuda", dtype=torch.int32)
+        masks = torch.zeros(n, 2, 4, device="cuda", dtype=torch.int32)   # gf_mlp_mask_words(64) = 8
         d_feat = torch.empty(n, 32, device="cuda", dtype=torch.float16)
         d_params, d_rb = torch.zeros(11603, device="cuda"), torch.zeros(R, 64, device="cuda")
 
