@@ -415,6 +415,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = []   # per timed() call: host milliseconds per step spent enqueueing (>= the device time => host-bound)
+
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
@@ -423,8 +425,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
+        t_host = time.perf_counter()
         for i in range(steps):
             fn(warmup + i)
+        host_ms.append((time.perf_counter() - t_host) * 1e3 / steps)   # host time to ENQUEUE a step (no sync inside)
         eng.flush()            # the last step's (deferred, N > 1) optimizer step belongs to the timed region
         e1.record()
         barrier()
@@ -543,6 +547,9 @@ def main():
             "data": "synthetic",
             "config": static_config(args.workload, args.hidden, world, log2t),
             "run": {"samples_per_step_per_gpu": round(v_mean), "sample_ahead": bool(ahead),
+                    # host milliseconds per step spent enqueueing the timed loops (resident, e2e): a value at or above
+                    # the device time of the same loop means that loop is bound by the host, not by the GPU
+                    "host_enqueue_ms_per_step": [round(x, 3) for x in host_ms[:2]],
                     "exchange": ("none (single GPU)" if world == 1 else "none (focal stage: private sub-encoders)"
                                  if args.workload == "focal" else
                                  "peer memory over NVLink: one kernel per rank = reduce-scatter (fp32 gradient rows, "

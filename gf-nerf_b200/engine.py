@@ -602,8 +602,8 @@ class GFNeRFEngine:
         staged now and sampled underneath this step's backward pass (`train_step(next_rays=...)`)."""
         dev = self.device
         if not hasattr(self, "_h2d"):
-            self._h2d = dict(stream=torch.cuda.Stream(device=dev), slot=0, free=[None] * 3, bufs=[{}, {}, {}],
-                             losses=[], pinned=[], staged_rays=[None] * 3)
+            self._h2d = dict(stream=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev), slot=0,
+                             free=[None] * 3, bufs=[{}, {}, {}], losses=[], pinned=None, staged_rays=[None] * 3)
         h = self._h2d
         slot = h["slot"]
         h["slot"] = (slot + 1) % 3
@@ -644,12 +644,24 @@ class GFNeRFEngine:
             ready = h["stream"].record_event()
         cur.wait_event(ready)
         out = self.train_step(staged[0], staged[1], staged[2], staged[3], next_rays=nxt, **kw)
-        h["free"][slot] = cur.record_event()
+        done = cur.record_event()
+        h["free"][slot] = done
+        # the loss goes home on its own stream, behind the step: the step's stream is not held up by a 4-byte DMA, and
+        # the pinned ring is allocated once (a pinned allocation per step is a cudaHostAlloc per step)
         k = len(h["losses"])
-        if k >= len(h["pinned"]):
-            h["pinned"].append(torch.empty(1, dtype=torch.float32).pin_memory())
-        h["pinned"][k].copy_(out.loss, non_blocking=True)
-        h["losses"].append(cur.record_event())
+        ring = h["pinned"]
+        if ring is None or k >= ring.numel():
+            new = torch.empty(max(1024, 2 * (k + 1)), dtype=torch.float32).pin_memory()
+            if ring is not None:
+                for ev in h["losses"]:
+                    ev.synchronize()
+                new[:k] = ring[:k]
+            h["pinned"] = ring = new
+        with torch.cuda.stream(h["d2h"]):
+            h["d2h"].wait_event(done)
+            ring[k:k + 1].copy_(out.loss, non_blocking=True)
+            out.loss.record_stream(h["d2h"])
+            h["losses"].append(h["d2h"].record_event())
         return out
 
     def read_losses(self):
@@ -660,7 +672,7 @@ class GFNeRFEngine:
         vals = []
         for k, ev in enumerate(h["losses"]):
             ev.synchronize()
-            vals.append(float(h["pinned"][k][0]))
+            vals.append(float(h["pinned"][k]))
         h["losses"] = []
         return vals
 
