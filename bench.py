@@ -516,11 +516,10 @@ def main():
     if top["kernel"] == "sample_rays":
         # the schema knows "hbm" and "tensor"; this kernel is neither: a serial recurrence per ray,
         # bound by instruction issue / latency, and in the step it runs a batch ahead underneath the backward pass
-        roofline["note"] = ("instruction-issue-bound serial march (ncu: ~55 % issue-active, 179 warp instructions per "
-                            "step of a ray pair, 0.16 GB DRAM per launch), not HBM-bound; in the step it runs a batch "
-                            "ahead underneath the backward pass, so its share of the STEP is smaller than its share of "
-                            "kernel time. Largest memory-bound kernels: see kernels[] (hash_bwd: LSU data pipe / L2 "
-                            "atomics; hash_fwd: L1->L2 request path)")
+        roofline["note"] = ("latency-bound serial march (a recurrence in t per ray: ncu r02al ~60 % issue-active, ~265 "
+                            "warp instructions per step of eight rays, 0.16 GB DRAM per launch), not HBM-bound; in the "
+                            "step it runs a batch ahead on a side stream. Largest memory-bound kernels: see kernels[] "
+                            "(hash_bwd: LSU data pipe / L2 atomics; hash_fwd: L1->L2 request path)")
     if rank == 0 and args.breakdown:
         for k in kernels:
             print(k, file=sys.stderr)
