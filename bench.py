@@ -499,8 +499,11 @@ def main():
         kernels.append(ent)
     # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture of this same command
     traffic = {}
-    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))     # the latest round's capture
-    tp = tps[-1] if tps else ""
+    # the latest capture: profiles/traffic_latest.json (a copy of the newest rNN_traffic.json; tags do not sort by age)
+    tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
+    if not os.path.exists(tp):
+        tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+        tp = tps[-1] if tps else ""
     if tp:
         with open(tp) as f:
             cap = json.load(f)
@@ -546,8 +549,9 @@ def main():
             "data": "synthetic",
             "config": static_config(args.workload, args.hidden, world, log2t),
             "run": {"samples_per_step_per_gpu": round(v_mean), "sample_ahead": bool(ahead),
-                    # host milliseconds per step spent enqueueing the timed loops (resident, e2e): a value at or above
-                    # the device time of the same loop means that loop is bound by the host, not by the GPU
+                    # host milliseconds per step spent enqueueing the timed loops (resident, e2e).  Short runs show the
+                    # host's real cost (~0.9 ms per step); in long runs the launch queue fills and the host is held
+                    # back to just under the device time -- host-bound would be a value ABOVE the device time
                     "host_enqueue_ms_per_step": [round(x, 3) for x in host_ms[:2]],
                     "exchange": ("none (single GPU)" if world == 1 else "none (focal stage: private sub-encoders)"
                                  if args.workload == "focal" else

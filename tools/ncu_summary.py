@@ -74,7 +74,7 @@ def full(src, dst, title, cmd):
 
 
 NAMES = [("mlp_tc128_kernel<3>", "mlp128_fwd"), ("mlp_tc128_kernel<2>", "mlp128_bwd"), ("peer_reduce_adam", "exchange"),
-         ("sample_rays_kernel", "sample_rays"), ("compact_kernel", "compact"), ("hash_fwd_kernel", "hash_fwd"),
+         ("sample_rays", "sample_rays"), ("compact_kernel", "compact"), ("hash_fwd_kernel", "hash_fwd"),
          ("hash_bwd_kernel", "hash_bwd"), ("mlp_tc_kernel<3>", "mlp_fwd"), ("mlp_tc_kernel<0>", "mlp_fwd_plain"), ("mlp_tc_kernel<2>", "mlp_bwd"),
          ("mlp_tc_kernel<1>", "mlp_bwd_frozen"), ("composite_fwd_kernel", "composite_fwd"),
          ("composite_bwd_kernel", "composite_bwd"), ("adam_kernel<1>", "adam_table")]
