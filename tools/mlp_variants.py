@@ -15,7 +15,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "tools", "trace")
 VARIANTS = {
     "base": [],
-    "early": ["-DGF_MLP_EARLY_LOADS"],
 }
 
 
