@@ -42,6 +42,8 @@ _SIGS = {
     "gf_octree_search_order": [_vp],
     "gf_octree_proc": [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _i64, _vp],
     "gf_octree_proc_device": [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp],
+    "gf_octree_mark_invisible": [_vp, _i64, _vp, _vp, _vp, _i64, _vp],
+    "gf_octree_set_block_idxs": [_vp, _i64, _vp, _i64, _vp],
     "gf_sampler_points_anchors": [_i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "gf_octree_edge_pool": [_vp, _i64, _vp, _i64, _vp],
     "gf_sampler_edge_samples": [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -320,6 +320,116 @@ octree_proc_kernel(const TreeNodeDev* __restrict__ in, int64_t n, const int64_t*
   if (tid == 0) *d_n_out = total;
 }
 
+
+// ---- MarkInvisibleNodesKernel + CheckVisible (PersSampler_cuda.cu:680-742) -------------------------------------------
+// A node no camera can see loses its transform (trans_idx = -1); run at the subdivision milestones between the two
+// ProcOctree calls (:657-677).  One thread per node; the cameras go through shared memory in tiles of kCamTile records
+// {w2c 3x4, fx, cx, fy, cy, bound0, bound1} read by the whole CTA, so a camera is fetched from HBM once per CTA and
+// not once per node; a thread stops testing at its first visible camera (the reference counts them all and compares
+// the count with 1), a CTA stops staging when all its nodes are settled.
+//
+// Arithmetic = the SASS nvcc 12.9 emits for the reference's kernel body at -fmad=true (oracle/_ref/libgf_ref_cuda.so;
+// tests/test_octree_device_gpu.py runs the two side by side and asserts identical blobs):
+//   radius  = float(double(side_len) * 0.707)            (the literal is a double)
+//   cam_i   = fma(c.x, m_i0, c.y * m_i1) + fma(c.z, m_i2, m_i3)
+//   norm    = sqrt(fma(x, x, fma(y, y, z * z)))
+//   q = radius / -z;  img_x = fx * (x / -z);  img_y = fy * (y / -z);  bias_y = fy * q
+//   out of image <=> img_x > fma(fx, q, cx)  ||  fma(fx, q, img_x) < -cx  ||  bias_y + img_y < -cy  ||  img_y > cy + bias_y
+// (bias_x never exists as a rounded value: its product is fused into both sums; bias_y does.)
+constexpr int kCamTile = 128;
+constexpr int kCamRec = 18;
+constexpr int kVisThreads = 256;
+
+__device__ __forceinline__ bool camera_sees(const float* __restrict__ c, float px, float py, float pz, float radius) {
+  const float x = __fadd_rn(__fmaf_rn(px, c[0], __fmul_rn(py, c[1])), __fmaf_rn(pz, c[2], c[3]));
+  const float y = __fadd_rn(__fmaf_rn(px, c[4], __fmul_rn(py, c[5])), __fmaf_rn(pz, c[6], c[7]));
+  const float z = __fadd_rn(__fmaf_rn(px, c[8], __fmul_rn(py, c[9])), __fmaf_rn(pz, c[10], c[11]));
+  const float fx = c[12], cx = c[13], fy = c[14], cy = c[15], b0 = c[16], b1 = c[17];
+  const float nz = -z;
+  if (nz < __fadd_rn(b0, -radius) || nz > __fadd_rn(radius, b1)) return false;
+  const float norm = __fsqrt_rn(__fmaf_rn(x, x, __fmaf_rn(y, y, __fmul_rn(z, z))));
+  if (norm < radius) return true;
+  const float q = __fdiv_rn(radius, nz);
+  const float bias_y = __fmul_rn(fy, q);
+  const float img_x = __fmul_rn(fx, __fdiv_rn(x, nz));
+  const float img_y = __fmul_rn(fy, __fdiv_rn(y, nz));
+  if (img_x > __fmaf_rn(fx, q, cx) || __fmaf_rn(fx, q, img_x) < -cx) return false;
+  if (__fadd_rn(bias_y, img_y) < -cy || img_y > __fadd_rn(cy, bias_y)) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(kVisThreads)
+mark_invisible_kernel(TreeNodeDev* __restrict__ nodes, int64_t n_nodes, const float* __restrict__ w2c,
+                      const float* __restrict__ intri, const float* __restrict__ bounds, int64_t n_cams) {
+  __shared__ float cams[kCamTile * kCamRec];
+  const int64_t n_round = (n_nodes + kVisThreads - 1) / kVisThreads * kVisThreads;   // whole CTAs stay in the loop
+  for (int64_t node = (int64_t)blockIdx.x * kVisThreads + threadIdx.x; node < n_round;
+       node += (int64_t)gridDim.x * kVisThreads) {
+    const bool live = node < n_nodes;
+    float px = 0.f, py = 0.f, pz = 0.f, radius = 0.f;
+    if (live) {
+      const float4 cs = *reinterpret_cast<const float4*>(nodes + node);   // center xyz, side_len
+      px = cs.x, py = cs.y, pz = cs.z;
+      radius = (float)((double)cs.w * 0.707);
+    }
+    bool seen = !live;
+    for (int64_t c0 = 0; c0 < n_cams; c0 += kCamTile) {
+      const int nc = (int)min((int64_t)kCamTile, n_cams - c0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nc * kCamRec; i += kVisThreads) {
+        const int cam = i / kCamRec, f = i - cam * kCamRec;
+        const int64_t g = c0 + cam;
+        float v;
+        if (f < 12) v = w2c[g * 12 + f];
+        else if (f < 16) v = intri[g * 9 + (f == 12 ? 0 : f == 13 ? 2 : f == 14 ? 4 : 5)];
+        else v = bounds[g * 2 + (f - 16)];
+        cams[i] = v;
+      }
+      __syncthreads();
+      for (int cam = 0; cam < nc && !seen; cam++) seen = camera_sees(cams + cam * kCamRec, px, py, pz, radius);
+      if (__syncthreads_and(seen)) break;
+    }
+    if (live && !seen) nodes[node].trans_idx = -1;
+  }
+}
+
+// ---- SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-766) ---------------------------------------------------------
+// block_idx of every node = index of the nearest block centre: fp32 difference and norm (fma(dx, dx, fma(dy, dy,
+// dz * dz)), IEEE sqrt -- the reference's SASS), compared as doubles against a running minimum that starts at 1e9 with
+// a strict `<` (the first of equal minima wins; -1 if no centre is closer than 1e9).
+constexpr int kCenterTile = 512;
+
+__global__ void __launch_bounds__(kVisThreads)
+set_block_idxs_kernel(TreeNodeDev* __restrict__ nodes, int64_t n_nodes, const float* __restrict__ centers,
+                      int64_t n_blocks) {
+  __shared__ float ctr[kCenterTile * 3];
+  const int64_t n_round = (n_nodes + kVisThreads - 1) / kVisThreads * kVisThreads;
+  for (int64_t node = (int64_t)blockIdx.x * kVisThreads + threadIdx.x; node < n_round;
+       node += (int64_t)gridDim.x * kVisThreads) {
+    const bool live = node < n_nodes;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (live) {
+      const float4 cs = *reinterpret_cast<const float4*>(nodes + node);
+      px = cs.x, py = cs.y, pz = cs.z;
+    }
+    double best = 1e+9;
+    int64_t best_idx = -1;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += kCenterTile) {
+      const int nb = (int)min((int64_t)kCenterTile, n_blocks - b0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nb * 3; i += kVisThreads) ctr[i] = centers[b0 * 3 + i];
+      __syncthreads();
+      for (int b = 0; b < nb; b++) {
+        const float dx = __fadd_rn(px, -ctr[3 * b]), dy = __fadd_rn(py, -ctr[3 * b + 1]),
+                    dz = __fadd_rn(pz, -ctr[3 * b + 2]);
+        const double d = (double)__fsqrt_rn(__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz))));
+        if (d < best) best = d, best_idx = b0 + b;
+      }
+    }
+    if (live) nodes[node].block_idx = best_idx;
+  }
+}
+
 }  // namespace
 }  // namespace gf
 
@@ -349,4 +459,26 @@ extern "C" int gf_octree_proc_device(const void* nodes_in, int64_t n_in, const i
       brute_force, (TreeNodeDev*)nodes_out, weight_stats_out, alpha_stats_out, capacity, (unsigned char*)scratch,
       d_n_out, d_error);
   return check_launch("octree_proc_kernel");
+}
+
+extern "C" int gf_octree_mark_invisible(void* tree_nodes, int64_t n_nodes, const float* w2c, const float* intri,
+                                        const float* bounds, int64_t n_cams, void* stream) {
+  GF_REQUIRE(tree_nodes && n_nodes > 0, "gf_octree_mark_invisible: null / empty node blob");
+  GF_REQUIRE(n_cams >= 0 && (n_cams == 0 || (w2c && intri && bounds)), "gf_octree_mark_invisible: null camera arrays");
+  GF_REQUIRE((reinterpret_cast<uintptr_t>(tree_nodes) & 15) == 0,
+             "gf_octree_mark_invisible: the node blob must be 16-byte aligned");
+  mark_invisible_kernel<<<stride_grid(n_nodes, kVisThreads, 4), kVisThreads, 0, (cudaStream_t)stream>>>(
+      (TreeNodeDev*)tree_nodes, n_nodes, w2c, intri, bounds, n_cams);
+  return check_launch("mark_invisible_kernel");
+}
+
+extern "C" int gf_octree_set_block_idxs(void* tree_nodes, int64_t n_nodes, const float* centers, int64_t n_blocks,
+                                        void* stream) {
+  GF_REQUIRE(tree_nodes && n_nodes > 0, "gf_octree_set_block_idxs: null / empty node blob");
+  GF_REQUIRE(n_blocks >= 0 && (n_blocks == 0 || centers), "gf_octree_set_block_idxs: null centres");
+  GF_REQUIRE((reinterpret_cast<uintptr_t>(tree_nodes) & 15) == 0,
+             "gf_octree_set_block_idxs: the node blob must be 16-byte aligned");
+  set_block_idxs_kernel<<<stride_grid(n_nodes, kVisThreads, 4), kVisThreads, 0, (cudaStream_t)stream>>>(
+      (TreeNodeDev*)tree_nodes, n_nodes, centers, n_blocks);
+  return check_launch("set_block_idxs_kernel");
 }

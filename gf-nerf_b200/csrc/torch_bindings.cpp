@@ -338,28 +338,13 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     visit_cnt_ = torch::zeros({n_out}, visit_cnt_.options());
   }
 
-  // MarkInvisibleNodesKernel + CheckVisible (PersSampler_cuda.cu:680-742): a node no camera can see loses its
-  // transform.  Cold (subdivision milestones only): a handful of torch ops over [n_nodes, n_cams].
+  // PersOctree::MarkInvisibleNodes (MarkInvisibleNodesKernel + CheckVisible, PersSampler_cuda.cu:680-742): a node no
+  // camera can see loses its transform -- one kernel over the device node blob (csrc/octree_device.cu)
   void MarkInvisibleNodes() {
     if (!w2c_.defined()) return;  // state loaded without cameras
-    auto nodes = tree_nodes_.view({-1, GF_TREE_NODE_BYTES});
-    auto cs = nodes.slice(1, 0, 16).contiguous().view(torch::kFloat32);  // center xyz, side_len
-    auto center = cs.slice(1, 0, 3), side = cs.select(1, 3);
-    auto cam = torch::einsum("cij,nj->nci", {w2c_.slice(2, 0, 3), center}) + w2c_.select(2, 3).unsqueeze(0);
-    auto radius = (side * 0.707f).unsqueeze(1);
-    auto z = -cam.select(2, 2);
-    auto out_z = (z < bound_.select(1, 0).unsqueeze(0) - radius) | (z > bound_.select(1, 1).unsqueeze(0) + radius);
-    auto inside = torch::linalg_norm(cam, 2, {-1}, false) < radius;
-    auto cx = intri_.select(1, 0).select(1, 2).unsqueeze(0), cy = intri_.select(1, 1).select(1, 2).unsqueeze(0);
-    auto fx = intri_.select(1, 0).select(1, 0).unsqueeze(0), fy = intri_.select(1, 1).select(1, 1).unsqueeze(0);
-    auto bx = radius / z * fx, by = radius / z * fy;
-    auto ix = cam.select(2, 0) / z * fx, iy = cam.select(2, 1) / z * fy;
-    auto out_img = (ix + bx < -cx) | (ix > cx + bx) | (iy + by < -cy) | (iy > cy + by);
-    auto visible = (~out_z) & (inside | ~out_img);
-    auto invisible = visible.sum(-1) < 1;
-    auto tidx = nodes.slice(1, 96, 104).contiguous().view(torch::kInt64).view({-1});
-    tidx.masked_fill_(invisible, -1);
-    nodes.slice(1, 96, 104).copy_(tidx.view({-1, 1}).view(torch::kUInt8));
+    c10::cuda::CUDAGuard guard(tree_nodes_.device());
+    GF_CHECK(gf_octree_mark_invisible(tree_nodes_.data_ptr(), n_nodes(), w2c_.data_ptr<float>(),
+                                      intri_.data_ptr<float>(), bound_.data_ptr<float>(), w2c_.size(0), stream()));
   }
 
   void UpdateRayMarch(int64_t cur_step) {  // PersSampler.cpp:958-967 (fp32 arithmetic)
@@ -430,16 +415,12 @@ struct PersSamplerImpl : torch::CustomClassHolder {
     return center.index_select(0, idx.clamp(0, n_nodes() - 1)) * ok.unsqueeze(1).to(torch::kFloat32);
   }
 
-  // PersOctree::UpdateBlockIdxs + SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-798): nearest block centre
+  // PersOctree::UpdateBlockIdxs + SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-798): nearest block centre per
+  // node (fp32 norm, the first of equal minima), then compact
   void UpdateBlockIdxs(const Tensor& centers) {
     c10::cuda::CUDAGuard guard(tree_nodes_.device());
-    auto nodes = tree_nodes_.view({-1, GF_TREE_NODE_BYTES});
-    // fp32 norm like the kernel (:758), first of equal minima like its strict `<` (torch::argmin returns the first)
-    auto center = nodes.slice(1, 0, 12).contiguous().view(torch::kFloat32);
-    auto c = centers.to(tree_nodes_.device()).to(torch::kFloat32);
-    auto d = torch::linalg_norm(center.unsqueeze(1) - c.unsqueeze(0), 2, {-1}, false);
-    auto best = torch::argmin(d, -1).to(torch::kInt64).contiguous();
-    nodes.slice(1, 104, 112).copy_(best.view({-1, 1}).view(torch::kUInt8));
+    auto c = centers.to(tree_nodes_.device()).to(torch::kFloat32).reshape({-1, 3}).contiguous();
+    GF_CHECK(gf_octree_set_block_idxs(tree_nodes_.data_ptr(), n_nodes(), c.data_ptr<float>(), c.size(0), stream()));
     ProcOctree(true, false, false);
   }
 

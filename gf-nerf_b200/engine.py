@@ -184,6 +184,69 @@ class GFNeRFEngine:
         self.stage = "init_stage"
         self.sampler.UpdateMode(0)
 
+    # ---- parameters in / out of the operator-API modules ------------------------------------------------------------
+    # GFNeRFField / GFNeRFModel carry the reference's state-dict keys (field.py), so this is also the way a checkpoint
+    # of the reference gets into the fused engine and back: load_state_dict on the modules, then `from_model`.
+    @classmethod
+    def from_model(cls, model, **kw) -> "GFNeRFEngine":
+        """Fused engine over the sampler and the parameters of a `GFNeRFModel` (model.py): same octree object (the
+        model's `persampler.sampler`), table size, width and embedding as its field; parameters copied (`load_model`)."""
+        f = model.field
+        eng = cls(model.persampler.sampler, log2_table_size=f.log2_table_size, num_images=f.num_images,
+                  hidden=f.hidden_dim, use_appearance_embedding=f.use_appearance_embedding, **kw)
+        eng.load_model(model)
+        return eng
+
+    def load_model(self, model, reset_optimizer: bool = True):
+        """Adopt the global table (+ primes / bias pool), both MLPs and the appearance embedding of a GFNeRFField (or of
+        a GFNeRFModel's field).  The Adam moments restart unless `reset_optimizer` is False (a checkpoint of the
+        reference keeps its optimizer state with the trainer, not with the model)."""
+        f = getattr(model, "field", model)
+        if int(f.hidden_dim) != self.hidden:
+            raise ValueError(f"gfnerf_b200: the field is {f.hidden_dim} wide, the engine {self.hidden}")
+        src = f.base_encoding_init.hash_3d
+        if tuple(src.feat_pool_.shape) != tuple(self.enc.feat_pool_.shape):
+            raise ValueError(f"gfnerf_b200: table of {tuple(src.feat_pool_.shape)} rows x channels into an engine built "
+                             f"for {tuple(self.enc.feat_pool_.shape)}")
+        if (self.emb is None) != (not f.use_appearance_embedding):
+            raise ValueError("gfnerf_b200: field and engine disagree on use_appearance_embedding")
+        self.flush()
+        self.enc.LoadStates([t.detach() for t in src.States()], 0)
+        self.n_volumes = self.enc.n_volumes_
+        blob = torch.cat([f.base_network.flat_params(), f.mlp_head.flat_params()]).detach().float()
+        if blob.numel() != self.mlp.numel():
+            raise ValueError(f"gfnerf_b200: {blob.numel()} MLP parameters, the fused kernel takes {self.mlp.numel()}")
+        self.mlp.copy_(blob)
+        if self.emb is not None:
+            w = f.embedding_appearance.embedding.weight.detach()
+            if tuple(w.shape) != tuple(self.emb.shape):
+                raise ValueError(f"gfnerf_b200: embedding {tuple(w.shape)} into an engine built for {tuple(self.emb.shape)}")
+            self.emb.copy_(w)
+        if reset_optimizer:
+            for opt in (self.opt_table, self.opt_mlp, self.opt_emb):
+                if opt is not None:
+                    opt.m.zero_(), opt.v.zero_(), opt.d_step.zero_()
+        self.enc.shadow(force=True)
+
+    def store_model(self, model):
+        """The inverse of `load_model`: the engine's current parameters into the field's modules (whose `state_dict()`
+        is the reference's checkpoint layout)."""
+        f = getattr(model, "field", model)
+        if int(f.hidden_dim) != self.hidden:
+            raise ValueError(f"gfnerf_b200: the field is {f.hidden_dim} wide, the engine {self.hidden}")
+        self.flush()
+        self.sync_master_params()       # peer exchange: every rank only keeps ITS fp32 rows current
+        f.base_encoding_init.load_states([t.detach() for t in self.enc.States()], 0)
+        o = 0
+        with torch.no_grad():
+            for lin in f.base_network.linears() + f.mlp_head.linears():
+                for p in (lin.weight, lin.bias):
+                    p.copy_(self.mlp[o:o + p.numel()].view_as(p))
+                    o += p.numel()
+            if self.emb is not None:
+                f.embedding_appearance.embedding.weight.copy_(self.emb)
+        assert o == self.mlp.numel()
+
     # ---- per-stage device timing (bench / profiling only) -----------------------------------
     def enable_timers(self, on: bool = True):
         """Brackets every stage with CUDA events on the launching stream; read with `stage_times()`."""

@@ -209,10 +209,18 @@ class Hash3DAnchoredCore:
     def LoadStates(self, states: List[torch.Tensor], idx: int) -> int:
         self.feat_pool_.data.copy_(states[idx]); idx += 1
         self.prim_pool_ = states[idx].clone().to(self.device).contiguous(); idx += 1   # the size may change
-        self.bias_pool_.data.copy_(states[idx]); idx += 1
+        bias = states[idx]; idx += 1
+        if tuple(bias.shape) == tuple(self.bias_pool_.shape):
+            self.bias_pool_.data.copy_(bias)
+        else:
+            # a checkpoint written with another n_volumes: the reference's `bias_pool_.data().copy_()` (:116) throws
+            # here although it lets prim_pool change size one line above; the pool follows the checkpoint instead
+            self.bias_pool_ = bias.detach().clone().to(self.device, torch.float32).contiguous()
         self.n_volumes_ = int(states[idx].item()); idx += 1
-        if self.bias_pool_.shape[0] != N_LEVELS * self.n_volumes_:
-            self.bias_pool_ = torch.zeros((N_LEVELS * self.n_volumes_, 3), dtype=torch.float32, device=self.device)
+        if (tuple(self.prim_pool_.shape) != (N_LEVELS, self.n_volumes_, 3)
+                or tuple(self.bias_pool_.shape) != (N_LEVELS * self.n_volumes_, 3)):
+            raise ValueError(f"Hash3DAnchored.LoadStates: prime pool {tuple(self.prim_pool_.shape)} / bias pool "
+                             f"{tuple(self.bias_pool_.shape)} do not belong to n_volumes = {self.n_volumes_}")
         # `.data.copy_()` does not bump `_version`: drop both cached decisions (fp16 shadow, all-zero bias) by hand
         self._shadow_key = None
         self._bias_key = None

@@ -371,47 +371,27 @@ class PersSamplerCore:
         self._octree = value
         self._octree_stale = False
 
-    @staticmethod
-    def invisible_nodes(nodes: torch.Tensor, w2c: torch.Tensor, intri: torch.Tensor, bound: torch.Tensor) -> torch.Tensor:
-        """CheckVisible over all (node, camera) pairs (PersSampler_cuda.cu:680-723) as torch ops on whatever device the
-        tensors live on: bool [n_nodes], True = seen by no camera.  nodes: uint8 [n,128] TreeNode blobs."""
-        cs = nodes[:, :16].contiguous().view(torch.float32)                    # center xyz, side_len
-        center, side = cs[:, :3], cs[:, 3]
-        cam = torch.einsum("cij,nj->nci", w2c[:, :, :3], center) + w2c[None, :, :, 3]   # [n,c,3]
-        radius = (side * 0.707)[:, None]
-        z = -cam[..., 2]
-        out_z = (z < bound[None, :, 0] - radius) | (z > bound[None, :, 1] + radius)
-        inside = torch.linalg.norm(cam, dim=-1) < radius
-        cx, cy = intri[None, :, 0, 2], intri[None, :, 1, 2]
-        fx, fy = intri[None, :, 0, 0], intri[None, :, 1, 1]
-        bx, by = radius / z * fx, radius / z * fy
-        ix, iy = cam[..., 0] / z * fx, cam[..., 1] / z * fy
-        out_img = (ix + bx < -cx) | (ix > cx + bx) | (iy + by < -cy) | (iy > cy + by)
-        visible = (~out_z) & (inside | ~out_img)
-        return visible.sum(-1) < 1
-
     def MarkInvisibleNodes(self):
-        """MarkInvisibleNodesKernel + CheckVisible (PersSampler_cuda.cu:680-742); cold (milestones only), so it
-        is a handful of torch ops over [n_nodes, n_cams] instead of a kernel of its own."""
-        nodes = self.tree_nodes_gpu_.view(-1, 128)
-        invisible = self.invisible_nodes(nodes, self.w2c_, self.intri_, self.bound_)
-        tidx = nodes[:, 96:104].contiguous().view(torch.int64).view(-1)
-        tidx[invisible] = -1
-        nodes[:, 96:104] = tidx.view(-1, 1).view(torch.uint8)
+        """PersOctree::MarkInvisibleNodes (MarkInvisibleNodesKernel + CheckVisible, PersSampler_cuda.cu:680-742): a node
+        no camera sees loses its transform.  One kernel over the device node blob (gf_octree_mark_invisible,
+        csrc/octree_device.cu), the cameras staged through shared memory; same bits as the reference's kernel."""
+        _lib.require_cuda(self.tree_nodes_gpu_, self.w2c_, self.intri_, self.bound_)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gf_octree_mark_invisible(
+                _lib.ptr(self.tree_nodes_gpu_), self.n_nodes, _lib.ptr(self.w2c_), _lib.ptr(self.intri_),
+                _lib.ptr(self.bound_), int(self.w2c_.shape[0]), _lib.cur_stream()), "gf_octree_mark_invisible")
+        self._octree_stale = True
 
     def UpdateBlockIdxs(self, centers: torch.Tensor):
-        """SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-798): nearest block centre per node, then compact."""
-        nodes = self.tree_nodes_gpu_.view(-1, 128)
-        nodes[:, 104:112] = self.nearest_block(nodes, centers.to(nodes.device)).view(-1, 1).view(torch.uint8)
+        """PersOctree::UpdateBlockIdxs (PersSampler_cuda.cu:746-798): nearest block centre per node
+        (SetBlockIdxsNearestKernel -> gf_octree_set_block_idxs), then compact."""
+        centers = torch.as_tensor(centers, dtype=torch.float32).to(self.device).contiguous().view(-1, 3)
+        _lib.require_cuda(self.tree_nodes_gpu_)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gf_octree_set_block_idxs(
+                _lib.ptr(self.tree_nodes_gpu_), self.n_nodes, _lib.ptr(centers), int(centers.shape[0]),
+                _lib.cur_stream()), "gf_octree_set_block_idxs")
         self.ProcOctree(True, False, False)
-
-    @staticmethod
-    def nearest_block(nodes: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
-        """int64 [n_nodes]: index of the block centre nearest to each node centre (SetBlockIdxsNearestKernel,
-        PersSampler_cuda.cu:746-766: fp32 norm, strict `<`, so the first of equal minima)."""
-        center = nodes[:, :12].contiguous().view(torch.float32)
-        d = torch.linalg.norm(center[:, None] - centers.float()[None], dim=-1)
-        return torch.argmin(d, dim=-1).to(torch.int64)      # torch returns the first of equal minima, like the strict `<`
 
     def UpdateMode(self, mode: int):
         self.mode_ = int(mode)

@@ -235,6 +235,18 @@ int gf_octree_proc_device(const void* nodes_in, int64_t n_in, const int64_t* wei
                           int64_t capacity, void* scratch, int64_t scratch_bytes, int64_t* d_n_out, int32_t* d_error,
                           void* stream);
 
+/* PersOctree::MarkInvisibleNodes (MarkInvisibleNodesKernel + CheckVisible, PersSampler_cuda.cu:680-742; run at the
+ * subdivision milestones, :657-677): every node whose bounding sphere (radius 0.707 * side_len) no camera sees gets
+ * trans_idx = -1, in place in the device node blob.  w2c f32 [n_cams,3,4], intri f32 [n_cams,3,3], bounds f32
+ * [n_cams,2] (device).  Same bits as the reference's kernel built by nvcc (arithmetic order: csrc/octree_device.cu). */
+int gf_octree_mark_invisible(void* tree_nodes, int64_t n_nodes, const float* w2c, const float* intri,
+                             const float* bounds, int64_t n_cams, void* stream);
+
+/* SetBlockIdxsNearestKernel (PersSampler_cuda.cu:746-766), the device half of PersOctree::UpdateBlockIdxs (:767-798;
+ * the caller compacts afterwards): block_idx of every node = index of the nearest of `centers` f32 [n_blocks,3]
+ * (device), the first of equal minima, -1 if none is closer than 1e9; in place in the device node blob. */
+int gf_octree_set_block_idxs(void* tree_nodes, int64_t n_nodes, const float* centers, int64_t n_blocks, void* stream);
+
 /* PersSampler::GetPointsAnchors (GetRaysTreeNodesIntersectsKernel + GetTreeNodeIdxFromTsKernel, :799-853, 924-980;
  * the proposal-sampler variant, cold): anchors i64 [n_rays, n_pts_per_ray] = index of the LEAF whose slab interval
  * along the ray contains t_cur (= (t_start + t_end) / 2, f32 [n_rays, n_pts_per_ray]), -1 if none; a sample exactly

@@ -1096,3 +1096,54 @@ void orc_edge_samples(int64_t n_pts, const void* edge_pool_blob, const void* per
     }
   }
 }
+
+/* ---- octree maintenance between two ProcOctree calls ------------------------------------------
+ * CheckVisible + MarkInvisibleNodesKernel (PersSampler_cuda.cu:680-723): a node whose bounding sphere (radius
+ * 0.707 * side_len -- a DOUBLE literal, so the product is taken in double and rounded once) is seen by no camera gets
+ * trans_idx = -1.  The contraction spelled out below is the one nvcc applies to the reference's expressions (read off
+ * the SASS of oracle/_ref/libgf_ref_cuda.so): the 4-term rows of w2c * center.homogeneous() as
+ * fma(x, m0, y * m1) + fma(z, m2, m3); the squared norm as fma(x, x, fma(y, y, z * z)); bias_x only ever fused into the
+ * two sums that use it, bias_y rounded.  w2c [n_cams,3,4], intri [n_cams,3,3], bounds [n_cams,2], row major. */
+static int check_visible(const float* c, float side_len, const float* K, const float* m, const float* bound) {
+  const float radius = (float)((double)side_len * 0.707);
+  const float x = fmaf(c[0], m[0], c[1] * m[1]) + fmaf(c[2], m[2], m[3]);
+  const float y = fmaf(c[0], m[4], c[1] * m[5]) + fmaf(c[2], m[6], m[7]);
+  const float z = fmaf(c[0], m[8], c[1] * m[9]) + fmaf(c[2], m[10], m[11]);
+  if (-z < bound[0] - radius || -z > bound[1] + radius) return 0;
+  if (sqrtf(fmaf(x, x, fmaf(y, y, z * z))) < radius) return 1;
+  const float cx = K[2], cy = K[5], fx = K[0], fy = K[4];
+  const float q = radius / -z;
+  const float bias_y = q * fy;
+  const float img_x = x / -z * fx, img_y = y / -z * fy;
+  if (fmaf(q, fx, img_x) < -cx || img_x > fmaf(q, fx, cx) || img_y + bias_y < -cy || img_y > cy + bias_y) return 0;
+  return 1;
+}
+
+void orc_mark_invisible_nodes(int64_t n_nodes, int64_t n_cams, void* tree_nodes_blob, const float* intri,
+                              const float* w2c, const float* bounds) {
+  tree_node* nodes = (tree_node*)tree_nodes_blob;
+#pragma omp parallel for schedule(static)
+  for (int64_t u = 0; u < n_nodes; u++) {
+    int64_t n_visible = 0;
+    for (int64_t k = 0; k < n_cams; k++)
+      n_visible += check_visible(nodes[u].center, nodes[u].side_len, intri + 9 * k, w2c + 12 * k, bounds + 2 * k);
+    if (n_visible < 1) nodes[u].trans_idx = -1;
+  }
+}
+
+/* SetBlockIdxsNearestKernel (:746-766): fp32 difference and norm, compared in double against a minimum that starts at
+ * 1e9 with a strict `<` (the first of equal minima; -1 when nothing is closer than 1e9). */
+void orc_set_block_idxs(int64_t n_nodes, int64_t n_blocks, void* tree_nodes_blob, const float* centers) {
+  tree_node* nodes = (tree_node*)tree_nodes_blob;
+  for (int64_t u = 0; u < n_nodes; u++) {
+    double min_dist = 1e+9;
+    int64_t best = -1;
+    for (int64_t b = 0; b < n_blocks; b++) {
+      const float dx = nodes[u].center[0] - centers[3 * b], dy = nodes[u].center[1] - centers[3 * b + 1],
+                  dz = nodes[u].center[2] - centers[3 * b + 2];
+      const double d = (double)sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+      if (d < min_dist) min_dist = d, best = b;
+    }
+    nodes[u].block_idx = best;
+  }
+}

@@ -265,6 +265,23 @@ def edge_samples(edge_pool_blob, pers_trans_blob, edge_idx, edge_coords):
     return pts, idx
 
 
+def mark_invisible_nodes(tree_nodes_blob, intri, w2c, bounds):
+    """in place on a copy: the node blob with trans_idx = -1 for every node no camera sees (PersSampler_cuda.cu:680-742)"""
+    nodes = np.ascontiguousarray(tree_nodes_blob, np.uint8).copy()
+    intri, w2c, bounds = _f32(intri), _f32(w2c), _f32(bounds)
+    lib().orc_mark_invisible_nodes(C.c_int64(nodes.size // 128), C.c_int64(w2c.shape[0]), _p(nodes), _p(intri),
+                                   _p(w2c), _p(bounds))
+    return nodes
+
+
+def set_block_idxs(tree_nodes_blob, centers):
+    """a copy of the node blob with block_idx = nearest block centre (SetBlockIdxsNearestKernel, :746-766)"""
+    nodes = np.ascontiguousarray(tree_nodes_blob, np.uint8).copy()
+    centers = _f32(centers)
+    lib().orc_set_block_idxs(C.c_int64(nodes.size // 128), C.c_int64(centers.shape[0]), _p(nodes), _p(centers))
+    return nodes
+
+
 def error_map_update(error_map, indices, pred_rgb, gt_rgb):
     """gfnerf/gf_pipeline.py:180-185 + nerfstudio/data/utils/dataloaders.py:140-142 in numpy: error = sum_c |gt - pred|
     (fp32, channel order 0,1,2), error_map[idx0, idx1, idx2] = error; in place on error_map [n,h,w]; returns error."""

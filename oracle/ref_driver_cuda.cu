@@ -141,4 +141,21 @@ int refcu_trans_query_frame(int64_t n_pts, void* tree_nodes, int64_t n_nodes, vo
   return (int)cudaDeviceSynchronize();
 }
 
+/* PersOctree::MarkInvisibleNodes (:707-742) and the kernel of PersOctree::UpdateBlockIdxs (:746-798), in place on the
+ * device node blob */
+int refcu_mark_invisible_nodes(int64_t n_nodes, int64_t n_cams, void* tree_nodes, float* intri, float* w2c,
+                               float* bounds) {
+  MarkInvisibleNodesKernel<<<div_up(n_nodes, THREADS), THREADS>>>(n_nodes, n_cams, (TreeNode*)tree_nodes,
+                                                                  (Watrix33f*)intri, (Watrix34f*)w2c, (Wec2f*)bounds);
+  CK(cudaGetLastError());
+  return (int)cudaDeviceSynchronize();
+}
+
+int refcu_set_block_idxs(int64_t n_nodes, int64_t n_blocks, void* tree_nodes, float* centers) {
+  SetBlockIdxsNearestKernel<<<div_up(n_nodes, THREADS), THREADS>>>(n_nodes, n_blocks, (TreeNode*)tree_nodes,
+                                                                   (Wec3f*)centers);
+  CK(cudaGetLastError());
+  return (int)cudaDeviceSynchronize();
+}
+
 } /* extern "C" */

@@ -217,6 +217,22 @@ def cuda_get_samples(rays_o, rays_d_unit, noise, tree_nodes, pers_trans, search_
     return out
 
 
+def cuda_mark_invisible_nodes(tree_nodes, intri, w2c, bounds):
+    """torch CUDA tensors; in place on tree_nodes (uint8 [128 * n])."""
+    rc = cuda_lib().refcu_mark_invisible_nodes(_i64(tree_nodes.numel() // 128), _i64(intri.shape[0]), _dp(tree_nodes),
+                                               _dp(intri.float().contiguous()), _dp(w2c.float().contiguous()),
+                                               _dp(bounds.float().contiguous()))
+    assert rc == 0, f"refcu_mark_invisible_nodes: cudaError {rc}"
+
+
+def cuda_set_block_idxs(tree_nodes, centers):
+    """torch CUDA tensors; in place on tree_nodes."""
+    centers = centers.float().contiguous()
+    rc = cuda_lib().refcu_set_block_idxs(_i64(tree_nodes.numel() // 128), _i64(centers.shape[0]), _dp(tree_nodes),
+                                         _dp(centers))
+    assert rc == 0, f"refcu_set_block_idxs: cudaError {rc}"
+
+
 # ---------------------------------------------------------------- host member functions of PersOctree
 def proc_octree(tree_nodes, weight_stats, alpha_stats, visit_cnt, compact, subdivide, brute_force, flavour="off"):
     """PersOctree::ProcOctree (PtsSampler/PersSampler.cpp:154-417), the reference's own body.  -> (nodes blob uint8,

@@ -133,3 +133,115 @@ def test_sampler_proc_octree_runs_on_the_device_and_matches_the_host_schedule():
     V = int(ca.total.item())
     assert V == int(cb.total.item()) and V > 0
     assert torch.equal(ca.node[:V], cb.node[:V]) and torch.equal(ca.t[:V], cb.t[:V])
+
+
+# ---- MarkInvisibleNodes / UpdateBlockIdxs on the device (gf_octree_mark_invisible, gf_octree_set_block_idxs) ----------
+def _cameras(rig, n_cams):
+    c2w = rig["c2w"][:n_cams]
+    m = np.tile(np.eye(4, dtype=np.float32)[None], (c2w.shape[0], 1, 1))
+    m[:, :3, :] = c2w
+    w2c = np.ascontiguousarray(np.linalg.inv(m)[:, :3, :].astype(np.float32)) if n_cams else np.zeros((0, 3, 4), np.float32)
+    return w2c, np.ascontiguousarray(rig["intri"][:n_cams]), np.ascontiguousarray(rig["bounds"][:n_cams])
+
+
+def _many_nodes(rig, copies, seed):
+    """The rig's node blob `copies` times over, centres and side lengths jittered: tens of thousands of spheres at
+    every distance from the frustum faces, so that the borderline comparisons of CheckVisible are exercised."""
+    rng = np.random.RandomState(seed)
+    blobs = [rig["tree_nodes"].reshape(-1, 128).copy() for _ in range(copies)]
+    for k, b in enumerate(blobs[1:]):
+        cs = b[:, :16].copy().view(np.float32)
+        cs[:, :3] += rng.normal(0, 0.5 * (k + 1), size=cs[:, :3].shape).astype(np.float32)
+        cs[:, 3] *= rng.uniform(0.25, 2.0, size=cs.shape[0]).astype(np.float32)
+        b[:, :16] = cs.view(np.uint8)
+    return np.ascontiguousarray(np.concatenate(blobs, 0).reshape(-1))
+
+
+@pytest.mark.parametrize("rig_name,n_cams,copies", [("rig8", 6, 1), ("rig8", 64, 16), ("rig20", 3, 4), ("rig20", 400, 8),
+                                                     ("rig8", 0, 1), ("rig8", 129, 3)])
+def test_mark_invisible_kernel_equals_oracle_and_the_reference_kernel(rig_name, n_cams, copies):
+    """Bar: the node blob the kernel leaves is byte-identical to the oracle's (PersSampler_cuda.cu:680-742 restated
+    with nvcc's contraction) and to what the reference's own kernel, built by nvcc, leaves on the same B200."""
+    from gfnerf_b200 import _lib
+    from oracle import oracle as orc
+    from oracle import ref_host as rh
+    rig = load_rig(rig_name)
+    if n_cams > rig["c2w"].shape[0]:                                    # more cameras than one shared-memory tile
+        rig = dict(rig)
+        reps = -(-n_cams // rig["c2w"].shape[0])
+        for k in ("c2w", "intri", "bounds"):
+            rig[k] = np.concatenate([rig[k]] * reps, 0)
+        rig["c2w"] = rig["c2w"].copy()
+        rig["c2w"][:, :3, 3] += np.random.RandomState(1).normal(0, 0.3, size=(rig["c2w"].shape[0], 3)).astype(np.float32)
+    w2c, intri, bound = _cameras(rig, n_cams)
+    blob = _many_nodes(rig, copies, seed=n_cams)
+    want = orc.mark_invisible_nodes(blob, intri, w2c, bound)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    nodes, tw, ti, tb = T(blob), T(w2c), T(intri), T(bound)
+    _lib.check(_lib.lib().gf_octree_mark_invisible(_lib.ptr(nodes), nodes.numel() // 128, _lib.ptr(tw), _lib.ptr(ti),
+                                                   _lib.ptr(tb), n_cams, _lib.cur_stream()), "gf_octree_mark_invisible")
+    got = nodes.cpu().numpy()
+    tidx0 = blob.view(np.int64).reshape(-1, 16)[:, 12]
+    marked = (got.view(np.int64).reshape(-1, 16)[:, 12] == -1) & (tidx0 != -1)
+    if n_cams:
+        assert 0 < marked.sum() < (tidx0 != -1).sum()
+    else:
+        assert (got.view(np.int64).reshape(-1, 16)[:, 12] == -1).all()
+    assert np.array_equal(got, want), (got != want).sum()
+    if rh.cuda_available() and n_cams:
+        ref = T(blob)
+        rh.cuda_mark_invisible_nodes(ref, ti, tw, tb)
+        assert torch.equal(ref, nodes), int((ref != nodes).sum())
+
+
+@pytest.mark.parametrize("n_blocks", [1, 7, 600])
+def test_set_block_idxs_kernel_equals_oracle_and_the_reference_kernel(n_blocks):
+    from gfnerf_b200 import _lib
+    from oracle import oracle as orc
+    from oracle import ref_host as rh
+    rig = load_rig("rig20")
+    blob = _many_nodes(rig, 4, seed=n_blocks)
+    rng = np.random.RandomState(n_blocks)
+    centers = rng.uniform(-4, 4, size=(n_blocks, 3)).astype(np.float32)
+    if n_blocks >= 7:
+        centers[5:7] = centers[1:3]                                    # exact ties: the first of equal minima wins
+    want = orc.set_block_idxs(blob, centers)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    nodes, tc = T(blob), T(centers)
+    _lib.check(_lib.lib().gf_octree_set_block_idxs(_lib.ptr(nodes), nodes.numel() // 128, _lib.ptr(tc), n_blocks,
+                                                   _lib.cur_stream()), "gf_octree_set_block_idxs")
+    got = nodes.cpu().numpy()
+    idx = got.view(np.int64).reshape(-1, 16)[:, 13]
+    assert idx.min() >= 0 and idx.max() < n_blocks and (n_blocks < 7 or not np.isin(idx, (5, 6)).any())
+    assert np.array_equal(got, want), (got != want).sum()
+    if rh.cuda_available():
+        ref = T(blob)
+        rh.cuda_set_block_idxs(ref, tc)
+        assert torch.equal(ref, nodes), int((ref != nodes).sum())
+    # nothing closer than 1e9: -1, like the reference's initial value
+    far = T(np.full((2, 3), 3e9, np.float32))
+    _lib.check(_lib.lib().gf_octree_set_block_idxs(_lib.ptr(nodes), nodes.numel() // 128, _lib.ptr(far), 2,
+                                                   _lib.cur_stream()), "gf_octree_set_block_idxs")
+    assert (nodes.cpu().numpy().view(np.int64).reshape(-1, 16)[:, 13] == -1).all()
+
+
+def test_sampler_mark_invisible_nodes_and_update_block_idxs():
+    """PersSamplerCore.MarkInvisibleNodes / UpdateBlockIdxs (the methods the milestones and the focal stage call) leave
+    the blobs the oracle leaves; UpdateBlockIdxs compacts afterwards like the reference (:767-798)."""
+    from oracle import oracle as orc
+    rig = load_rig("rig8")
+    s = make_sampler(rig, mode=1)
+    keep = 5                                                            # a sampler that only knows five cameras
+    s.w2c_, s.intri_, s.bound_ = s.w2c_[:keep].contiguous(), s.intri_[:keep].contiguous(), s.bound_[:keep].contiguous()
+    before = s.tree_nodes_gpu_.cpu().numpy().copy()
+    s.MarkInvisibleNodes()
+    want = orc.mark_invisible_nodes(before, s.intri_.cpu().numpy(), s.w2c_.cpu().numpy(), s.bound_.cpu().numpy())
+    assert np.array_equal(s.tree_nodes_gpu_.cpu().numpy(), want) and not np.array_equal(want, before)
+    centers = np.array([[-2.0, -2.0, 0.0], [2.0, 2.0, 0.0], [2.0, -2.0, 0.0]], np.float32)
+    marked = orc.set_block_idxs(want, centers)
+    b = make_sampler(rig, mode=1)                                       # the same through the host schedule
+    b.tree_nodes_gpu_ = torch.from_numpy(marked).cuda()
+    b.ProcOctreeHost(True, False, False)
+    s.UpdateBlockIdxs(torch.from_numpy(centers))
+    assert torch.equal(s.tree_nodes_gpu_, b.tree_nodes_gpu_)
+    assert set(s.get_tree_nodes_block_idx_()) <= {0, 1, 2}

@@ -224,3 +224,46 @@ def test_eval_mode_block_routing():
     rb_eval.steps, rb_eval.rel_camera_indices = None, None
     out = model.get_outputs(rb_eval)
     assert torch.isfinite(out["rgb"]).all()
+
+
+def test_engine_from_model_and_back():
+    """`GFNeRFEngine.from_model / load_model / store_model`: the bridge between the operator-API modules (whose state
+    dict is the reference's checkpoint layout) and the fused engine.  Same parameters -> same render; a training step
+    of the engine goes back into the modules bit for bit."""
+    from gfnerf_b200.engine import GFNeRFEngine
+    rig = load_rig("rig8")
+    eng, model = build(rig, seed=3)
+    f = model.field
+    f.base_encoding_init.hash_3d.bias_pool_.uniform_(0, 0.1)             # a checkpoint of the reference may carry one
+    eng2 = GFNeRFEngine.from_model(model, seed=99)                     # another seed: everything must come from the model
+    assert torch.equal(eng2.mlp, eng.mlp) and torch.equal(eng2.emb, eng.emb)
+    assert torch.equal(eng2.enc.feat_pool_, eng.enc.feat_pool_) and torch.equal(eng2.enc.prim_pool_, eng.enc.prim_pool_)
+    assert torch.equal(eng2.enc.bias_pool_, f.base_encoding_init.hash_3d.bias_pool_)
+    R = 256
+    rb, o, d, cam = bundle(rig, R, seed=11)
+    model.eval()
+    res = model.get_outputs(rb)
+    out = eng2.render(o, d, cam)
+    assert torch.allclose(res["rgb"], out.rgb, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(res["depth"][:, 0], out.depth, rtol=1e-4, atol=1e-5)
+    # one training step in the engine, then back into the modules
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    before = eng2.mlp.clone()
+    eng2.train_step(o, d, target, cam, update_octree=False)
+    eng2.flush()
+    assert not torch.equal(eng2.mlp, before) and eng2.opt_mlp.t == 1
+    eng2.store_model(model)
+    got = torch.cat([f.base_network.flat_params(), f.mlp_head.flat_params()]).detach()
+    assert torch.equal(got, eng2.mlp)
+    assert torch.equal(f.base_encoding_init.hash_3d.feat_pool_.detach(), eng2.enc.feat_pool_)
+    assert torch.equal(f.embedding_appearance.embedding.weight.detach(), eng2.emb)
+    res2 = model.get_outputs(rb)
+    out2 = eng2.render(o, d, cam)
+    assert torch.allclose(res2["rgb"], out2.rgb, rtol=1e-4, atol=1e-5) and not torch.allclose(res2["rgb"], res["rgb"])
+    # load_model again: the optimizer restarts
+    eng2.load_model(model)
+    assert eng2.opt_mlp.t == 0 and not eng2.opt_mlp.m.any()
+    # mismatches are refused, not papered over
+    _, other = build(rig, log2T=13)
+    with pytest.raises(ValueError):
+        eng2.load_model(other)

@@ -193,50 +193,53 @@ def test_live_sampler_2000_rays(rig, flavour):
         assert np.abs(a["world_pts"][m] - b["world_pts"][m]).max() <= 1e-4 * np.abs(b["world_pts"][m]).max()
 
 
-@live
-def test_live_mark_invisible_nodes_is_the_reference_kernel(rig):
-    """PersSamplerCore.invisible_nodes (the torch ops MarkInvisibleNodes runs at milestones) against the reference's
-    MarkInvisibleNodesKernel / CheckVisible (PersSampler_cuda.cu:680-723) on the rig's tree, with a camera subset so
-    that a good part of the nodes really is out of sight."""
-    import torch
-    from gfnerf_b200.perssampler import PersSamplerCore
-    c2w = rig["c2w"][:6]
+def _camera_subset(rig, n=6):
+    c2w = rig["c2w"][:n]
     m = np.tile(np.eye(4, dtype=np.float32)[None], (c2w.shape[0], 1, 1))
     m[:, :3, :] = c2w
     w2c = np.ascontiguousarray(np.linalg.inv(m)[:, :3, :].astype(np.float32))
-    intri, bound = np.ascontiguousarray(rig["intri"][:6]), np.ascontiguousarray(rig["bounds"][:6])
-    nodes_ref = rig["tree_nodes"].copy()
-    tidx0 = nodes_ref.view(np.int64).reshape(-1, 16)[:, 12].copy()
-    rh.mark_invisible_nodes(nodes_ref, intri, w2c, bound)
-    ref_invisible = (nodes_ref.view(np.int64).reshape(-1, 16)[:, 12] == -1) & (tidx0 != -1)
-    T = torch.from_numpy
-    mine = PersSamplerCore.invisible_nodes(T(rig["tree_nodes"].copy()).view(-1, 128), T(w2c), T(intri), T(bound)).numpy()
-    mine_marks = mine & (tidx0 != -1)
-    assert 0 < ref_invisible.sum() < (tidx0 != -1).sum()
-    # borderline nodes (a frustum edge within fp rounding of the node's bounding sphere) may fall either way
-    assert (mine_marks != ref_invisible).sum() <= 2, ((mine_marks != ref_invisible).sum(), ref_invisible.sum())
-    # the whole method on host tensors: the node blob it leaves is the blob the reference kernel leaves
-    core = PersSamplerCore.__new__(PersSamplerCore)
-    core.tree_nodes_gpu_ = T(rig["tree_nodes"].copy())
-    core.w2c_, core.intri_, core.bound_ = T(w2c), T(intri), T(bound)
-    core.MarkInvisibleNodes()
-    assert (core.tree_nodes_gpu_.numpy() != nodes_ref).sum() <= 2 * 8
+    return w2c, np.ascontiguousarray(rig["intri"][:n]), np.ascontiguousarray(rig["bounds"][:n])
+
+
+@live
+def test_live_mark_invisible_nodes_is_the_reference_kernel(rig):
+    """The oracle's MarkInvisibleNodes (the checker of gf_octree_mark_invisible, tests/test_octree_device_gpu.py) against
+    the reference's MarkInvisibleNodesKernel / CheckVisible (PersSampler_cuda.cu:680-723) compiled for the host, on the
+    rig's tree with a camera subset so that a good part of the nodes really is out of sight.  The oracle spells out
+    nvcc's contraction of the reference's expressions (the GPU test holds the kernel to the nvcc-built reference
+    kernel bit for bit); g++ contracts them its own way, so a node whose bounding sphere touches a frustum edge within
+    fp rounding may fall either way here."""
+    w2c, intri, bound = _camera_subset(rig)
+    tidx0 = rig["tree_nodes"].view(np.int64).reshape(-1, 16)[:, 12].copy()
+    mine = orc.mark_invisible_nodes(rig["tree_nodes"], intri, w2c, bound)
+    n_marked = ((mine.view(np.int64).reshape(-1, 16)[:, 12] == -1) & (tidx0 != -1)).sum()
+    assert 0 < n_marked < (tidx0 != -1).sum()
+    for flavour in ("off", "fma"):
+        nodes_ref = rig["tree_nodes"].copy()
+        rh.mark_invisible_nodes(nodes_ref, intri, w2c, bound, flavour=flavour)
+        # only trans_idx may change, and on at most two borderline nodes differently
+        assert (mine != nodes_ref).sum() <= 2 * 8, (flavour, (mine != nodes_ref).sum())
+    # no camera at all: every node loses its transform (the reference's count stays 0)
+    none = orc.mark_invisible_nodes(rig["tree_nodes"], intri[:0], w2c[:0], bound[:0])
+    assert (none.view(np.int64).reshape(-1, 16)[:, 12] == -1).all()
 
 
 @live
 def test_live_nearest_block_is_the_reference_kernel(rig):
-    """PersSamplerCore.nearest_block (what UpdateBlockIdxs writes into the nodes) against SetBlockIdxsNearestKernel
+    """The oracle's SetBlockIdxsNearest (the checker of gf_octree_set_block_idxs) against SetBlockIdxsNearestKernel
     (PersSampler_cuda.cu:746-766), incl. exact ties (duplicated centres: the first wins, strict `<`)."""
-    import torch
-    from gfnerf_b200.perssampler import PersSamplerCore
     centers = np.random.RandomState(0).uniform(-4, 4, size=(5, 3)).astype(np.float32)
     centers = np.concatenate([centers, centers[1:3]], 0)                      # blocks 5, 6 duplicate 1, 2
-    nodes_ref = rig["tree_nodes"].copy()
-    rh.set_block_idxs(nodes_ref, centers)
-    want = nodes_ref.view(np.int64).reshape(-1, 16)[:, 13]
-    got = PersSamplerCore.nearest_block(torch.from_numpy(rig["tree_nodes"].copy()).view(-1, 128),
-                                        torch.from_numpy(centers)).numpy()
-    assert want.max() <= 4 and (got != want).sum() <= 2, (got != want).sum()  # (fp32 norm rounding at near-ties)
+    got = orc.set_block_idxs(rig["tree_nodes"], centers).view(np.int64).reshape(-1, 16)[:, 13]
+    assert got.max() <= 4 and got.min() >= 0
+    for flavour in ("off", "fma"):
+        nodes_ref = rig["tree_nodes"].copy()
+        rh.set_block_idxs(nodes_ref, centers, flavour=flavour)
+        want = nodes_ref.view(np.int64).reshape(-1, 16)[:, 13]
+        assert (got != want).sum() <= 2, (flavour, (got != want).sum())       # (fp32 norm rounding at near-ties)
+    # nothing closer than 1e9: the index stays -1
+    far = orc.set_block_idxs(rig["tree_nodes"], np.full((2, 3), 3e9, np.float32))
+    assert (far.view(np.int64).reshape(-1, 16)[:, 13] == -1).all()
 
 
 def _history(rig, trial, rng):
