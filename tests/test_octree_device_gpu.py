@@ -245,3 +245,24 @@ def test_sampler_mark_invisible_nodes_and_update_block_idxs():
     s.UpdateBlockIdxs(torch.from_numpy(centers))
     assert torch.equal(s.tree_nodes_gpu_, b.tree_nodes_gpu_)
     assert set(s.get_tree_nodes_block_idx_()) <= {0, 1, 2}
+
+
+@pytest.mark.parametrize("name", ["rig8", "rig20"])
+def test_octree_mark_kernels_match_the_reference_fixture(name):
+    """gf_octree_mark_invisible + gf_octree_set_block_idxs against tests/golden/ref_marks.npz: the outputs of the
+    reference's own kernels (compiled for the host in the build container) on the same node blob, cameras, centres."""
+    import os
+    from gfnerf_b200 import _lib
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_marks.npz"))
+    tree = load_rig(name)["tree_nodes"]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    nodes, tw, ti, tb, tc = T(tree), T(fx[f"{name}_w2c"]), T(fx[f"{name}_intri"]), T(fx[f"{name}_bounds"]), T(fx[f"{name}_centers"])
+    L, n = _lib.lib(), tree.size // 128
+    _lib.check(L.gf_octree_mark_invisible(_lib.ptr(nodes), n, _lib.ptr(tw), _lib.ptr(ti), _lib.ptr(tb), tw.shape[0],
+                                          _lib.cur_stream()), "gf_octree_mark_invisible")
+    _lib.check(L.gf_octree_set_block_idxs(_lib.ptr(nodes), n, _lib.ptr(tc), tc.shape[0], _lib.cur_stream()),
+               "gf_octree_set_block_idxs")
+    blob, before = nodes.cpu().numpy().view(np.int64).reshape(-1, 16), tree.view(np.int64).reshape(-1, 16)
+    assert np.array_equal(blob[:, 12], fx[f"{name}_trans_idx"]) and np.array_equal(blob[:, 13], fx[f"{name}_block_idx"])
+    keep = [c for c in range(16) if c not in (12, 13)]
+    assert np.array_equal(blob[:, keep], before[:, keep])

@@ -193,6 +193,22 @@ def test_live_sampler_2000_rays(rig, flavour):
         assert np.abs(a["world_pts"][m] - b["world_pts"][m]).max() <= 1e-4 * np.abs(b["world_pts"][m]).max()
 
 
+@pytest.mark.parametrize("name", ["rig8", "rig20"])
+def test_octree_marks_match_the_reference_fixture(name):
+    """orc_mark_invisible_nodes / orc_set_block_idxs against the reference's own MarkInvisibleNodesKernel /
+    SetBlockIdxsNearestKernel outputs stored in tests/golden/ref_marks.npz (tests/golden/make_golden_marks.py): the
+    per-node trans_idx and block_idx are identical, and nothing else in the 128-byte blobs moves."""
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_marks.npz"))
+    tree = load_rig(name)["tree_nodes"]
+    nodes = orc.mark_invisible_nodes(tree, fx[f"{name}_intri"], fx[f"{name}_w2c"], fx[f"{name}_bounds"])
+    nodes = orc.set_block_idxs(nodes, fx[f"{name}_centers"])
+    blob, before = nodes.view(np.int64).reshape(-1, 16), tree.view(np.int64).reshape(-1, 16)
+    assert np.array_equal(blob[:, 12], fx[f"{name}_trans_idx"]) and np.array_equal(blob[:, 13], fx[f"{name}_block_idx"])
+    keep = [c for c in range(16) if c not in (12, 13)]
+    assert np.array_equal(blob[:, keep], before[:, keep])
+    assert not np.isin(blob[:, 13], (5, 6)).any()                             # ties: the first of equal minima
+
+
 def _camera_subset(rig, n=6):
     c2w = rig["c2w"][:n]
     m = np.tile(np.eye(4, dtype=np.float32)[None], (c2w.shape[0], 1, 1))
