@@ -247,6 +247,83 @@ class GFNeRFEngine:
                 f.embedding_appearance.embedding.weight.copy_(self.emb)
         assert o == self.mlp.numel()
 
+    # ---- resume ---------------------------------------------------------------------------------------------------------
+    def checkpoint(self) -> dict:
+        """Everything a resumed run of the fused engine needs, as host tensors / scalars (`torch.save`-able): parameters,
+        Adam moments and step counts, the octree blobs with their vote statistics, the march schedule.  (The reference
+        keeps model, optimizer and scheduler state in the trainer's checkpoint, nerfstudio/engine/trainer.py:455-489, and
+        drops the vote statistics: `PersSampler::LoadStates` restarts them at 1000, PersSampler.cpp:1010-1013.)  Data
+        parallel: call on every rank (the owners' table rows are collected first); the result is the same everywhere."""
+        self.flush()
+        self.sync_master_params()
+        cpu = lambda t: None if t is None else t.detach().to("cpu", copy=True)
+
+        def adam(opt):
+            # (the moments beyond n_active belong to table rows no level can reach: they stay zero, `_Adam`)
+            return None if opt is None else {"m": cpu(opt.m.view(-1)[:opt.n_active]), "v": cpu(opt.v.view(-1)[:opt.n_active]),
+                                             "t": opt.t, "n_active": opt.n_active}
+
+        s = self.sampler
+        s.flush_stats()
+        out = {"version": 1, "hidden": self.hidden, "step_count": self.step_count, "stage": self.stage,
+               "table": [cpu(t) for t in self.enc.States()], "mlp": cpu(self.mlp), "emb": cpu(self.emb),
+               "adam": {"table": adam(self.opt_table), "mlp": adam(self.opt_mlp), "emb": adam(self.opt_emb)},
+               "sampler": {"states": [cpu(t) for t in s.States()], "weight_stats": cpu(s.tree_weight_stats_),
+                           "alpha_stats": cpu(s.tree_alpha_stats_), "ray_march_fineness": s.ray_march_fineness_,
+                           "sampled_oct_per_ray": s.sampled_oct_per_ray_, "mode": s.mode_}}
+        if self.res is not None:
+            out["res_table"] = [cpu(t) for t in self.res.States()]
+            out["adam"]["res"] = adam(self.opt_res)
+            out["res_lr"] = self.opt_res.lr
+        return out
+
+    def restore(self, ckpt: dict) -> None:
+        """Inverse of `checkpoint()` on an engine built with the same table size, width and embedding shape."""
+        if ckpt.get("version") != 1 or int(ckpt["hidden"]) != self.hidden:
+            raise ValueError("gfnerf_b200: not a checkpoint of this engine (version / hidden width)")
+        if tuple(ckpt["table"][0].shape) != tuple(self.enc.feat_pool_.shape) or tuple(ckpt["mlp"].shape) != tuple(self.mlp.shape):
+            raise ValueError("gfnerf_b200: the checkpoint's table / MLP shapes are not this engine's")
+        if (ckpt["emb"] is None) != (self.emb is None) or (self.emb is not None and ckpt["emb"].shape != self.emb.shape):
+            raise ValueError("gfnerf_b200: the checkpoint's appearance embedding is not this engine's")
+        self.flush()
+        self._pre = None                       # samples taken ahead belong to the octree that is being replaced
+
+        def adam(opt, st):
+            n = int(st["n_active"])
+            if n != opt.n_active:
+                raise ValueError("gfnerf_b200: optimizer state of another table size")
+            opt.m.view(-1)[:n].copy_(st["m"].view(-1))
+            opt.v.view(-1)[:n].copy_(st["v"].view(-1))
+            opt.d_step.fill_(int(st["t"]))
+            opt.grad.zero_()
+
+        self.enc.LoadStates(ckpt["table"], 0)
+        self.n_volumes = self.enc.n_volumes_
+        self.mlp.copy_(ckpt["mlp"])
+        adam(self.opt_table, ckpt["adam"]["table"])
+        adam(self.opt_mlp, ckpt["adam"]["mlp"])
+        if self.emb is not None:
+            self.emb.copy_(ckpt["emb"])
+            adam(self.opt_emb, ckpt["adam"]["emb"])
+        self.enc.shadow(force=True)
+        s, ss = self.sampler, ckpt["sampler"]
+        s.LoadStates(ss["states"], 0)
+        s.tree_weight_stats_ = ss["weight_stats"].to(s.device).contiguous()
+        s.tree_alpha_stats_ = ss["alpha_stats"].to(s.device).contiguous()
+        s.ray_march_fineness_ = float(ss["ray_march_fineness"])
+        s.sampled_oct_per_ray_ = float(ss["sampled_oct_per_ray"])
+        s.UpdateMode(int(ss["mode"]))
+        s._octree_stale = True                 # the host mirror picks the statistics up when somebody asks for it
+        self.step_count = int(ckpt["step_count"])
+        if ckpt["stage"] == "block_stage":
+            self.start_block_stage(log2_table_size=int(np.log2(ckpt["res_table"][0].shape[0] // 16)),
+                                   lr=float(ckpt["res_lr"]))
+            self.res.LoadStates(ckpt["res_table"], 0)
+            self.res.shadow(force=True)
+            adam(self.opt_res, ckpt["adam"]["res"])
+        elif self.stage == "block_stage":
+            self.end_block_stage()
+
     # ---- per-stage device timing (bench / profiling only) -----------------------------------
     def enable_timers(self, on: bool = True):
         """Brackets every stage with CUDA events on the launching stream; read with `stage_times()`."""

@@ -382,3 +382,51 @@ def test_focal_stage_at_config4_size_matches_oracle():
     print("residual-table gradient (log2T = 21): max err / max", err, "rel L2", l2)
     assert err < 1e-2 and l2 < 1e-2
     assert not eng.opt_table.grad.any() and not eng.opt_mlp.grad.any()       # the global encoder and the MLPs are frozen
+
+
+def test_checkpoint_restore_resumes_the_run(tmp_path):
+    """`GFNeRFEngine.checkpoint() / restore()`: parameters, Adam moments and step counts, the octree with its vote
+    statistics and the march schedule survive a `torch.save` round trip into a freshly built engine, and the resumed run
+    continues like the original (up to the summation order of the fp32 gradient atomics)."""
+    from gfnerf_b200.persoctree import rig_rays
+    rig = load_rig("rig8")
+    R = 1024
+
+    def batch(it):
+        o, d, cam = rig_rays(rig["c2w"], rig["intri"], R, seed=300 + it)
+        t = np.random.RandomState(it).rand(R, 3).astype(np.float32)
+        return tuple(torch.from_numpy(a).cuda() for a in (o, d, t, cam))
+
+    a = make_engine(rig, log2T=14, mode=1, seed=1)          # eval-mode march noise: the sampling is deterministic
+    a.sampler.compact_freq_ = 3                             # the octree is compacted inside the run ...
+    a.sampler.tree_weight_stats_[::7] = -3                  # ... after a vote history that prunes part of it
+    for it in range(4):
+        a.train_step(*batch(it))
+    path = str(tmp_path / "engine.ckpt")
+    torch.save(a.checkpoint(), path)
+    b = make_engine(rig, log2T=14, mode=1, seed=77)         # another seed: everything must come from the file
+    b.sampler.compact_freq_ = 3
+    b.restore(torch.load(path, weights_only=False))
+    assert b.step_count == a.step_count == 4 and b.opt_table.t == a.opt_table.t == 4 and b.opt_mlp.t == 4
+    for x, y in ((a.enc.feat_pool_, b.enc.feat_pool_), (a.enc.prim_pool_, b.enc.prim_pool_), (a.mlp, b.mlp), (a.emb, b.emb),
+                 (a.opt_table.m, b.opt_table.m), (a.opt_table.v, b.opt_table.v), (a.opt_mlp.m, b.opt_mlp.m),
+                 (a.opt_emb.v, b.opt_emb.v), (a.enc._shadow, b.enc._shadow)):
+        assert torch.equal(x.detach(), y.detach())
+    sa, sb = a.sampler, b.sampler
+    assert sa.n_nodes == sb.n_nodes
+    print("octree nodes: fixture", rig["tree_nodes"].size // 128, "-> after 4 steps", sa.n_nodes)
+    for x, y in ((sa.tree_nodes_gpu_, sb.tree_nodes_gpu_), (sa.pers_trans_gpu_, sb.pers_trans_gpu_),
+                 (sa.tree_weight_stats_, sb.tree_weight_stats_), (sa.tree_alpha_stats_, sb.tree_alpha_stats_),
+                 (sa.tree_visit_cnt_, sb.tree_visit_cnt_)):
+        assert torch.equal(x, y)
+    assert sa.ray_march_fineness_ == sb.ray_march_fineness_ and sa.sub_div_milestones_ == sb.sub_div_milestones_
+    # both go on: same samples, same loss, the same parameters up to the order of the scatter's atomics
+    for it in range(4, 6):
+        oa, ob = a.train_step(*batch(it)), b.train_step(*batch(it))
+        assert int(oa.n_samples.item()) == int(ob.n_samples.item())
+        assert torch.allclose(oa.rgb, ob.rgb, rtol=1e-4, atol=1e-5)
+        assert abs(float(oa.loss) - float(ob.loss)) <= 1e-4 * abs(float(oa.loss))
+    assert torch.allclose(a.mlp, b.mlp, rtol=1e-3, atol=1e-5)
+    assert torch.equal(sa.tree_nodes_gpu_, sb.tree_nodes_gpu_)
+    with pytest.raises(ValueError):
+        make_engine(rig, log2T=13).restore(torch.load(path, weights_only=False))
