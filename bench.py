@@ -562,7 +562,14 @@ def main():
                                  "NCCL all-reduce of the fp32 table gradient + replicated Adam; octree votes: NCCL MAX")},
             "e2e": {"value": e2e_value, "unit": "rays/s",
                     "h2d_bytes_per_step": int(sum(a.numel() * a.element_size() for a in pinned[0])) * world,
-                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps,
+                    # the two legs of one run are different stretches of the same training run, and the hash scatter
+                    # slows down over the first ~50 steps of training (fewer fp16-underflowed products to skip,
+                    # DESIGN.md section 3): in a short run the later leg is slower for that reason, not because of
+                    # its copies (200-step runs: e2e = resident + 0.02 ms, profiles/r02at_bench_n1.json)
+                    "window": "training steps %d..%d of this run (the resident leg: %d..%d)" % (
+                        args.warmup + args.steps + 3, args.warmup + 2 * args.steps + 3, args.warmup,
+                        args.warmup + args.steps)},
             "e2e_operator_api": e2e_operator,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
