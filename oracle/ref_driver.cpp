@@ -51,6 +51,10 @@ const char* ref_build_flavour(void) {
 #endif
 }
 
+/* host threads a launch is spread over (1 = serial and deterministic: the default, what the tests use) */
+void ref_set_threads(int n) { gf_ref_threads = n < 1 ? 1 : n; }
+int ref_get_threads(void) { return gf_ref_threads; }
+
 /* Hash3DAnchoredFunction::forward, Hash3DAnchored_cuda.cu:160-196.  feat_pool_f16 = feat_pool.to(kFloat16) (:185),
  * out_f16 [n,32] zero-filled by the caller (:182); the caller widens it to fp32 (:195). */
 void ref_hash_forward(int n_points, int n_volumes, void* feat_pool_f16, int* prim_pool, int* feat_local_idx,

@@ -34,6 +34,14 @@ def lib(flavour="off"):
     return _libs[flavour]
 
 
+def set_threads(n, flavour="off"):
+    """Host threads a kernel launch of this flavour's library is spread over.  1 (the default) = one thread instance
+    after the other, deterministic -- what the tests use; os.cpu_count() = the reference's kernels on all host cores
+    (bench.py's CPU arm).  Outputs that do not depend on atomic ORDER (everything except the fp16 gradient sums and
+    where in the leaf pool a ray's list lands) are identical either way."""
+    lib(flavour).ref_set_threads(_int(int(n)))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(_vp)
 

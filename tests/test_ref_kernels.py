@@ -209,6 +209,46 @@ def test_octree_marks_match_the_reference_fixture(name):
     assert not np.isin(blob[:, 13], (5, 6)).any()                             # ties: the first of equal minima
 
 
+@live
+def test_live_threaded_launches_give_the_serial_results(rig):
+    """oracle/_ref with ref_set_threads(n > 1) -- what bench.py's CPU arm (kind "reference") runs: the thread instances
+    of a launch spread over host threads, the shim's atomics real atomics.  Everything that does not depend on the
+    ORDER of atomics is identical to the serial emulation: samples, anchors, ranges, hash encodings, vote statistics;
+    the fp16 gradient sums agree like two runs of the reference on a GPU do."""
+    from gfnerf_b200.persoctree import rig_rays
+    R = 192
+    o, d, _ = rig_rays(rig["c2w"], rig["intri"], R, seed=31)
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    noise = np.random.RandomState(2).uniform(0.5, 1.5, S + R + 10).astype(np.float32)
+    feat, prim, bias, _, _ = hash_inputs(8, rig["pers_trans"].size // 576, 12, seed=4)
+    out = {}
+    try:
+        for n in (1, 5):
+            rh.set_threads(n, "fma")
+            smp = rh.get_samples(o, d, noise, rig["tree_nodes"], rig["pers_trans"], orc.search_order(), flavour="fma")
+            m = smp["counts"][:, None] > np.arange(S)[None]
+            pts = ((smp["warp_pts"][m] + 1.5) / 3).astype(np.float32)
+            anc = np.ascontiguousarray(smp["anchors"][m][:, 0])
+            enc = rh.hash_forward(feat, prim, bias, pts, anc, "fma")
+            g = (np.random.RandomState(3).normal(size=(pts.shape[0], 32)) * 1e-3).astype(np.float32)
+            gt = rh.hash_backward(feat.shape[0] // 16, prim, bias, pts, anc, g, "fma")
+            nodes, ws, as_ = rig["tree_nodes"].copy(), np.full(rig["tree_nodes"].size // 128, 3, np.int64), \
+                np.full(rig["tree_nodes"].size // 128, 3, np.int64)
+            vc = np.zeros_like(ws)
+            w = np.random.RandomState(4).uniform(0, 0.02, size=(R, S)).astype(np.float32)
+            rh.update_oct_nodes(smp["pts_idx_start_end"], smp["anchors"][..., 1].reshape(-1), w.reshape(-1),
+                                (w * 2).reshape(-1), nodes, ws, as_, vc, flavour="fma")
+            out[n] = (smp, enc, gt, nodes, ws, as_, vc)
+    finally:
+        rh.set_threads(1, "fma")
+    a, b = out[1], out[5]
+    for k in ("counts", "pts_idx_start_end", "anchors", "ts", "dists", "warp_pts", "world_pts", "first_oct_dis", "n_oct"):
+        assert np.array_equal(a[0][k], b[0][k]), k
+    assert np.array_equal(a[1], b[1])
+    assert all(np.array_equal(x, y) for x, y in zip(a[3:], b[3:]))
+    assert np.linalg.norm(a[2] - b[2]) <= 2e-2 * np.linalg.norm(a[2])         # fp16 sums in another order
+
+
 def _camera_subset(rig, n=6):
     c2w = rig["c2w"][:n]
     m = np.tile(np.eye(4, dtype=np.float32)[None], (c2w.shape[0], 1, 1))
