@@ -685,6 +685,12 @@ def main():
                             "warp instructions per step of eight rays, 0.16 GB DRAM per launch), not HBM-bound; in the "
                             "step it runs a batch ahead on a side stream. Largest memory-bound kernels: see kernels[] "
                             "(hash_bwd: LSU data pipe / L2 atomics; hash_fwd: L1->L2 request path)")
+    if top["kernel"] == "hash_bwd":
+        roofline["note"] = ("effective bandwidth on ALGORITHMIC bytes (660 B per sample); the 17.8 MB of reachable table "
+                            "rows are L2-resident at log2T = 19, so DRAM moves `traffic` bytes per launch (the gradient "
+                            "rows in, the touched table lines once) and what bounds the kernel is the LSU data pipe and "
+                            "the L2 atomic unit (ncu, steady state: l1tex data-pipe wavefronts 88.7 %, 262 M red sector "
+                            "requests per launch, L2 79 %; DESIGN.md section 3)")
     if rank == 0 and args.breakdown:
         for k in kernels:
             print(k, file=sys.stderr)
