@@ -36,6 +36,15 @@ def test_version_and_error_string_without_a_gpu():
     # argument validation happens before any CUDA call
     rc = L.gf_hash_forward(-1, None, 1, 16, None, None, None, None, None, None, 0, None, None, None)
     assert rc == -1 and b"gf_hash_forward" in L.gf_last_error()
+    # the octree maintenance kernels: null / empty blob, missing camera arrays, misaligned blob
+    assert L.gf_octree_mark_invisible(None, 0, None, None, None, 0, None) == -1
+    assert b"gf_octree_mark_invisible" in L.gf_last_error()
+    assert L.gf_octree_mark_invisible(ctypes.c_void_p(4096), 3, None, None, None, 2, None) == -1
+    assert b"camera" in L.gf_last_error()
+    assert L.gf_octree_mark_invisible(ctypes.c_void_p(4100), 3, None, None, None, 0, None) == -1
+    assert b"aligned" in L.gf_last_error()
+    assert L.gf_octree_set_block_idxs(ctypes.c_void_p(4096), 3, None, 5, None) == -1
+    assert b"gf_octree_set_block_idxs" in L.gf_last_error()
 
 
 def test_library_is_sm100a_only():
